@@ -1,0 +1,90 @@
+"""The CPU oracle against the goldens produced by the reference's own code (tools/make_goldens.py)
+and against the reference's pure-function known answers.  No GPU."""
+import bz2
+import hashlib
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, GOLDEN_CASES, golden_case
+from oracle import lossycomp_oracle as O
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_compress_stages_bit_exact(name, model2):
+    g = golden_case(name)
+    x, thr = g["x"], float(g["abs_err"])
+    blob, parts = O.compress(x, thr, model2, return_parts=True)
+    assert parts["mean"] == g["mean"] and parts["std"] == g["std"]
+    assert parts["mean"].dtype == np.float32
+    np.testing.assert_array_equal(parts["latent"], g["latent"])
+    np.testing.assert_array_equal(parts["recon_std"], g["recon_std"])
+    np.testing.assert_array_equal(parts["dq"], g["dq"])
+    np.testing.assert_array_equal(parts["dm"], g["dm"])
+    slots = pickle.loads(blob)
+    assert [type(s).__name__ for s in slots] == list(g["slot_types"])
+    assert hashlib.sha256(slots[6]).hexdigest() == str(g["comp_error_sha"])
+    assert hashlib.sha256(slots[7]).hexdigest() == str(g["comp_mask_sha"])
+    assert tuple(slots[1]) == tuple(g["latent_shape"]) and tuple(slots[2]) == tuple(g["array_shape"])
+    assert tuple(slots[3]) == tuple(g["error_shape"]) and slots[8] == float(g["thr2"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_decompress_bit_exact_and_violation_set(name, model2):
+    g = golden_case(name)
+    x, thr = g["x"], float(g["abs_err"])
+    blob = O.compress(x, thr, model2)
+    xhat = O.decompress(blob, model2)
+    assert xhat.dtype == np.float32 and xhat.shape == x.shape[:3] + (1,)
+    np.testing.assert_array_equal(xhat, g["xhat"])
+    viol = int((np.abs(x[..., 0].astype(np.float64) - xhat[..., 0].astype(np.float64)) > thr).sum())
+    assert viol == int(g["violations"])   # the reference itself exceeds the bound by <= 1/2 ulp
+
+
+def test_chunk_known_answers():
+    with open(os.path.join(GOLDEN, "kats.pkl"), "rb") as fh:
+        kats = pickle.load(fh)
+    for shp_s, (n, firsts) in kats["chunk_facts"].items():
+        shp = eval(shp_s)
+        a = np.arange(np.prod(shp), dtype=np.float32).reshape(shp)
+        c = O.chunk_data(a)
+        assert c.shape[0] == n
+        assert [float(c[i, 0, 0, 0, 0]) for i in range(len(firsts))] == firsts
+        assert np.all(O.merge_data(c, shp) == a)
+    # notebooks/Chunking_data.ipynb cells 4 and 8
+    assert O.chunk_grid((16, 720, 720)) == (1, 15, 15) and O.chunk_grid((32, 721, 1440)) == (2, 16, 30)
+
+
+def test_chunk_asserts_small_input():
+    with pytest.raises(AssertionError):
+        O.chunk_data(np.zeros((15, 48, 48, 2), np.float32))
+
+
+def test_huffman_known_answers():
+    with open(os.path.join(GOLDEN, "kats.pkl"), "rb") as fh:
+        kats = pickle.load(fh)
+    for s, (bits, table) in kats["huffman"].items():
+        got_bits, got_table = O.huffman_code(s)
+        assert got_bits == bits and got_table == table
+        if len(table) > 1:
+            assert "".join(O.huffman_decode(bits, table)) == s
+    # SURVEY.md §8c KATs
+    assert O.huffman_code("0010-1002-20001-10") == ["00100111100011011111000010111100",
+                                                    {"2": "110", "-": "111", "1": "10", "0": "0"}]
+    assert O.huffman_code("aaaaaaaa") == ["", {"a": ""}]
+
+
+def test_quantiser_edges():
+    """half-to-even rounding and the float32 threshold compare (compress.py:120-135)."""
+    thr = 0.1
+    t32 = np.float32(thr)
+    e = np.array([t32, np.nextafter(t32, np.float32(1)), -t32, -np.nextafter(t32, np.float32(1)),
+                  np.float32(0.3), np.float32(0.5), np.float32(-0.7)], np.float32)
+    x = np.zeros((1, 1, e.size, 2), np.float32)
+    x[0, 0, :, 0] = e
+    mask, q, _ = O.residual_codes(x, np.zeros((1, 1, e.size, 1), np.float32), np.float32(0), np.float32(1), thr)
+    assert mask.reshape(-1).tolist() == [0, 1, 0, 2, 1, 1, 2]
+    ref = np.round(np.abs(e[[1, 3, 4, 5, 6]]) / np.float32(0.2)).astype(np.int32)
+    assert q.tolist() == ref.tolist()
