@@ -1,0 +1,171 @@
+/* lossycomp_b200.h -- C-ABI of the B200-native lossycomp codec hot path.
+ *
+ * The reference (SilkeDH/lossy-ml) is pure Python with no FFI of its own; its boundary for
+ * this path is the two callables lossycomp/compress.py:21 `compress(array, err_threshold)` and
+ * lossycomp/decompress.py:21 `decompress(blob)`.  Each entry point below replaces the span of
+ * reference Python named in its comment; lossy-ml_b200/lossycomp/{compress,decompress}.py call
+ * them through ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative LC_E* code otherwise; lc_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are host pointers;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises unless stated ("sync");
+ *   - no hidden allocation after lc_create(): scratch comes from caller workspaces whose sizes
+ *     the *_workspace_bytes queries return;
+ *   - all kernels are deterministic (fixed reduction / accumulation order, no float atomics):
+ *     the decoder output is bit-identical for any batch split, stream, GPU count or run, which
+ *     is what makes the error bound hold across compress/decompress.
+ */
+#ifndef LOSSYCOMP_B200_H
+#define LOSSYCOMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_OK 0
+#define LC_EINVAL (-1)
+#define LC_ECUDA (-2)
+#define LC_ENOMEM (-3)
+#define LC_EUNSUPPORTED (-4)
+
+#define LC_CHUNK_T 16
+#define LC_CHUNK_H 48
+#define LC_CHUNK_W 48
+
+/* arithmetic used by the convolution kernels */
+#define LC_PREC_FP32 0 /* CUDA-core fp32 FMA direct convolution (reference-grade numerics) */
+#define LC_PREC_BF16 1 /* tcgen05 implicit GEMM, bf16 operands, fp32 TMEM accumulators */
+#define LC_PREC_FP16 2 /* tcgen05 implicit GEMM, fp16 operands, fp32 TMEM accumulators */
+
+typedef struct lc_codec* lc_handle_t;
+
+/* one convolution layer of the autoencoder, Keras layouts (models.py:47-97) */
+typedef struct {
+  int32_t kind;     /* 0 = Conv3D, 1 = Conv3DTranspose */
+  int32_t k;        /* cubic kernel size */
+  int32_t stride;   /* 1 or 2 */
+  int32_t cin, cout;
+  int32_t relu;     /* fused ReLU on the output */
+  int32_t res_save; /* output is the skip input of the following ResBlock */
+  int32_t res_add;  /* add the saved skip tensor before the ReLU */
+  const float* h_kernel; /* Conv3D: (k,k,k,cin,cout); Conv3DTranspose: (k,k,k,cout,cin) */
+  const float* h_bias;   /* (cout) */
+} lc_layer_t;
+
+const char* lc_last_error(void);
+int lc_version(void);
+
+/* Replaces compress.py:41-57 / decompress.py:33-48 (parameter pickle, Keras graph build,
+ * load_weights): uploads and re-lays-out the weights once.  n_enc encoder layers followed by
+ * n_dec decoder layers, in execution order. */
+int lc_create(const lc_layer_t* layers, int n_enc, int n_dec, int in_channels, int precision,
+              int device, lc_handle_t* out);
+int lc_destroy(lc_handle_t h);
+int lc_latent_floats(lc_handle_t h); /* floats per chunk in the latent, e.g. 1*3*3*23 */
+
+/* chunk grid of dataLoader.py:449: ceil(T/16), ceil(H/48), ceil(W/48) */
+int lc_chunk_grid(int T, int H, int W, int grid[3]);
+
+/* dataLoader.py:437-481 chunk_data: (T,H,W,C) -> (N,16,48,48,C), N = product of lc_chunk_grid,
+ * chunk index lon-fastest, tail windows re-anchored at axis_len-size (overlap, no padding). */
+int lc_chunk_gather(const float* d_x, int T, int H, int W, int C, float* d_chunks, void* stream);
+/* dataLoader.py:484-532 merge_data: (N,16,48,48,C) -> (T,H,W,C); a tail chunk contributes only
+ * the voxels past its overlap with its predecessor. */
+int lc_chunk_merge(const float* d_chunks, int T, int H, int W, int C, float* d_out, void* stream);
+
+/* compress.py:64-65 -- statistics of channel 0 of d_x (T,H,W,C) float32.  Writes
+ * d_out[0..3] = { sum x, sum x^2, max|x|, n } as doubles (fixed-order two-level reduction).
+ * d_ws needs lc_stats_workspace_bytes(). */
+size_t lc_stats_workspace_bytes(void);
+int lc_stats(const float* d_x, int64_t n_vox, int C, double* d_out, void* d_ws, void* stream);
+
+/* compress.py:66-86 + dataLoader.py:437-481 + models.py:52-67 -- standardise channel 0,
+ * cut chunks [chunk_begin, chunk_begin+chunk_count) of the (T,H,W,C) field (tail windows are
+ * re-anchored at axis_len-size) and run the encoder.  d_latent receives
+ * (chunk_count, latent_floats) float32 in Keras order (t,h,w,f). */
+size_t lc_ae_workspace_bytes(lc_handle_t h, int max_chunks);
+int lc_encode(lc_handle_t h, const float* d_x, int T, int H, int W, int C, float mean, float std,
+              int chunk_begin, int chunk_count, float* d_latent, void* d_ws, size_t ws_bytes,
+              void* stream);
+
+/* compress.py:99-111 / decompress.py:66-72 + dataLoader.py:484-532 + models.py:70-85 -- run
+ * the decoder on chunks [chunk_begin, +chunk_count) and merge: each chunk writes only the
+ * voxels merge_data keeps from it into d_recon (T,H,W) float32 (standardised units).
+ * d_latent points at the latent of chunk `chunk_begin`. */
+int lc_decode(lc_handle_t h, const float* d_latent, int T, int H, int W, int chunk_begin,
+              int chunk_count, float* d_recon, void* d_ws, size_t ws_bytes, void* stream);
+
+/* compress.py:114-135 -- de-standardise, residual, 3-state mask, outlier compaction (C order)
+ * and quantisation, one pass over HBM:
+ *   r' = fl32(fl32(r*std)+mean); e = x0 - r'; m = |e|<=thr ? 0 : (e>0 ? 1 : 2)
+ *   q  = int32(rint(|e| / thr2)) for outliers, appended in C order.
+ * thr = fl32(abs_err), thr2 = fl32(2*abs_err) are passed by the host exactly as NumPy forms
+ * them.  d_count receives the number of outliers (uint64).  d_ws: lc_scan_workspace_bytes(). */
+size_t lc_scan_workspace_bytes(int64_t n);
+int lc_quantize(const float* d_x, int C, const float* d_recon, int64_t n_vox, float mean, float std,
+                float thr, float thr2, int8_t* d_mask, int32_t* d_q, unsigned long long* d_count,
+                void* d_ws, void* stream);
+
+/* compress.py:147-151,159-163 -- first difference [v0, v1-v0, ...] (int8 wraps like NumPy). */
+int lc_diff_i32(const int32_t* d_in, int64_t n, int32_t* d_out, void* stream);
+int lc_diff_i8(const int8_t* d_in, int64_t n, int8_t* d_out, void* stream);
+/* decompress.py:78,83 -- inclusive prefix sum undoing the first difference. */
+int lc_cumsum_i32(const int32_t* d_in, int64_t n, int32_t* d_out, void* d_ws, void* stream);
+int lc_cumsum_i8(const int8_t* d_in, int64_t n, int8_t* d_out, void* d_ws, void* stream);
+
+/* decompress.py:86-104 -- scatter de-quantised residuals by mask and add:
+ *   val = m>0 ? fl32(double(q_j)*thr2) : 0, negated where m==2 (j = rank of the outlier);
+ *   out = fl32(fl32(fl32(r*std)+mean) + val).   thr2 is the double stored in blob slot 8. */
+int lc_reconstruct(const float* d_recon, const int8_t* d_mask, const int32_t* d_q, int64_t n_vox,
+                   float mean, float std, double thr2, float* d_out, void* d_ws, void* stream);
+
+/* exhaustive |x - xhat| <= abs_err check in fp64.  d_x has C interleaved channels (channel 0
+ * is compared), d_xhat is (n_vox).  d_out[0] = violations (as double), d_out[1] = max |x-xhat|. */
+int lc_verify_bound(const float* d_x, int C, const float* d_xhat, int64_t n_vox, double abs_err,
+                    double* d_out, void* d_ws, void* stream);
+
+/* ---- entropy stage (north_star stage 4; host table builder mirrors huffman.py:20-45) ----
+ * Symbols are bytes (mask stream: packed trits; code stream: clipped first differences with
+ * escapes).  Histogram is warp-aggregated in shared memory; d_hist is 256 x uint32. */
+int lc_hist_u8(const uint8_t* d_sym, int64_t n, uint32_t* d_hist, void* stream);
+/* Map the int32 code stream (optionally first-differenced on the fly) to byte symbols:
+ * sym = v + bias if 0 <= v+bias < esc else esc; escaped values go to d_esc in order. */
+int lc_symbolize_i32(const int32_t* d_q, int64_t n, int diff, int bias, int esc, uint8_t* d_sym,
+                     int32_t* d_esc, unsigned long long* d_nesc, void* d_ws, void* stream);
+int lc_unsymbolize_i32(const uint8_t* d_sym, int64_t n, int diff, int bias, int esc,
+                       const int32_t* d_esc, int32_t* d_q, void* d_ws, void* stream);
+/* Pack five 3-state mask values per byte (m0 + 3 m1 + 9 m2 + 27 m3 + 81 m4), tail zero padded. */
+int lc_pack_trits(const int8_t* d_mask, int64_t n, uint8_t* d_sym, void* stream);
+int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* stream);
+
+/* Huffman bit packing from a host-built table: code[s] (right-aligned, MSB of the code is
+ * emitted first) and len[s] (0..32).  The stream is cut into segments of `seg` symbols; each
+ * segment starts at the bit offset d_seg_bits[i] (uint64, exclusive scan written by the call),
+ * bits are big-endian within bytes exactly like the '0101..' strings of huffman.py.
+ * d_total_bits receives the stream length in bits.  d_out must be zero-initialised and hold
+ * lc_huff_max_bytes(n) bytes. */
+size_t lc_huff_max_bytes(int64_t n);
+size_t lc_huff_workspace_bytes(int64_t n, int seg);
+int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d_code, const uint8_t* d_len,
+                   int seg, uint8_t* d_out, unsigned long long* d_seg_bits,
+                   unsigned long long* d_total_bits, void* d_ws, void* stream);
+/* Decode: d_lut is a 2^lut_bits table of (len << 8 | sym) for codes no longer than lut_bits;
+ * longer codes walk d_tree (node = {child0, child1}, leaves are ~sym). */
+int lc_huff_decode(const uint8_t* d_bits, int64_t n, int seg, const unsigned long long* d_seg_bits,
+                   const uint16_t* d_lut, int lut_bits, const int32_t* d_tree, uint8_t* d_sym,
+                   void* stream);
+
+/* synthetic ERA5-like field generated on the device for benchmarks:
+ * (T,H,W,2) float32 window starting at global time t0 of level `level`. */
+int lc_synth_field(float* d_x, int T, int H, int W, int t0, int level, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOSSYCOMP_B200_H */

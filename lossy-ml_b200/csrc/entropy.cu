@@ -1,0 +1,359 @@
+// Entropy stage: byte-symbol histogram, symbol mapping of the code / mask streams and Huffman
+// bit packing / unpacking from a host-built table (the host builder mirrors huffman.py:20-45).
+#include "scan.cuh"
+
+using namespace lcscan;
+
+namespace {
+
+// ---------------------------------------------------------------- histogram (warp-aggregated)
+__global__ void __launch_bounds__(256) hist_kernel(const uint8_t* __restrict__ sym, long long n,
+                                                   uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[8][256];   // one private histogram per warp: no inter-warp contention
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  uint32_t* mine = sh[threadIdx.x >> 5];
+  const long long nvec = n / 16;
+  const uint4* p = reinterpret_cast<const uint4*>(sym);
+  const bool vec = (reinterpret_cast<uintptr_t>(sym) & 15) == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    for (long long i = tid; i < nvec; i += stride) {
+      const uint4 v = __ldg(p + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t s = (w[k] >> (8 * b)) & 0xff;
+          // warp-aggregate: lanes holding the same symbol elect one leader that adds the count
+          const unsigned peers = __match_any_sync(__activemask(), s);
+          if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&mine[s], __popc(peers));
+        }
+      }
+    }
+    for (long long i = nvec * 16 + tid; i < n; i += stride) atomicAdd(&mine[sym[i]], 1u);
+  } else {
+    for (long long i = tid; i < n; i += stride) atomicAdd(&mine[sym[i]], 1u);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < 256; s += 256) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][s];
+    if (t) atomicAdd(&hist[s], t);
+  }
+}
+
+// ---------------------------------------------------------------- trits <-> bytes
+__global__ void pack_trits_kernel(const int8_t* __restrict__ m, long long n, uint8_t* __restrict__ out) {
+  const long long nb = (n + 4) / 5;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
+       b += (long long)gridDim.x * blockDim.x) {
+    const long long i = b * 5;
+    int v = 0, mul = 1;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int t = (i + k < n) ? (int)m[i + k] : 0;
+      v += t * mul;
+      mul *= 3;
+    }
+    out[b] = (uint8_t)v;
+  }
+}
+
+__global__ void unpack_trits_kernel(const uint8_t* __restrict__ in, long long n, int8_t* __restrict__ m) {
+  const long long nb = (n + 4) / 5;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
+       b += (long long)gridDim.x * blockDim.x) {
+    int v = in[b];
+    const long long i = b * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (i + k < n) m[i + k] = (int8_t)(v % 3);
+      v /= 3;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- int32 codes <-> byte symbols
+constexpr int kItems = 8;
+constexpr int kTile = kThreads * kItems;
+
+__global__ void __launch_bounds__(kThreads)
+symbolize_kernel(const int32_t* __restrict__ q, long long n, int diff, int bias, int esc,
+                 uint8_t* __restrict__ sym, int32_t* __restrict__ escv,
+                 unsigned long long* __restrict__ nesc, unsigned long long* ws) {
+  const int tile = take_ticket(ws);
+  const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
+  int v[kItems];
+  bool e[kItems];
+  int cnt = 0;
+  int prev = (diff && i0 > 0 && i0 - 1 < n) ? q[i0 - 1] : 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const int cur = (i0 + k < n) ? q[i0 + k] : 0;
+    v[k] = diff ? (cur - prev) : cur;
+    prev = cur;
+    const int s = v[k] + bias;
+    e[k] = (i0 + k < n) && (s < 0 || s >= esc);
+    cnt += e[k];
+    if (i0 + k < n) sym[i0 + k] = (uint8_t)(e[k] ? esc : s);
+  }
+  int total;
+  const int texcl = block_exclusive<int>(cnt, total);
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
+  long long o = (long long)base + texcl;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (e[k]) escv[o++] = v[k];
+  if ((long long)(tile + 1) * kTile >= n && threadIdx.x == 0) *nesc = base + (unsigned long long)total;
+}
+
+__global__ void __launch_bounds__(kThreads)
+unsymbolize_kernel(const uint8_t* __restrict__ sym, long long n, int bias, int esc,
+                   const int32_t* __restrict__ escv, int32_t* __restrict__ q, unsigned long long* ws) {
+  const int tile = take_ticket(ws);
+  const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
+  int s[kItems];
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    s[k] = (i0 + k < n) ? (int)sym[i0 + k] : 0;
+    cnt += (i0 + k < n) && (s[k] == esc);
+  }
+  int total;
+  const int texcl = block_exclusive<int>(cnt, total);
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
+  long long o = (long long)base + texcl;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (i0 + k < n) q[i0 + k] = (s[k] == esc) ? escv[o++] : (s[k] - bias);
+}
+
+// ---------------------------------------------------------------- Huffman pack
+// one tile == one segment of kSeg symbols; thread owns 16 consecutive symbols
+constexpr int kSegItems = 16;
+constexpr int kSeg = kThreads * kSegItems;   // 4096
+
+__global__ void __launch_bounds__(kThreads)
+huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t* __restrict__ code,
+                   const uint8_t* __restrict__ len, uint32_t* __restrict__ out,
+                   unsigned long long* __restrict__ seg_bits, unsigned long long* __restrict__ total_bits,
+                   unsigned long long* ws) {
+  __shared__ uint32_t s_code[256];
+  __shared__ uint8_t s_len[256];
+  s_code[threadIdx.x] = code[threadIdx.x];
+  s_len[threadIdx.x] = len[threadIdx.x];
+  const int tile = take_ticket(ws);   // contains a __syncthreads
+  const long long i0 = (long long)tile * kSeg + (long long)threadIdx.x * kSegItems;
+  uint8_t s[kSegItems];
+  if (i0 + kSegItems <= n && (reinterpret_cast<uintptr_t>(sym) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(sym + i0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < kSegItems; ++k) s[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kSegItems; ++k) s[k] = (i0 + k < n) ? sym[i0 + k] : 0;
+  }
+  int bits = 0;
+#pragma unroll
+  for (int k = 0; k < kSegItems; ++k) bits += (i0 + k < n) ? (int)s_len[s[k]] : 0;
+  int total;
+  const int texcl = block_exclusive<int>(bits, total);
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
+  if (threadIdx.x == 0) {
+    seg_bits[tile] = base;
+    if ((long long)(tile + 1) * kSeg >= n) *total_bits = base + (unsigned long long)total;
+  }
+  // emit: big-endian bit order within the byte stream == big-endian within 32-bit words that are
+  // byte-swapped on store.  Accumulate into a 64-bit window and flush 32 bits at a time.
+  unsigned long long pos = base + (unsigned long long)texcl;
+  unsigned long long word_idx = pos >> 5;
+  int fill = (int)(pos & 31);            // bits already used in the current word (by a neighbour)
+  unsigned long long acc = 0;            // top `fill + pending` bits valid, left-aligned at bit 63
+  int have = fill;
+#pragma unroll
+  for (int k = 0; k < kSegItems; ++k) {
+    if (i0 + k < n) {
+      const int l = s_len[s[k]];
+      if (l) {
+        acc |= (unsigned long long)s_code[s[k]] << (64 - have - l);
+        have += l;
+        if (have >= 32) {
+          const uint32_t w = (uint32_t)(acc >> 32);
+          atomicOr(&out[word_idx], __byte_perm(w, 0, 0x0123));
+          ++word_idx;
+          acc <<= 32;
+          have -= 32;
+        }
+      }
+    }
+  }
+  if (have > 0) {
+    const uint32_t w = (uint32_t)(acc >> 32);
+    if (w) atomicOr(&out[word_idx], __byte_perm(w, 0, 0x0123));
+  }
+}
+
+// ---------------------------------------------------------------- Huffman unpack
+__device__ __forceinline__ unsigned long long load_be64(const uint8_t* p, unsigned long long byte,
+                                                        unsigned long long nbytes) {
+  unsigned long long v = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const unsigned long long b = byte + k;
+    v = (v << 8) | (unsigned long long)(b < nbytes ? p[b] : 0);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(128)
+huff_decode_kernel(const uint8_t* __restrict__ bits, unsigned long long nbytes, long long n, int seg,
+                   const unsigned long long* __restrict__ seg_bits, const uint16_t* __restrict__ lut,
+                   int lut_bits, const int32_t* __restrict__ tree, uint8_t* __restrict__ sym) {
+  extern __shared__ uint16_t s_lut[];
+  for (int i = threadIdx.x; i < (1 << lut_bits); i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const long long nseg = (n + seg - 1) / seg;
+  const long long sg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sg >= nseg) return;
+  unsigned long long pos = seg_bits[sg];
+  const long long i0 = sg * seg;
+  const long long i1 = (i0 + seg < n) ? i0 + seg : n;
+  for (long long i = i0; i < i1; ++i) {
+    const unsigned long long win = load_be64(bits, pos >> 3, nbytes) << (pos & 7);   // >= 57 valid bits
+    const uint16_t e = s_lut[win >> (64 - lut_bits)];
+    int l = e >> 8;
+    int s = e & 0xff;
+    if (l == 0) {   // code longer than lut_bits (or the empty code of a one-symbol alphabet)
+      int node = 0;
+      l = 0;
+      if (tree[0] < 0 && tree[1] < 0 && tree[0] == tree[1]) {
+        s = ~tree[0];   // degenerate one-symbol table: zero-length code
+      } else {
+        while (true) {
+          const int bit = (int)((win >> (63 - l)) & 1);
+          ++l;
+          const int nx = tree[2 * node + bit];
+          if (nx < 0) { s = ~nx; break; }
+          node = nx;
+        }
+      }
+    }
+    sym[i] = (uint8_t)s;
+    pos += l;
+  }
+}
+
+inline unsigned grid_for(long long n, int per_block) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b > 148 * 32) b = 148 * 32;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+
+extern "C" int lc_hist_u8(const uint8_t* d_sym, int64_t n, uint32_t* d_hist, void* stream) {
+  LC_REQUIRE(d_hist, "null argument");
+  cudaStream_t s = as_stream(stream);
+  LC_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint32_t), s));
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_sym, "null argument");
+  hist_kernel<<<grid_for(n, 256 * 64), 256, 0, s>>>(d_sym, n, d_hist);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_pack_trits(const int8_t* d_mask, int64_t n, uint8_t* d_sym, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_mask && d_sym, "null argument");
+  pack_trits_kernel<<<grid_for((n + 4) / 5, 256), 256, 0, as_stream(stream)>>>(d_mask, n, d_sym);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_mask && d_sym, "null argument");
+  unpack_trits_kernel<<<grid_for((n + 4) / 5, 256), 256, 0, as_stream(stream)>>>(d_sym, n, d_mask);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_symbolize_i32(const int32_t* d_q, int64_t n, int diff, int bias, int esc, uint8_t* d_sym,
+                                int32_t* d_esc, unsigned long long* d_nesc, void* d_ws, void* stream) {
+  LC_REQUIRE(d_nesc && d_ws, "null argument");
+  cudaStream_t s = as_stream(stream);
+  LC_CUDA(cudaMemsetAsync(d_nesc, 0, sizeof(unsigned long long), s));
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_q && d_sym && d_esc, "null argument");
+  LC_REQUIRE(esc >= 1 && esc <= 255, "escape symbol out of range");
+  const long long nt = (n + kTile - 1) / kTile;
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  symbolize_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_q, n, diff, bias, esc, d_sym, d_esc, d_nesc,
+                                                     reinterpret_cast<unsigned long long*>(d_ws));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_unsymbolize_i32(const uint8_t* d_sym, int64_t n, int diff, int bias, int esc,
+                                  const int32_t* d_esc, int32_t* d_q, void* d_ws, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_q && d_sym && d_ws, "null argument");
+  cudaStream_t s = as_stream(stream);
+  const long long nt = (n + kTile - 1) / kTile;
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  unsymbolize_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, bias, esc, d_esc, d_q,
+                                                       reinterpret_cast<unsigned long long*>(d_ws));
+  LC_LAUNCH_CHECK();
+  if (diff) return lc_cumsum_i32(d_q, n, d_q, d_ws, stream);
+  return LC_OK;
+}
+
+extern "C" size_t lc_huff_max_bytes(int64_t n) { return (size_t)(n < 0 ? 0 : n) * 4 + 64; }
+
+extern "C" size_t lc_huff_workspace_bytes(int64_t n, int seg) {
+  (void)seg;
+  const long long nt = ((n < 1 ? 1 : n) + kSeg - 1) / kSeg;
+  return ws_bytes(nt);
+}
+
+extern "C" int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d_code, const uint8_t* d_len,
+                              int seg, uint8_t* d_out, unsigned long long* d_seg_bits,
+                              unsigned long long* d_total_bits, void* d_ws, void* stream) {
+  LC_REQUIRE(d_total_bits && d_ws, "null argument");
+  LC_REQUIRE(seg == kSeg, "segment length must be 4096 symbols");
+  cudaStream_t s = as_stream(stream);
+  LC_CUDA(cudaMemsetAsync(d_total_bits, 0, sizeof(unsigned long long), s));
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_sym && d_code && d_len && d_out && d_seg_bits, "null argument");
+  LC_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 3) == 0, "output must be 4-byte aligned");
+  const long long nt = (n + kSeg - 1) / kSeg;
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  huff_encode_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, d_code, d_len,
+                                                       reinterpret_cast<uint32_t*>(d_out), d_seg_bits,
+                                                       d_total_bits,
+                                                       reinterpret_cast<unsigned long long*>(d_ws));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_huff_decode(const uint8_t* d_bits, int64_t n, int seg, const unsigned long long* d_seg_bits,
+                              const uint16_t* d_lut, int lut_bits, const int32_t* d_tree, uint8_t* d_sym,
+                              void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_bits && d_seg_bits && d_lut && d_tree && d_sym, "null argument");
+  LC_REQUIRE(lut_bits >= 1 && lut_bits <= 14 && seg > 0, "bad decode table");
+  const long long nseg = (n + seg - 1) / seg;
+  // the caller guarantees the bit buffer is readable up to the last byte holding a code bit and
+  // zero padded to 8 more bytes; pass the conservative size bound
+  huff_decode_kernel<<<(unsigned)((nseg + 127) / 128), 128, (size_t)(1 << lut_bits) * 2,
+                       as_stream(stream)>>>(d_bits, ~0ull, n, seg, d_seg_bits, d_lut, lut_bits, d_tree,
+                                            d_sym);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}

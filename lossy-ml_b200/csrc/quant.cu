@@ -1,0 +1,250 @@
+// Residual / mask / quantise / compaction (compress.py:114-135) and its inverse
+// (decompress.py:75-104), plus first-difference and cumsum helpers.
+//
+// Bit-exactness with NumPy: every float op is an explicit round-to-nearest intrinsic so nvcc
+// cannot contract a*b+c into an FMA; the divide is IEEE (__fdiv_rn), the
+// rounding is half-to-even (__float2int_rn == np.round().astype(int32) for in-range values).
+#include "scan.cuh"
+
+using namespace lcscan;
+
+namespace {
+
+constexpr int kItems = 8;
+constexpr int kTile = kThreads * kItems;
+
+__device__ __forceinline__ void load8_strided(const float* __restrict__ x, int C, long long i0,
+                                              long long n, bool vec, float v[kItems]) {
+  if (vec && C == 2 && i0 + kItems <= n) {
+    const float4* p = reinterpret_cast<const float4*>(x + i0 * 2);
+#pragma unroll
+    for (int k = 0; k < kItems / 2; ++k) {
+      float4 a = __ldg(p + k);
+      v[2 * k] = a.x;
+      v[2 * k + 1] = a.z;
+    }
+  } else if (vec && C == 1 && i0 + kItems <= n) {
+    const float4* p = reinterpret_cast<const float4*>(x + i0);
+#pragma unroll
+    for (int k = 0; k < kItems / 4; ++k) {
+      float4 a = __ldg(p + k);
+      v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = a.z; v[4 * k + 3] = a.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) v[k] = (i0 + k < n) ? __ldg(x + (i0 + k) * C) : 0.f;
+  }
+}
+
+__device__ __forceinline__ int classify(float x0, float r, float mean, float stdv, float thr,
+                                        float thr2, int& q) {
+  const float rr = __fadd_rn(__fmul_rn(r, stdv), mean);   // compress.py:114
+  const float e = __fsub_rn(x0, rr);                      // compress.py:117
+  const float a = fabsf(e);
+  q = 0;
+  if (!(a > thr)) return 0;                               // compress.py:121 (|e| <= thr -> 0)
+  q = __float2int_rn(__fdiv_rn(a, thr2));                 // compress.py:135
+  return e > 0.f ? 1 : 2;                                 // compress.py:122-123
+}
+
+__global__ void __launch_bounds__(kThreads)
+quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ recon, long long n,
+                float mean, float stdv, float thr, float thr2, int8_t* __restrict__ mask,
+                int32_t* __restrict__ qout, unsigned long long* __restrict__ count,
+                unsigned long long* ws, bool vec_x, bool vec_r, bool vec_m) {
+  const int tile = take_ticket(ws);
+  const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
+  float xv[kItems], rv[kItems];
+  load8_strided(x, C, i0, n, vec_x, xv);
+  load8_strided(recon, 1, i0, n, vec_r, rv);
+  int q[kItems];
+  int m[kItems];
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    m[k] = (i0 + k < n) ? classify(xv[k], rv[k], mean, stdv, thr, thr2, q[k]) : 0;
+    cnt += (m[k] != 0);
+  }
+  if (i0 + kItems <= n && vec_m) {
+    unsigned long long pk = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) pk |= (unsigned long long)(m[k] & 0xff) << (8 * k);
+    *reinterpret_cast<unsigned long long*>(mask + i0) = pk;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+      if (i0 + k < n) mask[i0 + k] = (int8_t)m[k];
+  }
+  int total;
+  const int texcl = block_exclusive<int>(cnt, total);
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
+  long long o = (long long)base + texcl;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (m[k] != 0) qout[o++] = q[k];
+  if ((long long)(tile + 1) * kTile >= n && threadIdx.x == 0) *count = base + (unsigned long long)total;
+}
+
+__global__ void __launch_bounds__(kThreads)
+reconstruct_kernel(const float* __restrict__ recon, const int8_t* __restrict__ mask,
+                   const int32_t* __restrict__ q, long long n, float mean, float stdv, double thr2,
+                   float* __restrict__ out, unsigned long long* ws, bool vec_r, bool vec_m,
+                   bool vec_o) {
+  const int tile = take_ticket(ws);
+  const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
+  float rv[kItems];
+  load8_strided(recon, 1, i0, n, vec_r, rv);
+  int m[kItems];
+  if (i0 + kItems <= n && vec_m) {
+    const unsigned long long pk = *reinterpret_cast<const unsigned long long*>(mask + i0);
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) m[k] = (int)(int8_t)((pk >> (8 * k)) & 0xff);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) m[k] = (i0 + k < n) ? (int)mask[i0 + k] : 0;
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) cnt += (m[k] > 0);
+  int total;
+  const int texcl = block_exclusive<int>(cnt, total);
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
+  long long o = (long long)base + texcl;
+  float y[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    // decompress.py:86-95: val = float32(mask); val[val>0] = float64(q)*thr2 -> float32; negate where mask==2
+    float val = (float)m[k];
+    if (m[k] > 0) {
+      val = (float)((double)q[o++] * thr2);
+      if (m[k] == 2) val = -val;
+    }
+    const float rr = __fadd_rn(__fmul_rn(rv[k], stdv), mean);   // decompress.py:98
+    y[k] = __fadd_rn(rr, val);                                  // decompress.py:104
+  }
+  if (i0 + kItems <= n && vec_o) {
+    float4* po = reinterpret_cast<float4*>(out + i0);
+    po[0] = make_float4(y[0], y[1], y[2], y[3]);
+    po[1] = make_float4(y[4], y[5], y[6], y[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+      if (i0 + k < n) out[i0 + k] = y[k];
+  }
+}
+
+template <typename T>
+__global__ void diff_kernel(const T* __restrict__ in, long long n, T* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = (i == 0) ? in[0] : (T)(in[i] - in[i - 1]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cumsum_kernel(const T* __restrict__ in, long long n, T* __restrict__ out, unsigned long long* ws) {
+  const int tile = take_ticket(ws);
+  const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
+  long long v[kItems];
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    v[k] = (i0 + k < n) ? (long long)in[i0 + k] : 0;
+    s += v[k];
+  }
+  long long total;
+  const long long texcl = block_exclusive<long long>(s, total);
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
+  // 62-bit modular arithmetic: sign-extend
+  long long run = (long long)(base << 2) >> 2;
+  run += texcl;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    run += v[k];
+    if (i0 + k < n) out[i0 + k] = (T)run;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+inline long long tiles_for(long long n) { return (n + kTile - 1) / kTile; }
+
+}  // namespace
+
+extern "C" size_t lc_scan_workspace_bytes(int64_t n) { return ws_bytes(tiles_for(n < 1 ? 1 : n)); }
+
+extern "C" int lc_quantize(const float* d_x, int C, const float* d_recon, int64_t n_vox, float mean,
+                           float stdv, float thr, float thr2, int8_t* d_mask, int32_t* d_q,
+                           unsigned long long* d_count, void* d_ws, void* stream) {
+  LC_REQUIRE(d_x && d_recon && d_mask && d_q && d_count && d_ws, "null argument");
+  LC_REQUIRE(n_vox > 0 && C >= 1, "empty input");
+  cudaStream_t s = as_stream(stream);
+  const long long nt = tiles_for(n_vox);
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  quantize_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_x, C, d_recon, n_vox, mean, stdv, thr, thr2,
+                                                    d_mask, d_q, d_count,
+                                                    reinterpret_cast<unsigned long long*>(d_ws),
+                                                    aligned16(d_x), aligned16(d_recon), aligned8(d_mask));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_reconstruct(const float* d_recon, const int8_t* d_mask, const int32_t* d_q,
+                              int64_t n_vox, float mean, float stdv, double thr2, float* d_out,
+                              void* d_ws, void* stream) {
+  LC_REQUIRE(d_recon && d_mask && d_out && d_ws, "null argument");
+  LC_REQUIRE(n_vox > 0, "empty input");
+  cudaStream_t s = as_stream(stream);
+  const long long nt = tiles_for(n_vox);
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  reconstruct_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_recon, d_mask, d_q, n_vox, mean, stdv, thr2,
+                                                       d_out, reinterpret_cast<unsigned long long*>(d_ws),
+                                                       aligned16(d_recon), aligned8(d_mask),
+                                                       aligned16(d_out));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_diff_i32(const int32_t* d_in, int64_t n, int32_t* d_out, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_in && d_out && d_in != d_out, "bad argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  diff_kernel<int32_t><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_in, n, d_out);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_diff_i8(const int8_t* d_in, int64_t n, int8_t* d_out, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_in && d_out && d_in != d_out, "bad argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  diff_kernel<int8_t><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_in, n, d_out);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_cumsum_i32(const int32_t* d_in, int64_t n, int32_t* d_out, void* d_ws, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_in && d_out && d_ws, "null argument");
+  cudaStream_t s = as_stream(stream);
+  const long long nt = tiles_for(n);
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  cumsum_kernel<int32_t><<<(unsigned)nt, kThreads, 0, s>>>(d_in, n, d_out,
+                                                           reinterpret_cast<unsigned long long*>(d_ws));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_cumsum_i8(const int8_t* d_in, int64_t n, int8_t* d_out, void* d_ws, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_in && d_out && d_ws, "null argument");
+  cudaStream_t s = as_stream(stream);
+  const long long nt = tiles_for(n);
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  cumsum_kernel<int8_t><<<(unsigned)nt, kThreads, 0, s>>>(d_in, n, d_out,
+                                                          reinterpret_cast<unsigned long long*>(d_ws));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}

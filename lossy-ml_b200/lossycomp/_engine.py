@@ -1,0 +1,367 @@
+"""Host orchestration of the B200 codec: marshals buffers and launches the C-ABI kernels.
+
+PyTorch is used for device memory, streams and (in dist.py) torch.distributed only; all the
+arithmetic is in liblossycomp_b200.so.  The stage order follows the reference
+(compress.py:64-168, decompress.py:54-104).
+"""
+from __future__ import annotations
+
+import bz2
+import ctypes as C
+import json
+import math
+import os
+import struct
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _native as N
+from . import huffman as HF
+from .models import CHUNK, Model, load_model
+
+LATENT_MAGIC = b"LCL1"
+HUFF_MAGIC = b"LCH1"
+SEG = 4096                      # symbols per independently decodable Huffman segment
+ESC = 255                       # escape symbol of the code stream
+DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "128"))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One codec instance per (device, model, precision); replaces the per-call Keras build +
+    load_weights of compress.py:41-57 / decompress.py:33-48 by a one-time weight upload."""
+
+    _cache: Dict[tuple, "Engine"] = {}
+
+    @classmethod
+    def get(cls, model_path: Optional[str] = None, precision: Optional[str] = None,
+            device: Optional[int] = None) -> "Engine":
+        torch = N.require_cuda()
+        precision = precision or os.environ.get("LOSSYCOMP_PRECISION", "fp32")
+        device = torch.cuda.current_device() if device is None else device
+        key = (model_path or "default", precision, device)
+        if key not in cls._cache:
+            cls._cache[key] = Engine(load_model(model_path), precision, device)
+        return cls._cache[key]
+
+    def __init__(self, model: Model, precision: str = "fp32", device: int = 0):
+        self.torch = N.require_cuda()
+        self.lib = N.lib()
+        self.model = model
+        self.precision = precision
+        self.device = device
+        self.dev = self.torch.device("cuda", device)
+        layers = model.layers
+        arr = (N.LcLayer * len(layers))()
+        self._keep = []
+        for i, L in enumerate(layers):
+            k = np.ascontiguousarray(L.kernel, dtype=np.float32)
+            b = np.ascontiguousarray(L.bias, dtype=np.float32)
+            self._keep += [k, b]
+            arr[i] = N.LcLayer(0 if L.kind == "conv" else 1, L.k, L.stride, L.cin, L.cout, int(L.relu),
+                               int(L.res_save), int(L.res_add), k.ctypes.data, b.ctypes.data)
+        h = C.c_void_p()
+        N.check(self.lib.lc_create(arr, len(model.encoder), len(model.decoder), model.arch.in_channels,
+                                   N.PRECISIONS[precision], device, C.byref(h)), "lc_create")
+        self.h = h
+        self.latent_floats = self.lib.lc_latent_floats(h)
+        self._ws = None
+        self._ws_chunks = 0
+        self._small = {}
+        self.launches = 0          # kernels launched by this engine (bench.py gpu_launches)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.lc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- buffers ---------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _ae_ws(self, n_chunks):
+        if self._ws is None or self._ws_chunks < n_chunks:
+            nbytes = self.lib.lc_ae_workspace_bytes(self.h, n_chunks)
+            self._ws = None
+            self._ws = self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.dev)
+            self._ws_chunks = n_chunks
+        return self._ws
+
+    def _buf(self, name, nbytes):
+        b = self._small.get(name)
+        if b is None or b.numel() < nbytes:
+            b = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.dev)
+            self._small[name] = b
+        return b
+
+    # -- stages ------------------------------------------------------------------
+    def stats(self, x):
+        """compress.py:64-65 -> (mean float32, std float32, max|x|).  Sync (reads 32 bytes)."""
+        T, H, W, Cc = x.shape
+        out = self.torch.empty(4, dtype=self.torch.float64, device=self.dev)
+        ws = self._buf("stats", self.lib.lc_stats_workspace_bytes())
+        N.check(self.lib.lc_stats(_ptr(x), T * H * W, Cc, _ptr(out), _ptr(ws), self._stream()), "lc_stats")
+        self.launches += 2
+        s, s2, mx, n = out.cpu().tolist()
+        mean64 = s / n
+        var = max(s2 / n - mean64 * mean64, 0.0)
+        return np.float32(mean64), np.float32(math.sqrt(var)), mx
+
+    def n_chunks(self, T, H, W):
+        g = (C.c_int * 3)()
+        N.check(self.lib.lc_chunk_grid(T, H, W, C.byref(g)), "lc_chunk_grid")
+        return g[0] * g[1] * g[2]
+
+    def encode(self, x, mean, std, batch=None):
+        """compress.py:66-86: standardise + chunk + encoder -> latent (N, latent_floats) float32."""
+        T, H, W, Cc = x.shape
+        n = self.n_chunks(T, H, W)
+        batch = min(batch or DEFAULT_BATCH, n)
+        latent = self.torch.empty((n, self.latent_floats), dtype=self.torch.float32, device=self.dev)
+        ws = self._ae_ws(batch)
+        for b in range(0, n, batch):
+            c = min(batch, n - b)
+            N.check(self.lib.lc_encode(self.h, _ptr(x), T, H, W, Cc, float(mean), float(std), b, c,
+                                       C.c_void_p(latent.data_ptr() + b * self.latent_floats * 4),
+                                       _ptr(ws), ws.numel(), self._stream()), "lc_encode")
+            self.launches += 1 + len(self.model.encoder)
+        return latent
+
+    def decode(self, latent, T, H, W, batch=None):
+        """compress.py:99-111 / decompress.py:66-72: decoder + merge -> recon (T,H,W) float32."""
+        n = self.n_chunks(T, H, W)
+        assert latent.shape[0] == n, "latent does not match the array size"
+        batch = min(batch or DEFAULT_BATCH, n)
+        recon = self.torch.empty((T, H, W), dtype=self.torch.float32, device=self.dev)
+        ws = self._ae_ws(batch)
+        for b in range(0, n, batch):
+            c = min(batch, n - b)
+            N.check(self.lib.lc_decode(self.h, C.c_void_p(latent.data_ptr() + b * self.latent_floats * 4),
+                                       T, H, W, b, c, _ptr(recon), _ptr(ws), ws.numel(), self._stream()),
+                    "lc_decode")
+            self.launches += 1 + len(self.model.decoder)
+        return recon
+
+    def quantize(self, x, recon, mean, std, thr):
+        """compress.py:114-135.  thr is the (possibly guard-banded) absolute bound as a Python float;
+        the float32 forms are made here exactly as NumPy makes them.  Sync (reads the count)."""
+        T, H, W, Cc = x.shape
+        n = T * H * W
+        mask = self.torch.empty(n, dtype=self.torch.int8, device=self.dev)
+        q = self.torch.empty(n, dtype=self.torch.int32, device=self.dev)
+        cnt = self.torch.zeros(1, dtype=self.torch.int64, device=self.dev)
+        ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n))
+        thr32 = np.float32(thr)
+        thr2_32 = np.float32(thr * 2.0)
+        N.check(self.lib.lc_quantize(_ptr(x), Cc, _ptr(recon), n, float(mean), float(std), float(thr32),
+                                     float(thr2_32), _ptr(mask), _ptr(q), _ptr(cnt), _ptr(ws), self._stream()),
+                "lc_quantize")
+        self.launches += 1
+        n_out = int(cnt.item())
+        return mask, q[:n_out]
+
+    def reconstruct(self, recon, mask, q, mean, std, thr2):
+        """decompress.py:86-104 -> (T,H,W) float32."""
+        n = recon.numel()
+        out = self.torch.empty_like(recon)
+        ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n))
+        N.check(self.lib.lc_reconstruct(_ptr(recon), _ptr(mask), _ptr(q), n, float(mean), float(std),
+                                        float(thr2), _ptr(out), _ptr(ws), self._stream()), "lc_reconstruct")
+        self.launches += 1
+        return out
+
+    def verify(self, x, xhat, abs_err):
+        """Exhaustive fp64 bound check -> (violations, max |x - xhat|).  Sync."""
+        T, H, W, Cc = x.shape
+        out = self.torch.empty(2, dtype=self.torch.float64, device=self.dev)
+        ws = self._buf("stats", self.lib.lc_stats_workspace_bytes())
+        N.check(self.lib.lc_verify_bound(_ptr(x), Cc, _ptr(xhat), T * H * W, float(abs_err), _ptr(out),
+                                         _ptr(ws), self._stream()), "lc_verify_bound")
+        self.launches += 2
+        v, mx = out.cpu().tolist()
+        return int(v), mx
+
+    # -- first difference / cumsum (compress.py:147-163, decompress.py:78,83) ------
+    def diff(self, v):
+        out = self.torch.empty_like(v)
+        if v.numel():
+            fn = self.lib.lc_diff_i32 if v.dtype == self.torch.int32 else self.lib.lc_diff_i8
+            N.check(fn(_ptr(v), v.numel(), _ptr(out), self._stream()), "lc_diff")
+            self.launches += 1
+        return out
+
+    def cumsum(self, v):
+        out = self.torch.empty_like(v)
+        if v.numel():
+            ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(v.numel()))
+            fn = self.lib.lc_cumsum_i32 if v.dtype == self.torch.int32 else self.lib.lc_cumsum_i8
+            N.check(fn(_ptr(v), v.numel(), _ptr(out), _ptr(ws), self._stream()), "lc_cumsum")
+            self.launches += 1
+        return out
+
+    # -- entropy stage ---------------------------------------------------------------
+    def hist(self, sym):
+        h = self.torch.empty(256, dtype=self.torch.int32, device=self.dev)
+        N.check(self.lib.lc_hist_u8(_ptr(sym), sym.numel(), _ptr(h), self._stream()), "lc_hist_u8")
+        self.launches += 1
+        return h.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+
+    def huff_pack(self, sym, table: HF.Table):
+        """Symbols (uint8 device tensor) -> (payload bytes, per-segment bit lengths uint32, total bits)."""
+        t = self.torch
+        n = sym.numel()
+        nseg = (n + SEG - 1) // SEG
+        out = t.zeros(self.lib.lc_huff_max_bytes(n), dtype=t.uint8, device=self.dev)
+        segb = t.zeros(max(nseg, 1), dtype=t.int64, device=self.dev)
+        tot = t.zeros(1, dtype=t.int64, device=self.dev)
+        code = t.from_numpy(table.code.view(np.int32).copy()).to(self.dev)
+        ln = t.from_numpy(table.len.copy()).to(self.dev)
+        ws = self._buf("scan", self.lib.lc_huff_workspace_bytes(n, SEG))
+        N.check(self.lib.lc_huff_encode(_ptr(sym), n, _ptr(code), _ptr(ln), SEG, _ptr(out), _ptr(segb),
+                                        _ptr(tot), _ptr(ws), self._stream()), "lc_huff_encode")
+        self.launches += 1
+        total_bits = int(tot.item())
+        nbytes = (total_bits + 7) // 8
+        payload = out[:nbytes].cpu().numpy().tobytes()
+        offs = segb.cpu().numpy()
+        lens = np.diff(np.concatenate((offs[:nseg], [total_bits]))).astype(np.uint32) if nseg else \
+            np.zeros(0, np.uint32)
+        return payload, lens, total_bits
+
+    def huff_unpack(self, payload: bytes, n: int, seg_lens: np.ndarray, table: HF.Table):
+        t = self.torch
+        sym = t.empty(n, dtype=t.uint8, device=self.dev)
+        if n == 0:
+            return sym
+        bits = t.zeros(len(payload) + 16, dtype=t.uint8, device=self.dev)
+        if payload:
+            bits[:len(payload)] = t.frombuffer(bytearray(payload), dtype=t.uint8).to(self.dev)
+        offs = np.concatenate(([0], np.cumsum(seg_lens.astype(np.int64))[:-1])).astype(np.int64)
+        segb = t.from_numpy(offs).to(self.dev)
+        lut, tree = table.decode_arrays()
+        d_lut = t.from_numpy(lut.view(np.int16).copy()).to(self.dev)
+        d_tree = t.from_numpy(tree.copy()).to(self.dev)
+        N.check(self.lib.lc_huff_decode(_ptr(bits), n, SEG, _ptr(segb), _ptr(d_lut), HF.LUT_BITS,
+                                        _ptr(d_tree), _ptr(sym), self._stream()), "lc_huff_decode")
+        self.launches += 1
+        return sym
+
+    def pack_stream(self, sym, extra: dict) -> bytes:
+        """uint8 symbols -> self-describing 'LCH1' container."""
+        n = sym.numel()
+        hist = self.hist(sym) if n else np.zeros(256, np.int64)
+        table = HF.build_table(hist)
+        payload, lens, total_bits = self.huff_pack(sym, table) if n else (b"", np.zeros(0, np.uint32), 0)
+        meta = dict(extra, n=int(n), seg=SEG, bits=int(total_bits), ref_tree=bool(table.reference_tree))
+        mj = json.dumps(meta).encode()
+        tb = table.to_bytes()
+        return b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), lens.size), mj, tb,
+                         lens.tobytes(), payload])
+
+    def unpack_stream(self, blob: bytes):
+        assert blob[:4] == HUFF_MAGIC
+        lm, ltb, nl = struct.unpack("<III", blob[4:16])
+        p = 16
+        meta = json.loads(blob[p:p + lm]); p += lm
+        table, _ = HF.Table.from_bytes(blob[p:p + ltb]); p += ltb
+        lens = np.frombuffer(blob, dtype=np.uint32, count=nl, offset=p); p += 4 * nl
+        payload = blob[p:]
+        sym = self.huff_unpack(payload, meta["n"], lens, table)
+        return sym, meta
+
+    def pack_mask(self, mask) -> bytes:
+        """3-state mask -> five trits per byte -> Huffman ('LCH1', kind=mask)."""
+        t = self.torch
+        n = mask.numel()
+        sym = t.empty((n + 4) // 5, dtype=t.uint8, device=self.dev)
+        N.check(self.lib.lc_pack_trits(_ptr(mask), n, _ptr(sym), self._stream()), "lc_pack_trits")
+        self.launches += 1
+        return self.pack_stream(sym, {"kind": "mask5", "n_mask": int(n)})
+
+    def unpack_mask(self, blob: bytes):
+        t = self.torch
+        sym, meta = self.unpack_stream(blob)
+        n = meta["n_mask"]
+        mask = t.empty(n, dtype=t.int8, device=self.dev)
+        N.check(self.lib.lc_unpack_trits(_ptr(sym), n, _ptr(mask), self._stream()), "lc_unpack_trits")
+        self.launches += 1
+        return mask
+
+    def pack_codes(self, q) -> bytes:
+        """int32 quantisation codes -> byte symbols (+ escapes) -> Huffman.  The stream is coded
+        either as is or first-differenced (the reference's transform, compress.py:147-151),
+        whichever the histogram says is shorter; the choice is recorded in the header."""
+        t = self.torch
+        n = q.numel()
+        best = None
+        for diff, bias in ((0, 0), (1, 127)):
+            if n == 0 and diff:
+                break
+            sym = t.empty(n, dtype=t.uint8, device=self.dev)
+            esc = t.empty(max(n, 1), dtype=t.int32, device=self.dev)
+            nesc = t.zeros(1, dtype=t.int64, device=self.dev)
+            ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(max(n, 1)))
+            N.check(self.lib.lc_symbolize_i32(_ptr(q), n, diff, bias, ESC, _ptr(sym), _ptr(esc), _ptr(nesc),
+                                              _ptr(ws), self._stream()), "lc_symbolize_i32")
+            self.launches += 1
+            hist = self.hist(sym) if n else np.zeros(256, np.int64)
+            ne = int(nesc.item())
+            cost = HF.build_table(hist).encoded_bits(hist) + 32 * ne
+            if best is None or cost < best[0]:
+                best = (cost, diff, bias, sym, esc[:ne])
+        _, diff, bias, sym, esc = best
+        escb = esc.cpu().numpy().astype("<i4").tobytes()
+        body = self.pack_stream(sym, {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC,
+                                      "n_esc": len(escb) // 4})
+        return body + escb
+
+    def unpack_codes(self, blob: bytes):
+        t = self.torch
+        # the escape list trails the container; its length is in the header
+        lm = struct.unpack("<I", blob[4:8])[0]
+        meta = json.loads(blob[16:16 + lm])
+        ne = meta["n_esc"]
+        body, escb = (blob[:len(blob) - 4 * ne], blob[len(blob) - 4 * ne:]) if ne else (blob, b"")
+        sym, meta = self.unpack_stream(body)
+        n = meta["n"]
+        q = t.empty(n, dtype=t.int32, device=self.dev)
+        if n == 0:
+            return q
+        esc = t.from_numpy(np.frombuffer(escb, dtype="<i4").copy()).to(self.dev) if ne else \
+            t.zeros(1, dtype=t.int32, device=self.dev)
+        ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n))
+        N.check(self.lib.lc_unsymbolize_i32(_ptr(sym), n, meta["diff"], meta["bias"], meta["esc"], _ptr(esc),
+                                            _ptr(q), _ptr(ws), self._stream()), "lc_unsymbolize_i32")
+        self.launches += 2 if meta["diff"] else 1
+        return q
+
+    # -- latent slot (compress.py:142-144; fpzip is replaced by a tagged container) -----
+    def pack_latent(self, latent, codec="raw") -> bytes:
+        meta = {"precision": self.precision, "model": self.model.arch.name,
+                "filters": self.model.arch.filters, "kernel": self.model.arch.kernel, "codec": codec}
+        mj = json.dumps(meta).encode()
+        raw = latent.cpu().numpy().astype("<f4").tobytes()
+        if codec == "bz2":
+            raw = bz2.compress(raw, 9)
+        return LATENT_MAGIC + struct.pack("<I", len(mj)) + mj + raw
+
+    def unpack_latent(self, blob: bytes, shape):
+        if blob[:4] != LATENT_MAGIC:
+            raise N.NativeError("blob slot 0 is not an 'LCL1' latent container (fpzip streams written by the "
+                                "TensorFlow reference cannot be decoded: fpzip is not available and the decoder "
+                                "numerics must match the compressor's, SURVEY.md H2)")
+        (lm,) = struct.unpack("<I", blob[4:8])
+        meta = json.loads(blob[8:8 + lm])
+        raw = blob[8 + lm:]
+        if meta.get("codec") == "bz2":
+            raw = bz2.decompress(raw)
+        n = int(np.prod(shape))
+        lat = np.frombuffer(raw, dtype="<f4", count=n).reshape(shape[0], -1)
+        return self.torch.from_numpy(lat.copy()).to(self.dev), meta

@@ -1,0 +1,102 @@
+"""ctypes binding of liblossycomp_b200.so (include/lossycomp_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no CUDA device is present the
+codec raises -- the product path is the GPU path or nothing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblossycomp_b200.so")
+
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class LcLayer(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32), ("cin", C.c_int32),
+                ("cout", C.c_int32), ("relu", C.c_int32), ("res_save", C.c_int32), ("res_add", C.c_int32),
+                ("h_kernel", C.c_void_p), ("h_bias", C.c_void_p)]
+
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+_d = C.c_double
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/lossycomp_b200.h one to one
+SIGNATURES = {
+    "lc_last_error": (C.c_char_p, []),
+    "lc_version": (_i, []),
+    "lc_create": (_i, [C.POINTER(LcLayer), _i, _i, _i, _i, _i, C.POINTER(_p)]),
+    "lc_destroy": (_i, [_p]),
+    "lc_latent_floats": (_i, [_p]),
+    "lc_chunk_grid": (_i, [_i, _i, _i, C.POINTER(_i * 3)]),
+    "lc_stats_workspace_bytes": (_sz, []),
+    "lc_stats": (_i, [_p, _i64, _i, _p, _p, _p]),
+    "lc_ae_workspace_bytes": (_sz, [_p, _i]),
+    "lc_encode": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _i, _p, _p, _sz, _p]),
+    "lc_decode": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "lc_scan_workspace_bytes": (_sz, [_i64]),
+    "lc_quantize": (_i, [_p, _i, _p, _i64, _f, _f, _f, _f, _p, _p, _p, _p, _p]),
+    "lc_diff_i32": (_i, [_p, _i64, _p, _p]),
+    "lc_diff_i8": (_i, [_p, _i64, _p, _p]),
+    "lc_cumsum_i32": (_i, [_p, _i64, _p, _p, _p]),
+    "lc_cumsum_i8": (_i, [_p, _i64, _p, _p, _p]),
+    "lc_reconstruct": (_i, [_p, _p, _p, _i64, _f, _f, _d, _p, _p, _p]),
+    "lc_verify_bound": (_i, [_p, _i, _p, _i64, _d, _p, _p, _p]),
+    "lc_hist_u8": (_i, [_p, _i64, _p, _p]),
+    "lc_symbolize_i32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "lc_unsymbolize_i32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p]),
+    "lc_pack_trits": (_i, [_p, _i64, _p, _p]),
+    "lc_unpack_trits": (_i, [_p, _i64, _p, _p]),
+    "lc_huff_max_bytes": (_sz, [_i64]),
+    "lc_huff_workspace_bytes": (_sz, [_i64, _i]),
+    "lc_huff_encode": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "lc_huff_decode": (_i, [_p, _i64, _i, _p, _p, _i, _p, _p, _p]),
+    "lc_synth_field": (_i, [_p, _i, _i, _i, _i, _i, C.c_uint64, _p]),
+    "lc_chunk_gather": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "lc_chunk_merge": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises NativeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C lossy-ml_b200/csrc). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().lc_last_error().decode(errors="replace")
+        if rc == -1 and "Chunks size cannot be larger" in msg:
+            raise AssertionError(msg.split(" ", 1)[-1])     # dataLoader.py:447
+        raise NativeError(f"{what} failed ({rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError("lossycomp (B200 build) needs a CUDA device; there is no CPU fallback.")
+    return torch

@@ -1,0 +1,69 @@
+"""Decompressor -- drop-in for the reference's lossycomp/decompress.py.
+
+    decompress(compressed_data, verbose=False) -> np.ndarray float32 (time, lat, lon, 1)   (decompress.py:21)
+
+Reads the 9-slot blob of compress.py:168 / decompress.py:54.  Slots 6/7 may be the reference's bz2
+streams (first-differenced int32 / int8) or this package's 'LCH1' Huffman containers; slot 0 must be an
+'LCL1' latent container written by this package (it names the decoder precision the blob needs).
+"""
+from __future__ import annotations
+
+import bz2
+import pickle
+
+import numpy as np
+
+from . import _native as N
+from ._engine import HUFF_MAGIC, Engine
+
+
+def decompress_device(eng: Engine, slots, *, inject=None, batch=None):
+    """Returns the reconstruction as a torch float32 CUDA tensor (T,H,W)."""
+    torch = eng.torch
+    comp_data, lshape, array_size, error_shape, mean, std, comp_error, comp_mask, thr2 = slots
+    T, H, W = (int(v) for v in array_size[:3])
+    latent, meta = eng.unpack_latent(comp_data, lshape)                              # decompress.py:58-60
+    if meta["precision"] != eng.precision:
+        raise N.NativeError(f"blob was written with decoder precision {meta['precision']!r}, engine is "
+                            f"{eng.precision!r}: the error bound only holds with identical decoder numerics")
+    if inject and "recon_std" in inject:
+        recon = inject["recon_std"]
+    else:
+        recon = eng.decode(latent, T, H, W, batch=batch)                             # decompress.py:66-72
+    n = T * H * W
+    if comp_error[:4] == HUFF_MAGIC:
+        q = eng.unpack_codes(comp_error)
+    else:                                                                            # decompress.py:75-78
+        dq = np.frombuffer(bz2.decompress(comp_error), dtype=np.int32).reshape(error_shape)
+        q = eng.cumsum(torch.from_numpy(dq.copy()).to(eng.dev))
+    if comp_mask[:4] == HUFF_MAGIC:
+        mask = eng.unpack_mask(comp_mask)
+    else:                                                                            # decompress.py:81-84
+        dm = np.frombuffer(bz2.decompress(comp_mask), dtype=np.int8).reshape((n,))
+        mask = eng.cumsum(torch.from_numpy(dm.copy()).to(eng.dev))
+    assert q.numel() == int(error_shape[0]) and mask.numel() == n
+    return eng.reconstruct(recon, mask, q, mean, std, thr2)                          # decompress.py:86-104
+
+
+def decompress(compressed_data, verbose=False, *, precision=None, model=None, device=None):
+    """Decompression method (reference: decompress.py:21).  Returns the reconstructed data."""
+    N.require_cuda()
+    slots = pickle.loads(compressed_data)                                            # decompress.py:54
+    if precision is None:
+        try:
+            precision = _peek_precision(slots[0])
+        except Exception:
+            precision = None
+    eng = Engine.get(model, precision, device)
+    out = decompress_device(eng, slots)
+    T, H, W = (int(v) for v in slots[2][:3])
+    if verbose:
+        print("Done.")
+    return out.cpu().numpy().reshape(T, H, W, 1)                                     # decompress.py:104-108
+
+
+def _peek_precision(comp_data: bytes):
+    import json
+    import struct
+    (lm,) = struct.unpack("<I", comp_data[4:8])
+    return json.loads(comp_data[8:8 + lm])["precision"]

@@ -1,0 +1,140 @@
+"""Host-side Huffman table builder for the GPU bit packer.
+
+Mirrors the reference's lossycomp/huffman.py: the same (non-canonical) tree construction and
+tie-breaking -- leaves ordered by (count, symbol) (huffman.py:71), the queue stably re-sorted by
+count before each merge, the two smallest popped (first = left = '0'), the parent appended at
+the end (huffman.py:20-33), code = root-to-leaf path (huffman.py:35-45) -- so that the bit
+stream the GPU emits for a symbol sequence equals the '0101...' string `getHuffmanCode` returns
+for the same sequence.  `getHuffmanCode` / `decode_huffman` keep the reference's names and
+return conventions for string input; `build_table` is the integer-symbol entry the codec uses.
+"""
+from __future__ import annotations
+
+from typing import Dict, Hashable, List, Sequence, Tuple
+
+import numpy as np
+
+MAX_CODE_BITS = 32      # the GPU packer takes codes of at most 32 bits
+LUT_BITS = 12           # direct decode table; longer codes walk the tree
+
+
+def _tree_codes(leaves: Sequence[Tuple[Hashable, int]]) -> Dict[Hashable, str]:
+    """leaves: [(symbol, count)] already ordered by (count, symbol)."""
+    n = len(leaves)
+    parent: Dict[int, Tuple[int, str]] = {}
+    queue: List[Tuple[int, int]] = [(leaves[i][1], i) for i in range(n)]
+    nxt = n
+    while len(queue) > 1:
+        queue.sort(key=lambda it: it[0])
+        (fa, a), (fb, b) = queue.pop(0), queue.pop(0)
+        parent[a] = (nxt, "0")
+        parent[b] = (nxt, "1")
+        queue.append((fa + fb, nxt))
+        nxt += 1
+    codes = {}
+    for i, (sym, _) in enumerate(leaves):
+        bits, node = "", i
+        while node in parent:
+            node, bit = parent[node]
+            bits = bit + bits
+        codes[sym] = bits
+    return codes
+
+
+def getHuffmanCode(string):
+    """Reference signature (huffman.py:63): returns [bit string, {char: code}]."""
+    freqs: Dict[str, int] = {}
+    for ch in string:
+        freqs[ch] = freqs.get(ch, 0) + 1
+    leaves = sorted(freqs.items(), key=lambda kv: (kv[1], kv[0]))
+    table = _tree_codes(leaves)
+    return ["".join(table[ch] for ch in string), table]
+
+
+def decode_huffman(input_string, char_store, freq_store):
+    """Reference signature (huffman.py:48): greedy prefix match of `input_string` against the codes."""
+    inv = {code: ch for ch, code in zip(char_store, freq_store)}
+    out, cur = [], ""
+    for b in input_string:
+        cur += b
+        if cur in inv:
+            out.append(inv[cur])
+            cur = ""
+    return "".join(out)
+
+
+class Table:
+    """A prefix code over byte symbols in the arrays the C-ABI wants."""
+
+    def __init__(self, codes: Dict[int, str], reference_tree: bool):
+        self.codes = codes
+        self.reference_tree = reference_tree
+        self.code = np.zeros(256, dtype=np.uint32)
+        self.len = np.zeros(256, dtype=np.uint8)
+        for s, bits in codes.items():
+            assert len(bits) <= MAX_CODE_BITS
+            self.code[s] = int(bits, 2) if bits else 0
+            self.len[s] = len(bits)
+
+    # -- decode side ---------------------------------------------------------
+    def decode_arrays(self, lut_bits: int = LUT_BITS):
+        lut = np.zeros(1 << lut_bits, dtype=np.uint16)
+        nodes: List[List[int]] = [[0, 0]]
+        if len(self.codes) == 1:
+            (s,) = self.codes.keys()
+            return lut, np.array([~s, ~s], dtype=np.int32)
+        for s, bits in self.codes.items():
+            L = len(bits)
+            if L <= lut_bits:
+                base = int(bits, 2) << (lut_bits - L)
+                lut[base:base + (1 << (lut_bits - L))] = (L << 8) | s
+            node = 0
+            for i, b in enumerate(bits):
+                bi = int(b)
+                if i == L - 1:
+                    nodes[node][bi] = ~s
+                else:
+                    if nodes[node][bi] <= 0:
+                        nodes.append([0, 0])
+                        nodes[node][bi] = len(nodes) - 1
+                    node = nodes[node][bi]
+        return lut, np.array(nodes, dtype=np.int32).reshape(-1)
+
+    # -- serialisation (explicit codes: the tree is not canonical) -----------
+    def to_bytes(self) -> bytes:
+        syms = sorted(self.codes)
+        out = bytearray([len(syms) & 0xFF, len(syms) >> 8])
+        for s in syms:
+            out += bytes([s, int(self.len[s])]) + int(self.code[s]).to_bytes(4, "little")
+        return bytes(out)
+
+    @staticmethod
+    def from_bytes(b: bytes) -> Tuple["Table", int]:
+        n = b[0] | (b[1] << 8)
+        codes = {}
+        p = 2
+        for _ in range(n):
+            s, L = b[p], b[p + 1]
+            c = int.from_bytes(b[p + 2:p + 6], "little")
+            codes[s] = format(c, "b").zfill(L) if L else ""
+            p += 6
+        return Table(codes, False), p
+
+    def encoded_bits(self, hist) -> int:
+        return int((np.asarray(hist, dtype=np.int64) * self.len.astype(np.int64)).sum())
+
+
+def build_table(hist) -> Table:
+    """hist: 256 counts.  Reference tree when its depth fits the packer, otherwise the same
+    construction on counts flattened just enough to cap the depth at MAX_CODE_BITS."""
+    hist = np.asarray(hist, dtype=np.int64)
+    shift = 0
+    while True:
+        h = hist if shift == 0 else np.where(hist > 0, np.maximum(hist >> shift, 1), 0)
+        leaves = sorted(((int(s), int(h[s])) for s in np.nonzero(h)[0]), key=lambda kv: (kv[1], kv[0]))
+        if not leaves:
+            leaves = [(0, 1)]
+        codes = _tree_codes(leaves)
+        if max(len(c) for c in codes.values()) <= MAX_CODE_BITS:
+            return Table(codes, reference_tree=(shift == 0))
+        shift += 1

@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / the public API) against the CPU oracle
+and the goldens made by the reference's own code.  Integer / byte / index stages: bit-exact.
+Autoencoder (fp32 CUDA-core mode): |diff| <= 2e-4 on standardised outputs (fp32 vs fp32 with a
+different summation order; typical values are O(1))."""
+import bz2
+import hashlib
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, golden_case
+
+pytestmark = pytest.mark.gpu
+
+AE_FP32_TOL = 2e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from lossycomp._engine import Engine
+    return Engine.get(None, "fp32", 0)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("shape", [(16, 48, 48, 2), (17, 49, 50, 2), (33, 100, 97, 1), (40, 96, 144, 3)])
+def test_chunk_gather_merge_match_oracle(eng, torch, shape):
+    from lossycomp import dataLoader as DL
+    from oracle import lossycomp_oracle as O
+    a = np.arange(np.prod(shape), dtype=np.float32).reshape(shape)
+    c = DL.chunk_data(a, (16, 48, 48))
+    np.testing.assert_array_equal(c, O.chunk_data(a))
+    np.testing.assert_array_equal(DL.merge_data(c, shape), a)          # Chunking_data.ipynb cells 15, 19
+
+
+def test_chunk_rejects_small(eng):
+    from lossycomp import dataLoader as DL
+    with pytest.raises(AssertionError):
+        DL.chunk_data(np.zeros((15, 48, 48, 2), np.float32), (16, 48, 48))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_stats(eng, torch, name):
+    g = golden_case(name)
+    mean, std, mx = eng.stats(dev(torch, g["x"]))
+    assert mean.dtype == np.float32 and std.dtype == np.float32
+    assert abs(float(mean) - float(g["mean"])) <= 2 * np.spacing(np.float32(g["mean"]))
+    assert abs(float(std) - float(g["std"])) <= 4 * np.spacing(np.float32(g["std"]))
+    assert mx == float(np.abs(g["x"][..., 0]).max())
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_autoencoder_fp32_matches_oracle(eng, torch, name):
+    g = golden_case(name)
+    x = dev(torch, g["x"])
+    T, H, W, _ = g["x"].shape
+    latent = eng.encode(x, g["mean"], g["std"])
+    ref_lat = g["latent"].reshape(latent.shape[0], -1)
+    assert np.abs(latent.cpu().numpy() - ref_lat).max() <= AE_FP32_TOL
+    # decoder on the oracle's latent, so that only the decoder is compared
+    recon = eng.decode(dev(torch, ref_lat), T, H, W)
+    assert np.abs(recon.cpu().numpy() - g["recon_std"][..., 0]).max() <= AE_FP32_TOL
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_quantise_codes_bit_exact_on_reference_reconstruction(eng, torch, name):
+    """compress.py:114-166 fed the reference's own reconstruction: mask, q, both first differences
+    and the bz2 streams must equal what the reference produced."""
+    g = golden_case(name)
+    x = dev(torch, g["x"])
+    recon = dev(torch, g["recon_std"][..., 0])
+    thr = float(g["abs_err"])
+    mask, q = eng.quantize(x, recon, g["mean"], g["std"], thr)
+    ref_q = np.cumsum(g["dq"].astype(np.int64)).astype(np.int32)
+    ref_m = np.cumsum(g["dm"].astype(np.int64)).astype(np.int8)
+    np.testing.assert_array_equal(q.cpu().numpy(), ref_q)
+    np.testing.assert_array_equal(mask.cpu().numpy(), ref_m)
+    dq = eng.diff(q).cpu().numpy()
+    dm = eng.diff(mask).cpu().numpy()
+    np.testing.assert_array_equal(dq, g["dq"])
+    np.testing.assert_array_equal(dm, g["dm"])
+    assert hashlib.sha256(bz2.compress(dq.tobytes(), 9)).hexdigest() == str(g["comp_error_sha"])
+    assert hashlib.sha256(bz2.compress(dm.tobytes(), 9)).hexdigest() == str(g["comp_mask_sha"])
+    # cumsum is the exact inverse (decompress.py:78,83)
+    np.testing.assert_array_equal(eng.cumsum(dev(torch, g["dq"])).cpu().numpy(), ref_q)
+    np.testing.assert_array_equal(eng.cumsum(dev(torch, g["dm"])).cpu().numpy(), ref_m)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_reconstruct_bit_exact_and_violation_set(eng, torch, name):
+    """decompress.py:86-104 on the reference's reconstruction and codes: output bit-identical to
+    the reference's decompress(), including the elements where the reference exceeds the bound."""
+    g = golden_case(name)
+    recon = dev(torch, g["recon_std"][..., 0])
+    q = dev(torch, np.cumsum(g["dq"].astype(np.int64)).astype(np.int32))
+    m = dev(torch, np.cumsum(g["dm"].astype(np.int64)).astype(np.int8))
+    xhat = eng.reconstruct(recon, m, q, g["mean"], g["std"], float(g["thr2"]))
+    np.testing.assert_array_equal(xhat.cpu().numpy(), g["xhat"][..., 0])
+    viol, mx = eng.verify(dev(torch, g["x"]), xhat, float(g["abs_err"]))
+    assert viol == int(g["violations"])
+    ref_max = np.abs(g["x"][..., 0].astype(np.float64) - g["xhat"][..., 0].astype(np.float64)).max()
+    assert mx == ref_max
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_parity_mode_blob_slots_match_reference(eng, torch, name):
+    """Whole compress_device in parity mode with the reference's mean/std/reconstruction injected:
+    slots 1-8 equal the reference blob's (slot 0 is our latent container by design)."""
+    from lossycomp.compress import compress_device
+    from lossycomp.decompress import decompress_device
+    g = golden_case(name)
+    x = dev(torch, g["x"])
+    inj = {"mean": g["mean"], "std": g["std"], "recon_std": dev(torch, g["recon_std"][..., 0])}
+    slots, info = compress_device(eng, x, float(g["abs_err"]), mode="parity", codec="bz2", inject=inj)
+    assert tuple(slots[1]) == tuple(g["latent_shape"]) and tuple(slots[2]) == tuple(g["array_shape"])
+    assert tuple(slots[3]) == tuple(g["error_shape"])
+    assert slots[4] == g["mean"] and slots[5] == g["std"] and slots[8] == float(g["thr2"])
+    assert [type(s).__name__ for s in slots] == list(g["slot_types"])
+    assert hashlib.sha256(slots[6]).hexdigest() == str(g["comp_error_sha"])
+    assert hashlib.sha256(slots[7]).hexdigest() == str(g["comp_mask_sha"])
+    out = decompress_device(eng, pickle.loads(pickle.dumps(slots)), inject=inj)
+    np.testing.assert_array_equal(out.cpu().numpy(), g["xhat"][..., 0])
+
+
+@pytest.mark.parametrize("codec", ["huff", "bz2"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_public_api_roundtrip_strict_bound(name, codec):
+    """compress() -> decompress() through the drop-in API: hard bound on every element."""
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    g = golden_case(name)
+    x, thr = g["x"], float(g["abs_err"])
+    blob = compress(x, thr, codec=codec, precision="fp32")
+    assert isinstance(blob, bytes)
+    slots = pickle.loads(blob)
+    assert len(slots) == 9 and slots[8] < 2 * thr
+    xhat = decompress(blob)
+    assert xhat.dtype == np.float32 and xhat.shape == x.shape[:3] + (1,)
+    err = np.abs(x[..., 0].astype(np.float64) - xhat[..., 0].astype(np.float64))
+    assert err.max() <= thr, f"{(err > thr).sum()} violations"
+    # compression factor within 1% of the reference's for the same input (bz2 codec: same coder)
+    if codec == "bz2":
+        ref_len = int(g["comp_error_len"]) + int(g["comp_mask_len"])
+        got = len(slots[6]) + len(slots[7])
+        assert abs(got - ref_len) / ref_len < 0.01
+
+
+def test_decoder_is_batch_invariant(eng, torch):
+    """H2: the decoder output must be bit-identical for any batch split."""
+    g = golden_case("odd_all_axes")
+    T, H, W, _ = g["x"].shape
+    lat = dev(torch, g["latent"].reshape(g["latent"].shape[0], -1))
+    a = eng.decode(lat, T, H, W, batch=27).cpu().numpy()
+    b = eng.decode(lat, T, H, W, batch=4).cpu().numpy()
+    c = eng.decode(lat, T, H, W, batch=1).cpu().numpy()
+    assert a.tobytes() == b.tobytes() == c.tobytes()
+
+
+@pytest.mark.parametrize("n,alpha", [(1, 1), (5, 2), (4096, 3), (4097, 7), (100003, 40), (300000, 200)])
+def test_huffman_bits_equal_reference_builder(eng, torch, n, alpha):
+    """GPU bit packing from the host-built table == the '0101' string of the reference's
+    getHuffmanCode for the same symbol sequence (symbols mapped to single characters)."""
+    from lossycomp import huffman as HF
+    from oracle import lossycomp_oracle as O
+    rng = np.random.default_rng(n)
+    p = rng.dirichlet(np.ones(alpha) * 0.3)
+    sym = rng.choice(alpha, size=n, p=p).astype(np.uint8)
+    table = HF.build_table(np.bincount(sym, minlength=256))
+    assert table.reference_tree
+    payload, lens, total_bits = eng.huff_pack(dev(torch, sym), table)
+    bits, ref_table = O.huffman_code("".join(chr(0x100 + int(s)) for s in sym))
+    assert {ord(k) - 0x100: v for k, v in ref_table.items()} == table.codes
+    assert total_bits == len(bits)
+    got = "".join(format(b, "08b") for b in payload)[:total_bits]
+    assert got == bits
+    back = eng.huff_unpack(payload, n, lens, table).cpu().numpy()
+    np.testing.assert_array_equal(back, sym)
+
+
+def test_mask_and_code_streams_roundtrip(eng, torch):
+    rng = np.random.default_rng(5)
+    mask = rng.choice(3, size=123457, p=[0.5, 0.3, 0.2]).astype(np.int8)
+    blob = eng.pack_mask(dev(torch, mask))
+    np.testing.assert_array_equal(eng.unpack_mask(blob).cpu().numpy(), mask)
+    q = np.rint(np.abs(rng.normal(0, 6, size=77777))).astype(np.int32) + 1
+    q[::1000] = 100000 + np.arange(q[::1000].size)      # escapes
+    blob = eng.pack_codes(dev(torch, q))
+    np.testing.assert_array_equal(eng.unpack_codes(blob).cpu().numpy(), q)
+    empty = eng.pack_codes(dev(torch, np.zeros(0, np.int32)))
+    assert eng.unpack_codes(empty).numel() == 0
+
+
+def test_no_outliers_is_handled(torch):
+    """The reference raises IndexError when nothing exceeds the bound (compress.py:148); we return a
+    valid blob with an empty code stream."""
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    g = golden_case("one_chunk")
+    blob = compress(g["x"], 1000.0, precision="fp32")
+    slots = pickle.loads(blob)
+    assert slots[3] == (0,)
+    xhat = decompress(blob)
+    assert np.abs(g["x"][..., 0] - xhat[..., 0]).max() <= 1000.0
+
+
+def test_api_errors(torch):
+    from lossycomp.compress import compress
+    with pytest.raises(AssertionError):
+        compress(np.zeros((16, 48, 48, 2), np.float32), 0)
+    with pytest.raises(AssertionError):
+        compress(np.zeros((16, 48, 48, 3), np.float32), 0.1)
+    with pytest.raises(AssertionError):
+        compress(np.zeros((15, 48, 48, 2), np.float32), 0.1)
