@@ -69,6 +69,12 @@ int lc_create(const lc_layer_t* layers, int n_enc, int n_dec, int in_channels, i
 int lc_destroy(lc_handle_t h);
 int lc_latent_floats(lc_handle_t h); /* floats per chunk in the latent, e.g. 1*3*3*23 */
 
+/* Per-layer kernel timing for bench.py's roofline: when enabled, every convolution launch is
+ * bracketed by a CUDA event pair on the launching stream; lc_profile_read (sync) returns and
+ * resets the accumulated milliseconds and launch counts per layer (n >= n_enc + n_dec). */
+int lc_profile_enable(lc_handle_t h, int on);
+int lc_profile_read(lc_handle_t h, double* h_ms, long long* h_launches, int n);
+
 /* chunk grid of dataLoader.py:449: ceil(T/16), ceil(H/48), ceil(W/48) */
 int lc_chunk_grid(int T, int H, int W, int grid[3]);
 

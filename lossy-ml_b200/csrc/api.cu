@@ -38,6 +38,8 @@ extern "C" int lc_create(const lc_layer_t* layers, int n_enc, int n_dec, int in_
   LC_CUDA(cudaSetDevice(device));
   lc_codec* h = new lc_codec();
   memset(h, 0, sizeof(*h));
+  h->spans = new std::vector<ProfSpan>();
+  h->pool = new std::vector<cudaEvent_t>();
   h->device = device;
   h->precision = precision;
   h->in_channels = in_channels;
@@ -109,7 +111,49 @@ extern "C" int lc_destroy(lc_handle_t h) {
     cudaFree(h->layers[i].d_b);
     if (h->layers[i].d_wtc) cudaFree(h->layers[i].d_wtc);
   }
+  for (auto& sp : *h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto& e : *h->pool) cudaEventDestroy(e);
+  delete h->spans;
+  delete h->pool;
   delete h;
+  return LC_OK;
+}
+
+// ---- per-layer kernel timing (CUDA events on the launching stream) -------------------------
+static cudaEvent_t prof_event(lc_codec* h) {
+  if (!h->pool->empty()) { cudaEvent_t e = h->pool->back(); h->pool->pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(lc_codec* h, int layer, cudaStream_t s) {
+  if (!h->profile) return;
+  ProfSpan sp{layer, prof_event(h), prof_event(h)};
+  cudaEventRecord(sp.a, s);
+  h->spans->push_back(sp);
+}
+void prof_end(lc_codec* h, cudaStream_t s) {
+  if (!h->profile) return;
+  cudaEventRecord(h->spans->back().b, s);
+}
+extern "C" int lc_profile_enable(lc_handle_t h, int on) {
+  LC_REQUIRE(h, "null handle");
+  h->profile = on;
+  return LC_OK;
+}
+extern "C" int lc_profile_read(lc_handle_t h, double* h_ms, long long* h_launches, int n) {
+  LC_REQUIRE(h && h_ms && h_launches && n >= h->n_enc + h->n_dec, "bad argument");
+  for (int i = 0; i < n; ++i) { h_ms[i] = 0; h_launches[i] = 0; }
+  for (auto& sp : *h->spans) {
+    LC_CUDA(cudaEventSynchronize(sp.b));
+    float ms = 0;
+    LC_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    h_ms[sp.layer] += ms;
+    h_launches[sp.layer] += 1;
+    h->pool->push_back(sp.a);
+    h->pool->push_back(sp.b);
+  }
+  h->spans->clear();
   return LC_OK;
 }
 
@@ -186,7 +230,9 @@ static int run_layers_fp32(lc_codec* h, int first, int count, float* cur, float*
       for (int b = 0; b < 3; ++b)
         if (bufs[b] != cur && bufs[b] != skip) { dst = bufs[b]; break; }
     }
+    prof_begin(h, i, s);
     int rc = conv_direct_launch(h, L, cur, dst, L.res_add ? skip : nullptr, n_chunks, s);
+    prof_end(h, s);
     if (rc != LC_OK) return rc;
     if (L.res_add) skip = nullptr;
     if (L.res_save) skip = dst;

@@ -49,7 +49,12 @@ struct DevLayer {
   size_t wtc_bytes;
 };
 
+struct ProfSpan { int layer; cudaEvent_t a, b; };
+
 struct lc_codec {
+  int profile;                       // record a CUDA event pair around every conv launch
+  std::vector<ProfSpan>* spans;      // pending (unread) spans
+  std::vector<cudaEvent_t>* pool;    // recycled events
   int device;
   int precision;
   int in_channels;
@@ -89,6 +94,10 @@ static inline ChunkGeom make_geom(int T, int H, int W) {
   g.gt = (T + CT - 1) / CT; g.gh = (H + CH - 1) / CH; g.gw = (W + CW - 1) / CW;
   return g;
 }
+
+// profiling helpers (api.cu)
+void prof_begin(lc_codec* h, int layer, cudaStream_t s);
+void prof_end(lc_codec* h, cudaStream_t s);
 
 // ---- conv back ends ---------------------------------------------------------------------
 // fp32 CUDA-core direct convolution over NDHWC fp32 activations (conv_direct.cu)

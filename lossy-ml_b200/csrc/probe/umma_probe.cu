@@ -72,8 +72,8 @@ static int run_case(int N, int G, int S, const std::vector<int>& tap_offs) {
   // K groups: for every tap, G channel groups; flattened list, paired into K steps (last padded)
   struct Grp { int tap, g; };
   std::vector<Grp> groups;
-  for (size_t t = 0; t < tap_offs.size(); ++t)
-    for (int g = 0; g < G; ++g) groups.push_back({(int)t, g});
+  for (int g = 0; g < G; ++g)   // group-major: operand addresses increase, so every LBO is >= 0
+    for (size_t t = 0; t < tap_offs.size(); ++t) groups.push_back({(int)t, g});
   const int nsteps = (int)(groups.size() + 1) / 2;
   std::vector<uint16_t> wt((size_t)nsteps * 2 * N * 8, 0);
   std::vector<float> wref((size_t)groups.size() * N * 8);

@@ -82,6 +82,17 @@ class Engine:
         except Exception:
             pass
 
+    # -- per-layer kernel timing (bench.py roofline) --------------------------------
+    def profile(self, on: bool):
+        N.check(self.lib.lc_profile_enable(self.h, int(on)), "lc_profile_enable")
+
+    def profile_read(self):
+        n = len(self.model.layers)
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        N.check(self.lib.lc_profile_read(self.h, ms, cnt, n), "lc_profile_read")
+        return list(ms), list(cnt)
+
     # -- buffers ---------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
