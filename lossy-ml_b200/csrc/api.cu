@@ -111,6 +111,7 @@ extern "C" int lc_destroy(lc_handle_t h) {
     cudaFree(h->layers[i].d_b);
     if (h->layers[i].d_wtc) cudaFree(h->layers[i].d_wtc);
   }
+  tc_release(h);
   for (auto& sp : *h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto& e : *h->pool) cudaEventDestroy(e);
   delete h->spans;
@@ -212,8 +213,8 @@ static size_t act_floats_per_chunk(const lc_codec* h) {
 
 extern "C" size_t lc_ae_workspace_bytes(lc_handle_t h, int max_chunks) {
   if (!h || max_chunks <= 0) return 0;
-  size_t fp32_path = 3 * act_floats_per_chunk(h) * sizeof(float) * (size_t)max_chunks;
-  return fp32_path + tc_workspace_bytes(h, max_chunks) + 1024;
+  if (h->precision != LC_PREC_FP32) return tc_workspace_bytes(h, max_chunks);
+  return 3 * act_floats_per_chunk(h) * sizeof(float) * (size_t)max_chunks + 1024;
 }
 
 // Runs layers [first, first+count) with the fp32 direct back end.  bufs: 3 activation buffers.

@@ -63,6 +63,7 @@ struct lc_codec {
   int max_c;                 // widest activation in channels
   DevLayer layers[kMaxLayers];
   int num_sms;
+  void* tc_plan;             // TcPlan* (conv_tc.cu), null in LC_PREC_FP32 mode
 };
 
 // chunk index -> origin in the field (dataLoader.py:457-481): lon fastest, tail re-anchored.
@@ -106,8 +107,15 @@ int conv_direct_launch(const lc_codec* h, const DevLayer& L, const float* d_in, 
 
 // tcgen05 implicit-GEMM back end (conv_tc.cu)
 int tc_prepare(lc_codec* h);
+void tc_release(lc_codec* h);
+int tc_backend_of(const lc_codec* h, int layer);
 size_t tc_workspace_bytes(const lc_codec* h, int max_chunks);
 int tc_encode(lc_codec* h, const float* d_x, const ChunkGeom& g, int C, float mean, float stdv,
               int chunk_begin, int chunk_count, float* d_latent, void* d_ws, cudaStream_t s);
 int tc_decode(lc_codec* h, const float* d_latent, const ChunkGeom& g, int chunk_begin, int chunk_count,
               float* d_recon, void* d_ws, cudaStream_t s);
+
+struct ActView;
+ActView f32_view(const DevLayer& L, bool output, const float* base);
+int conv_direct_views(const lc_codec* h, const DevLayer& L, const float* d_w, const ActView& in,
+                      const ActView& out, const ActView* skip, int n_chunks, cudaStream_t s);

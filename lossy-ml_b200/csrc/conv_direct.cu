@@ -1,112 +1,167 @@
-// fp32 CUDA-core direct Conv3D / Conv3DTranspose over channels-last fp32 activations.
+// fp32 CUDA-core direct Conv3D / Conv3DTranspose.
 //
-// This is the LC_PREC_FP32 back end (reference-grade numerics: fp32 FMA, fixed tap order) and
-// the back end of the small inner layers in the tensor-core modes.  Semantics follow Keras
-// (models.py:47-97; SURVEY.md §8c a-M): cross-correlation, "same" padding with
-// before = total/2, Conv3DTranspose = full transposed convolution cropped by (k-s)/2.
+// This is the LC_PREC_FP32 back end (reference-grade numerics: fp32 FMA, fixed tap order) and,
+// in the tensor-core modes, the back end of the layers that have no tcgen05 kernel (the tiny
+// inner levels of the autoencoder); there it reads and writes the same 16-bit group-plane
+// activations as the tensor-core kernels (act.cuh) and uses weights rounded through the same
+// 16-bit format, so a layer computes the same function whichever back end runs it.
 //
+// Semantics follow Keras (models.py:47-97; SURVEY.md §8c a-M): cross-correlation, "same" padding
+// with before = total/2, Conv3DTranspose = full transposed convolution cropped by (k-s)/2.
 // One thread owns one output voxel and all output channels; weights live in shared memory as
 // [tap][cin][cout padded to 4] so that every FMA quad is fed by one broadcast LDS.128.
-#include "common.cuh"
+#include "act.cuh"
 
 namespace {
 
 struct ConvParams {
-  const float* in;
-  float* out;
-  const float* skip;
-  const float* w;     // [taps][cin][cout]
+  ActView in, out, skip;   // skip.base == nullptr when there is no residual add
+  const float* w;          // [taps][cin][cout]
   const float* b;
-  int kind, k, stride, cin, cout, cout_pad, relu, pad_lo;
-  int in_t, in_h, in_w, out_t, out_h, out_w;
-  long long total_vox;  // n_chunks * out_t*out_h*out_w
+  int kind, k, stride, cin, cout, relu, pad_lo;
+  long long total_vox;     // n_chunks * out voxels per chunk
 };
 
-template <int CO4>  // cout_pad / 4
+template <int CO4>
+__device__ __forceinline__ void fma_row(float (&acc)[CO4 * 4], const float x, const float4* __restrict__ wrow) {
+#pragma unroll
+  for (int c4 = 0; c4 < CO4; ++c4) {
+    const float4 w = wrow[c4];
+    acc[c4 * 4 + 0] = fmaf(x, w.x, acc[c4 * 4 + 0]);
+    acc[c4 * 4 + 1] = fmaf(x, w.y, acc[c4 * 4 + 1]);
+    acc[c4 * 4 + 2] = fmaf(x, w.z, acc[c4 * 4 + 2]);
+    acc[c4 * 4 + 3] = fmaf(x, w.w, acc[c4 * 4 + 3]);
+  }
+}
+
+template <int CO4>
 __global__ void __launch_bounds__(512, 1) conv_direct_kernel(ConvParams p) {
   extern __shared__ float4 smem_w4[];
   float* smem_w = reinterpret_cast<float*>(smem_w4);
   const int taps = p.k * p.k * p.k;
-  const int cp = CO4 * 4;
-  // stage weights: [tap*cin + ci][cp], zero padded
+  constexpr int cp = CO4 * 4;
   for (int i = threadIdx.x; i < taps * p.cin * cp; i += blockDim.x) {
-    int co = i % cp;
-    int r = i / cp;
+    const int co = i % cp;
+    const int r = i / cp;
     smem_w[i] = (co < p.cout) ? p.w[(size_t)r * p.cout + co] : 0.f;
   }
   __syncthreads();
 
-  const int ovox = p.out_t * p.out_h * p.out_w;
-  const int ivox = p.in_t * p.in_h * p.in_w;
+  const int OT = p.out.T, OH = p.out.H, OW = p.out.W;
+  const int IT = p.in.T, IH = p.in.H, IW = p.in.W;
+  const int ovox = OT * OH * OW;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < p.total_vox;
        v += (long long)gridDim.x * blockDim.x) {
     const int chunk = (int)(v / ovox);
     int r = (int)(v % ovox);
-    const int ow = r % p.out_w;
-    r /= p.out_w;
-    const int oh = r % p.out_h;
-    const int ot = r / p.out_h;
-    const float* inb = p.in + (size_t)chunk * ivox * p.cin;
+    const int ow = r % OW;
+    r /= OW;
+    const int oh = r % OH;
+    const int ot = r / OH;
 
-    float acc[CO4 * 4];
+    float acc[cp];
 #pragma unroll
-    for (int c = 0; c < CO4 * 4; ++c) acc[c] = (c < p.cout) ? p.b[c] : 0.f;
+    for (int c = 0; c < cp; ++c) acc[c] = (c < p.cout) ? p.b[c] : 0.f;
 
     for (int kt = 0; kt < p.k; ++kt) {
       int it;
       if (p.kind == 0) {
         it = ot * p.stride + kt - p.pad_lo;
       } else {
-        int num = ot + p.pad_lo - kt;
+        const int num = ot + p.pad_lo - kt;
         if (num < 0 || (num % p.stride) != 0) continue;
         it = num / p.stride;
       }
-      if (it < 0 || it >= p.in_t) continue;
+      if (it < 0 || it >= IT) continue;
       for (int kh = 0; kh < p.k; ++kh) {
         int ih;
         if (p.kind == 0) {
           ih = oh * p.stride + kh - p.pad_lo;
         } else {
-          int num = oh + p.pad_lo - kh;
+          const int num = oh + p.pad_lo - kh;
           if (num < 0 || (num % p.stride) != 0) continue;
           ih = num / p.stride;
         }
-        if (ih < 0 || ih >= p.in_h) continue;
+        if (ih < 0 || ih >= IH) continue;
         for (int kw = 0; kw < p.k; ++kw) {
           int iw;
           if (p.kind == 0) {
             iw = ow * p.stride + kw - p.pad_lo;
           } else {
-            int num = ow + p.pad_lo - kw;
+            const int num = ow + p.pad_lo - kw;
             if (num < 0 || (num % p.stride) != 0) continue;
             iw = num / p.stride;
           }
-          if (iw < 0 || iw >= p.in_w) continue;
-          const float* xin = inb + ((size_t)(it * p.in_h + ih) * p.in_w + iw) * p.cin;
+          if (iw < 0 || iw >= IW) continue;
           const float4* wt = smem_w4 + (size_t)((kt * p.k + kh) * p.k + kw) * p.cin * CO4;
-          for (int ci = 0; ci < p.cin; ++ci) {
-            const float x = __ldg(xin + ci);
+          if (p.in.fmt == FMT_F32) {
+            const float* xin = reinterpret_cast<const float*>(p.in.base) + (size_t)chunk * p.in.chunk_stride +
+                               ((size_t)(it * IH + ih) * IW + iw) * p.cin;
+            for (int ci = 0; ci < p.cin; ++ci) fma_row<CO4>(acc, __ldg(xin + ci), wt + ci * CO4);
+          } else {
+            const uint4* xin = reinterpret_cast<const uint4*>(p.in.base);
+            for (int g = 0; g < p.in.G; ++g) {
+              float f[8];
+              unpack8(__ldg(xin + gp_vec_index(p.in, chunk, it, ih, iw, g)), p.in.half, f);
 #pragma unroll
-            for (int c4 = 0; c4 < CO4; ++c4) {
-              const float4 w = wt[ci * CO4 + c4];
-              acc[c4 * 4 + 0] = fmaf(x, w.x, acc[c4 * 4 + 0]);
-              acc[c4 * 4 + 1] = fmaf(x, w.y, acc[c4 * 4 + 1]);
-              acc[c4 * 4 + 2] = fmaf(x, w.z, acc[c4 * 4 + 2]);
-              acc[c4 * 4 + 3] = fmaf(x, w.w, acc[c4 * 4 + 3]);
+              for (int k8 = 0; k8 < 8; ++k8) {
+                const int ci = g * 8 + k8;
+                if (ci < p.cin) fma_row<CO4>(acc, f[k8], wt + ci * CO4);
+              }
             }
           }
         }
       }
     }
-    float* o = p.out + (size_t)v * p.cout;
-    const float* sk = p.skip ? p.skip + (size_t)v * p.cout : nullptr;
+    // ---- epilogue: (+ skip) -> ReLU -> store
+    if (p.skip.base) {
+      if (p.skip.fmt == FMT_F32) {
+        const float* sk = reinterpret_cast<const float*>(p.skip.base) + (size_t)chunk * p.skip.chunk_stride +
+                          (size_t)(v % ovox) * p.cout;
 #pragma unroll
-    for (int c = 0; c < CO4 * 4; ++c) {
-      if (c < p.cout) {
-        float y = acc[c];
-        if (sk) y = __fadd_rn(y, sk[c]);
-        if (p.relu) y = fmaxf(y, 0.f);
-        o[c] = y;
+        for (int c = 0; c < cp; ++c)
+          if (c < p.cout) acc[c] = __fadd_rn(acc[c], sk[c]);
+      } else {
+        const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base);
+#pragma unroll
+        for (int g = 0; g < (cp + 7) / 8; ++g) {
+          if (g < p.skip.G) {
+            float f[8];
+            unpack8(__ldg(sk + gp_vec_index(p.skip, chunk, ot, oh, ow, g)), p.skip.half, f);
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const int c = g * 8 + k8;
+              if (c < cp) {
+                if (c < p.cout) acc[c] = __fadd_rn(acc[c], f[k8]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int c = 0; c < cp; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    }
+    if (p.out.fmt == FMT_F32) {
+      float* o = reinterpret_cast<float*>(p.out.base) + (size_t)chunk * p.out.chunk_stride +
+                 (size_t)(v % ovox) * p.cout;
+#pragma unroll
+      for (int c = 0; c < cp; ++c)
+        if (c < p.cout) o[c] = acc[c];
+    } else {
+      uint4* o = reinterpret_cast<uint4*>(p.out.base);
+#pragma unroll
+      for (int g = 0; g < (cp + 7) / 8; ++g) {
+        if (g < p.out.G) {
+          float f[8];
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int c = g * 8 + k8;
+            f[k8] = (c < cp && c < p.cout) ? acc[c < cp ? c : 0] : 0.f;
+          }
+          o[gp_vec_index(p.out, chunk, ot, oh, ow, g)] = pack8(f, p.out.half);
+        }
       }
     }
   }
@@ -131,17 +186,29 @@ int launch(const ConvParams& p, int num_sms, cudaStream_t s) {
 
 }  // namespace
 
-int conv_direct_launch(const lc_codec* h, const DevLayer& L, const float* d_in, float* d_out,
-                       const float* d_skip, int n_chunks, cudaStream_t s) {
+ActView f32_view(const DevLayer& L, bool output, const float* base) {
+  ActView v;
+  memset(&v, 0, sizeof(v));
+  v.base = const_cast<float*>(base);
+  v.fmt = FMT_F32;
+  v.T = output ? L.out_t : L.in_t;
+  v.H = output ? L.out_h : L.in_h;
+  v.W = output ? L.out_w : L.in_w;
+  v.C = output ? L.cout : L.cin;
+  v.chunk_stride = (long long)v.T * v.H * v.W * v.C;
+  return v;
+}
+
+int conv_direct_views(const lc_codec* h, const DevLayer& L, const float* d_w, const ActView& in,
+                      const ActView& out, const ActView* skip, int n_chunks, cudaStream_t s) {
   ConvParams p;
-  p.in = d_in; p.out = d_out; p.skip = d_skip; p.w = L.d_w; p.b = L.d_b;
+  p.in = in; p.out = out;
+  if (skip) p.skip = *skip; else memset(&p.skip, 0, sizeof(p.skip));
+  p.w = d_w; p.b = L.d_b;
   p.kind = L.kind; p.k = L.k; p.stride = L.stride; p.cin = L.cin; p.cout = L.cout;
   p.relu = L.relu; p.pad_lo = L.pad_lo;
-  p.in_t = L.in_t; p.in_h = L.in_h; p.in_w = L.in_w;
-  p.out_t = L.out_t; p.out_h = L.out_h; p.out_w = L.out_w;
   p.total_vox = (long long)n_chunks * L.out_t * L.out_h * L.out_w;
   const int co4 = (L.cout + 3) / 4;
-  p.cout_pad = co4 * 4;
   switch (co4) {
     case 1: return launch<1>(p, h->num_sms, s);
     case 2: return launch<2>(p, h->num_sms, s);
@@ -155,4 +222,11 @@ int conv_direct_launch(const lc_codec* h, const DevLayer& L, const float* d_in, 
       lc_set_error("conv_direct: cout %d not supported (max 32)", L.cout);
       return LC_EUNSUPPORTED;
   }
+}
+
+int conv_direct_launch(const lc_codec* h, const DevLayer& L, const float* d_in, float* d_out,
+                       const float* d_skip, int n_chunks, cudaStream_t s) {
+  ActView in = f32_view(L, false, d_in), out = f32_view(L, true, d_out), sk;
+  if (d_skip) sk = f32_view(L, true, d_skip);
+  return conv_direct_views(h, L, L.d_w, in, out, d_skip ? &sk : nullptr, n_chunks, s);
 }

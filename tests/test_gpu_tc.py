@@ -1,0 +1,112 @@
+"""Tensor-core (tcgen05) autoencoder path: against the CUDA-core back end on identical 16-bit
+activations/weights, against the fp32 oracle within the 16-bit tolerance, and end to end."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, golden_case
+
+pytestmark = pytest.mark.gpu
+
+# 16-bit operands, fp32 accumulation, activations rounded to 16 bit after every layer:
+# standardised outputs are O(1); bf16 has 8 significant bits, fp16 11.
+TOL_VS_ORACLE = {"bf16": 6e-2, "fp16": 1e-2}
+# same function, different fp32 summation order -> occasional 1-ulp flips of a 16-bit activation
+TOL_TC_VS_DIRECT = {"bf16": 2e-2, "fp16": 3e-3}
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make_engine(prec, no_tc=False):
+    from lossycomp._engine import Engine
+    from lossycomp.models import load_model
+    old = os.environ.pop("LOSSYCOMP_NO_TC", None)
+    if no_tc:
+        os.environ["LOSSYCOMP_NO_TC"] = "1"
+    try:
+        return Engine(load_model(), prec, 0)
+    finally:
+        os.environ.pop("LOSSYCOMP_NO_TC", None)
+        if old is not None:
+            os.environ["LOSSYCOMP_NO_TC"] = old
+
+
+@pytest.fixture(scope="module", params=["bf16", "fp16"])
+def engines(request):
+    prec = request.param
+    return prec, make_engine(prec), make_engine(prec, no_tc=True)
+
+
+@pytest.mark.parametrize("name", ["one_chunk", "two_by_three", "odd_all_axes"])
+def test_tc_matches_cuda_core_backend(engines, name):
+    prec, tc, direct = engines
+    g = golden_case(name)
+    x = dev(g["x"])
+    T, H, W, _ = g["x"].shape
+    la = tc.encode(x, g["mean"], g["std"]).cpu().numpy()
+    lb = direct.encode(x, g["mean"], g["std"]).cpu().numpy()
+    assert np.abs(la - lb).max() <= TOL_TC_VS_DIRECT[prec], np.abs(la - lb).max()
+    lat = dev(g["latent"].reshape(la.shape))
+    ra = tc.decode(lat, T, H, W).cpu().numpy()
+    rb = direct.decode(lat, T, H, W).cpu().numpy()
+    d = np.abs(ra - rb)
+    assert d.max() <= TOL_TC_VS_DIRECT[prec], d.max()
+    assert (d == 0).mean() > 0.5     # most voxels agree to the bit
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_tc_autoencoder_within_tolerance_of_oracle(engines, name):
+    prec, tc, _ = engines
+    g = golden_case(name)
+    x = dev(g["x"])
+    T, H, W, _ = g["x"].shape
+    lat = tc.encode(x, g["mean"], g["std"]).cpu().numpy()
+    ref = g["latent"].reshape(lat.shape)
+    assert np.abs(lat - ref).max() <= TOL_VS_ORACLE[prec] * max(1.0, np.abs(ref).max())
+    recon = tc.decode(dev(ref), T, H, W).cpu().numpy()
+    assert np.abs(recon - g["recon_std"][..., 0]).max() <= TOL_VS_ORACLE[prec]
+
+
+def test_tc_decoder_is_batch_invariant_and_repeatable(engines):
+    prec, tc, _ = engines
+    g = golden_case("odd_all_axes")
+    T, H, W, _ = g["x"].shape
+    lat = dev(g["latent"].reshape(g["latent"].shape[0], -1))
+    a = tc.decode(lat, T, H, W, batch=27).cpu().numpy()
+    b = tc.decode(lat, T, H, W, batch=5).cpu().numpy()
+    c = tc.decode(lat, T, H, W, batch=1).cpu().numpy()
+    d = tc.decode(lat, T, H, W, batch=27).cpu().numpy()
+    assert a.tobytes() == b.tobytes() == c.tobytes() == d.tobytes()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_tc_roundtrip_bound_and_cf(prec, name):
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    g = golden_case(name)
+    x, thr = g["x"], float(g["abs_err"])
+    blob = compress(x, thr, precision=prec)
+    xhat = decompress(blob)
+    err = np.abs(x[..., 0].astype(np.float64) - xhat[..., 0].astype(np.float64))
+    assert err.max() <= thr, f"{(err > thr).sum()} violations"
+    ref = compress(x, thr, precision="fp32")
+    # compression factor of the 16-bit autoencoder within 1 % (fp16) / 3 % (bf16) of the fp32 one
+    lim = 0.01 if prec == "fp16" else 0.03
+    assert abs(len(blob) - len(ref)) / len(ref) < lim, (len(blob), len(ref))
+
+
+def test_blob_records_decoder_precision():
+    from lossycomp import _native as N
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    g = golden_case("one_chunk")
+    blob = compress(g["x"], 0.1, precision="bf16")
+    with pytest.raises(N.NativeError):
+        decompress(blob, precision="fp32")
+    assert decompress(blob).shape == (16, 48, 48, 1)      # picks bf16 from the blob header
