@@ -44,7 +44,7 @@ __device__ __forceinline__ float h16_to_float(unsigned short u, int half) {
   return __uint_as_float((unsigned)u << 16);
 }
 __device__ __forceinline__ unsigned short float_to_h16(float f, int half) {
-  if (half) return __half_as_ushort(__float2half_rn(f));
+  if (half) return __half_as_ushort(__float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f)));   // saturate
   return __bfloat16_as_ushort(__float2bfloat16_rn(f));
 }
 __device__ __forceinline__ void unpack8(const uint4 v, int half, float f[8]) {

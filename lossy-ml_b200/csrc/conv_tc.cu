@@ -318,6 +318,7 @@ int launch_conv3_tc(const lc_codec* h, const LayerPlan& lp, const TensorPlan& ti
   p.in = base + tin.offset_vecs;
   p.out = base + tout.offset_vecs;
   p.skip = tskip ? base + tskip->offset_vecs : nullptr;
+  if (tskip) { p.skip_S = tskip->S; p.skip_GL = tskip->GL; p.skip_PW = tskip->PW; }
   p.in_cs = p.out_cs = p.skip_cs = block_vecs;
   p.n_items = n_chunks * p.tiles_per_chunk;
   const int stage_bytes = p.G * p.slab_slots * 16;

@@ -56,7 +56,7 @@ def test_tc_matches_cuda_core_backend(engines, name):
     rb = direct.decode(lat, T, H, W).cpu().numpy()
     d = np.abs(ra - rb)
     assert d.max() <= TOL_TC_VS_DIRECT[prec], d.max()
-    assert (d == 0).mean() > 0.5     # most voxels agree to the bit
+    assert d.mean() <= TOL_TC_VS_DIRECT[prec] / 20
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
