@@ -1,79 +1,155 @@
 // Tensor-core (tcgen05 / TMEM / bulk-async-copy) back end of the autoencoder, LC_PREC_BF16 and
 // LC_PREC_FP16 modes.
 //
-// Plane-sweep implicit GEMM (stride-1 k=3 convolutions, 80 % of the model's FLOPs):
+// Plane-sweep implicit GEMM.  Common idea of all four kernels:
 //   * activations are 16-bit group-plane tensors (act.cuh): a 128-voxel tile of one time plane is a
-//     128-row K-major UMMA operand, and the in-plane tap (dh,dw) is the same operand started
-//     (dh*PW+dw) vectors later -- no im2col, no swizzle, one 1-D bulk copy per channel group;
-//   * the time taps are folded into N: D[voxel, (dt,co)] = sum_{dh,dw,ci} X[t_in][voxel+(dh,dw)][ci] *
-//     W[dt][dh][dw][ci][co], so one A tile read from shared memory feeds 3x23 output columns (N=80)
-//     instead of 23 -- with N=32 the MMA would be bound by the 128 B/clk shared-memory read of A;
-//   * a CTA sweeps t_in = 0..15 for a fixed 128-voxel tile: the dt-block of D belongs to output
-//     plane t_in-dt+1, which is the same TMEM lane = the same epilogue thread for every t_in, so
-//     the fold is undone by thread-local register accumulation (no cross-lane traffic);
-//   * K steps pair channel groups across taps through the descriptor's leading-byte-offset
-//     (27 groups of 8 channels -> 14 MMAs per plane instead of 18 with channels padded to 32);
+//     128-row K-major UMMA operand, and an in-plane tap (dh,dw) is the same operand started
+//     (dh*PW+dw) vectors later -- no im2col, no swizzle, one 1-D bulk copy per channel-group plane;
+//   * the time taps are folded into N: D[voxel, (dt,co)] = sum_{taps,ci} X[t_in][voxel+tap][ci] *
+//     W[dt][tap][ci][co], so one A tile read from shared memory feeds up to 4x23 output columns;
+//     with N=32 the MMA would be bound by the 128 B/clk shared-memory read of the A operand;
+//   * a CTA sweeps the input planes t_in for a fixed 128-voxel tile: the dt-block of D belongs to an
+//     output plane that is the same TMEM lane = the same epilogue thread for every t_in, so the fold
+//     is undone by thread-local register accumulation (no cross-lane traffic, fixed order);
+//   * K steps pair 8-channel groups across taps through the descriptor's leading-byte-offset
+//     (k=3: 27 groups -> 14 MMAs per plane instead of 18 with channels padded to 32);
 //   * warp-specialised: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected thread),
-//     warps 2-5 = epilogue (TMEM -> registers -> bias/skip/ReLU -> 16-bit stores); 4-stage smem ring,
-//     double-buffered TMEM accumulators.
-// Everything is deterministic: fixed item -> CTA mapping is irrelevant to the result because each
-// output voxel is produced by exactly one thread in a fixed accumulation order.
+//     warps 2-5 = epilogue (TMEM -> registers -> bias/skip/ReLU -> stores); smem ring of input
+//     planes, double-buffered TMEM accumulators.
+// Modes:
+//   K3    Conv3D k=3 s=1 (the ResBlock convs, 80 % of the FLOPs): 9 taps x 3 groups, N = 3x24(+8)
+//   K4    Conv3D k=4 s=1: first layer (input pre-folded along w by the chunk gather: 4 taps x
+//         ceil(4*Cin/8) groups, N = 4x24) and last layer (16 taps x 3 groups, cout=1, N = 16,
+//         fp32 output scattered straight into the merged field = dataLoader.merge_data fused)
+//   DOWN  Conv3D k=4 s=2 on a parity-split input (stride-2 taps become stride-1 taps of the four
+//         (h,w)-parity planes), N = 2x24, weights selected by the parity of t_in
+//   UP    Conv3DTranspose k=4 s=2: one work item per output (h,w)-parity class, 4 taps x 3 groups,
+//         N = 4x24 (the four kt), outputs written at (2j+ph, 2j+pw)
+// Everything is deterministic: each output voxel is produced by exactly one thread in a fixed
+// accumulation order, independent of the item -> CTA mapping.
 #include "act.cuh"
 #include "umma.cuh"
 
 namespace {
 
-constexpr int kStages = 4;
 constexpr int kTcThreads = 192;
-constexpr int kMaxKs = 40;
+constexpr int kMaxKs = 24;
+constexpr int kMaxVar = 4;
 constexpr int kTmemCols = 256;
 constexpr int kAccStride = 128;   // TMEM columns between the two accumulator buffers
+constexpr int kMaxStages = 4;
 
-struct TcParams {
+enum { MODE_K3 = 1, MODE_K4 = 2, MODE_K4_OUT1 = 3, MODE_DOWN = 4, MODE_UP = 5 };
+
+struct SweepParams {
+  // input (GP16): planes per time step = in_NPG (parities x groups)
   const uint4* in;
-  uint4* out;
-  const uint4* skip;
-  long long in_cs, out_cs, skip_cs;
-  int in_S, in_GL, in_PW;
-  int out_S, out_GL, out_PW;
-  int skip_S, skip_GL, skip_PW;
-  int G, T, H, W;
+  long long in_cs;
+  int in_S, in_GL, in_NPG, in_T;
+  // output (GP16) and skip (GP16, same logical extent as the output)
+  ActView out, skip;
+  // MODE_K4_OUT1: merged fp32 field
+  float* out_f32;
+  ChunkGeom geom;
+  int chunk_begin;
+  // row numbering of a tile: row r of tile j is slot row0 + 128*j + r of a pitch-row_PW image;
+  // (hp, wp) = divmod(slot, row_PW); voxel = (hp - row_off, wp - row_off), valid inside [0,H)x[0,W)
+  int row_PW, row0, row_off_h, row_off_w, rows_H, rows_W;
+  int tiles_per_chunk, n_items, n_classes;
+  int slab_slots, slab_start;    // the stage holds slots [row0 + 128*j + slab_start, +slab_slots) of every plane
+  int stages;
+  // MMA
+  int N, nks, nvar;
   const uint4* wimg;
   int wimg_bytes;
+  uint32_t b_base[kMaxVar];
+  uint32_t a_off[kMaxVar][kMaxKs], a_lbo[kMaxVar][kMaxKs];
   const float* bias;
-  int cout, relu, half;
-  int n_items, tiles_per_chunk;
-  int nks, N;
-  int slab_slots;
-  uint32_t a_off[kMaxKs], a_lbo[kMaxKs];
+  int cout, relu, half, out_T;
 };
 
-__device__ __forceinline__ void ld_block24(uint32_t taddr, float d[24]) {
-  uint32_t v[8];
+__device__ __forceinline__ void ld_cols24(uint32_t taddr, float d[24]) {
+  uint32_t v0[8], v1[8], v2[8];
+  umma::tmem_ld8(taddr, v0);
+  umma::tmem_ld8(taddr + 8, v1);
+  umma::tmem_ld8(taddr + 16, v2);
+  umma::tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    umma::tmem_ld8(taddr + j * 8, v);
-    umma::tmem_ld_wait();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) d[j * 8 + k] = __uint_as_float(v[k]);
+  for (int k = 0; k < 8; ++k) {
+    d[k] = __uint_as_float(v0[k]);
+    d[8 + k] = __uint_as_float(v1[k]);
+    d[16 + k] = __uint_as_float(v2[k]);
   }
 }
 
-// k=3, stride 1, dt folded (3 blocks of 24 columns)
-__global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_constant__ TcParams p) {
+struct RowInfo {
+  int n, cls, h, w;
+  bool valid;
+};
+
+__device__ __forceinline__ RowInfo row_info(const SweepParams& p, int item, int row) {
+  RowInfo r;
+  const int per_chunk = p.tiles_per_chunk * p.n_classes;
+  r.n = item / per_chunk;
+  const int rem = item - r.n * per_chunk;
+  r.cls = rem / p.tiles_per_chunk;
+  const int tile = rem - r.cls * p.tiles_per_chunk;
+  const int slot = p.row0 + tile * 128 + row;
+  const int hp = slot / p.row_PW, wp = slot - hp * p.row_PW;
+  r.h = hp - p.row_off_h;
+  r.w = wp - p.row_off_w;
+  r.valid = (r.h >= 0) && (r.h < p.rows_H) && (r.w >= 0) && (r.w < p.rows_W);
+  return r;
+}
+
+// y = acc + bias (+ skip) -> ReLU -> 16-bit -> out(n, t, h, w)
+__device__ __forceinline__ void store_voxel(const SweepParams& p, const float* s_bias, int n, int t, int h, int w,
+                                            const float (&acc)[24]) {
+  float y[24];
+#pragma unroll
+  for (int c = 0; c < 24; ++c) y[c] = acc[c] + s_bias[c];
+  if (p.skip.base) {
+    const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base);
+    const long long si = gp_vec_index(p.skip, n, t, h, w, 0);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      float f[8];
+      unpack8(__ldg(sk + si + (long long)g * p.skip.S), p.half, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[g * 8 + k] = __fadd_rn(y[g * 8 + k], f[k]);
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(p.out.base);
+  const long long oi = gp_vec_index(p.out, n, t, h, w, 0);
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = y[g * 8 + k];
+      if (p.relu) v = fmaxf(v, 0.f);
+      f[k] = (g * 8 + k < p.cout) ? v : 0.f;
+    }
+    if (g < p.out.G) o[oi + (long long)g * p.out.S] = pack8(f, p.half);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, (MODE == MODE_K3) ? 2 : 1)
+sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full[kStages], empty[kStages], tfull[2], tempty[2], wbar;
+  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2], wbar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[24];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab_bytes = p.slab_slots * 16;
-  const int stage_bytes = p.G * slab_bytes;
+  const int stage_bytes = p.in_NPG * slab_bytes;
   uint8_t* sB = smem;
   uint8_t* sA = smem + ((p.wimg_bytes + 127) & ~127);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
     umma::mbar_init(&wbar, 1);
     umma::fence_barrier_init();
@@ -84,6 +160,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
   __syncthreads();
   umma::tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
+  const int per_chunk = p.tiles_per_chunk * p.n_classes;
 
   if (warp == 0) {
     // ===================== producer: bulk async copies (TMA engine) =====================
@@ -92,16 +169,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
       umma::bulk_g2s(sB, p.wimg, (uint32_t)p.wimg_bytes, &wbar);
       int stage = 0, phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int n = item / p.tiles_per_chunk, tile = item % p.tiles_per_chunk;
-        // tile rows are slots [PW + 128*tile, +128); the slab starts PW+1 slots earlier
-        const long long slab0 = (long long)n * p.in_cs + p.in_GL + tile * 128 - 1;
-        for (int t = 0; t < p.T; ++t) {
+        const int n = item / per_chunk;
+        const int tile = (item - n * per_chunk) % p.tiles_per_chunk;
+        const long long slab0 = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * 128 + p.slab_start;
+        for (int t = 0; t < p.in_T; ++t) {
           umma::mbar_wait(&empty[stage], phase ^ 1);
           umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
-          for (int g = 0; g < p.G; ++g)
+          for (int g = 0; g < p.in_NPG; ++g)
             umma::bulk_g2s(sA + stage * stage_bytes + g * slab_bytes,
-                           p.in + slab0 + (long long)(t * p.G + g) * p.in_S, (uint32_t)slab_bytes, &full[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+                           p.in + slab0 + (long long)(t * p.in_NPG + g) * p.in_S, (uint32_t)slab_bytes,
+                           &full[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -114,21 +192,25 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
       const uint32_t kstep_bytes = 2u * p.N * 16u;
       int stage = 0, phase = 0, it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        for (int t = 0; t < p.T; ++t, ++it) {
+        int var = 0;
+        if (MODE == MODE_UP) var = ((item % per_chunk) / p.tiles_per_chunk);
+        for (int t = 0; t < p.in_T; ++t, ++it) {
+          if (MODE == MODE_DOWN) var = t & 1;
           const int buf = it & 1;
           umma::mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
           umma::mbar_wait(&full[stage], phase);
           umma::tcgen05_fence_after();
           const uint32_t a_base = sA_u + stage * stage_bytes;
+          const uint32_t b_base = sB_u + p.b_base[var];
           const uint32_t d_addr = tmem + buf * kAccStride;
           for (int ks = 0; ks < p.nks; ++ks) {
-            const uint64_t da = umma::make_desc(a_base + p.a_off[ks], p.a_lbo[ks], 128);
-            const uint64_t db = umma::make_desc(sB_u + ks * kstep_bytes, p.N * 16u, 128);
+            const uint64_t da = umma::make_desc(a_base + p.a_off[var][ks], p.a_lbo[var][ks], 128);
+            const uint64_t db = umma::make_desc(b_base + ks * kstep_bytes, p.N * 16u, 128);
             umma::mma_f16(d_addr, da, db, idesc, ks > 0);
           }
           umma::commit(&empty[stage]);
           umma::commit(&tfull[buf]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -138,67 +220,158 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     int it = 0;
+    auto wait_d = [&]() -> uint32_t {
+      const int buf = it & 1;
+      umma::mbar_wait(&tfull[buf], (it >> 1) & 1);
+      umma::tcgen05_fence_after();
+      return lane_addr + buf * kAccStride;
+    };
+    auto release_d = [&]() {
+      umma::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tempty[it & 1]);
+      ++it;
+    };
+
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int n = item / p.tiles_per_chunk, tile = item % p.tiles_per_chunk;
-      const int slot = p.in_PW + tile * 128 + row;
-      const int hp = slot / p.in_PW, wp = slot - hp * p.in_PW;
-      const bool valid = (hp >= 1) && (hp <= p.H) && (wp >= 1) && (wp <= p.W);
-      const long long o_base = (long long)n * p.out_cs + p.out_GL + hp * p.out_PW + wp;
-      const long long s_base = (long long)n * p.skip_cs + p.skip_GL + hp * p.skip_PW + wp;
-      float accP[24], accC[24], accN[24];
+      const RowInfo ri = row_info(p, item, row);
+      if (MODE == MODE_K3) {
+        // block dt -> output plane t_in - dt + 1
+        float aP[24], aC[24], aN[24], d[24];
 #pragma unroll
-      for (int c = 0; c < 24; ++c) { accP[c] = 0.f; accC[c] = 0.f; }
-
-      auto finalize = [&](int t, const float (&acc)[24]) {
-        if (!valid) return;
-        float y[24];
+        for (int c = 0; c < 24; ++c) { aP[c] = 0.f; aC[c] = 0.f; }
+        for (int t = 0; t < p.in_T; ++t) {
+          const uint32_t ta = wait_d();
+          ld_cols24(ta, d);
 #pragma unroll
-        for (int c = 0; c < 24; ++c) y[c] = acc[c] + s_bias[c];
-        if (p.skip) {
+          for (int c = 0; c < 24; ++c) aN[c] = d[c];
+          ld_cols24(ta + 24, d);
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            float f[8];
-            unpack8(__ldg(p.skip + s_base + (long long)(t * p.G + g) * p.skip_S), p.half, f);
+          for (int c = 0; c < 24; ++c) aC[c] += d[c];
+          ld_cols24(ta + 48, d);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) y[g * 8 + k] = __fadd_rn(y[g * 8 + k], f[k]);
+          for (int c = 0; c < 24; ++c) aP[c] += d[c];
+          release_d();
+          if (t >= 1 && ri.valid) store_voxel(p, s_bias, ri.n, t - 1, ri.h, ri.w, aP);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) { aP[c] = aC[c]; aC[c] = aN[c]; }
+        }
+        if (ri.valid) store_voxel(p, s_bias, ri.n, p.in_T - 1, ri.h, ri.w, aP);
+      } else if (MODE == MODE_K4) {
+        // k=4, pad 1/2: block dt -> output plane t_in - dt + 1  (planes t+1, t, t-1, t-2)
+        float a1[24], a2[24], a3[24], a0[24], d[24];
+#pragma unroll
+        for (int c = 0; c < 24; ++c) { a1[c] = 0.f; a2[c] = 0.f; a3[c] = 0.f; }
+        for (int t = 0; t < p.in_T; ++t) {
+          const uint32_t ta = wait_d();
+          ld_cols24(ta, d);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) a0[c] = d[c];
+          ld_cols24(ta + 24, d);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) a1[c] += d[c];
+          ld_cols24(ta + 48, d);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) a2[c] += d[c];
+          ld_cols24(ta + 72, d);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) a3[c] += d[c];
+          release_d();
+          if (t >= 2 && ri.valid) store_voxel(p, s_bias, ri.n, t - 2, ri.h, ri.w, a3);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) { a3[c] = a2[c]; a2[c] = a1[c]; a1[c] = a0[c]; }
+        }
+        if (ri.valid) {
+          store_voxel(p, s_bias, ri.n, p.in_T - 2, ri.h, ri.w, a3);
+          store_voxel(p, s_bias, ri.n, p.in_T - 1, ri.h, ri.w, a2);
+        }
+      } else if (MODE == MODE_K4_OUT1) {
+        // cout = 1: column dt*4 holds the contribution to plane t_in - dt + 1; fp32 output is
+        // scattered into the merged (T,H,W) field, keeping only what merge_data keeps of this chunk
+        float a0, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int t0, h0, w0, kt, kh, kw;
+        p.geom.origin(p.chunk_begin + ri.n, t0, h0, w0);
+        p.geom.keep_from(p.chunk_begin + ri.n, kt, kh, kw);
+        const bool keep_hw = ri.valid && ri.h >= kh && ri.w >= kw;
+        float* dst = p.out_f32 + ((size_t)t0 * p.geom.H + (h0 + ri.h)) * p.geom.W + (w0 + ri.w);
+        const size_t plane = (size_t)p.geom.H * p.geom.W;
+        auto emit = [&](int t, float acc) {
+          if (keep_hw && t >= kt) {
+            float y = acc + s_bias[0];
+            if (p.relu) y = fmaxf(y, 0.f);
+            dst[(size_t)t * plane] = y;
+          }
+        };
+        for (int t = 0; t < p.in_T; ++t) {
+          const uint32_t ta = wait_d();
+          uint32_t v0[8], v1[8];
+          umma::tmem_ld8(ta, v0);
+          umma::tmem_ld8(ta + 8, v1);
+          umma::tmem_ld_wait();
+          release_d();
+          a0 = __uint_as_float(v0[0]);
+          a1 += __uint_as_float(v0[4]);
+          a2 += __uint_as_float(v1[0]);
+          a3 += __uint_as_float(v1[4]);
+          if (t >= 2) emit(t - 2, a3);
+          a3 = a2; a2 = a1; a1 = a0;
+        }
+        emit(p.in_T - 2, a3);
+        emit(p.in_T - 1, a2);
+      } else if (MODE == MODE_DOWN) {
+        // t_in = 2*to + dt - 1.  odd t_in: block0 = dt 0 -> plane (t_in+1)/2 (starts it), block1 = dt 2 ->
+        // plane (t_in-1)/2.  even t_in: block0 = dt 1 -> plane t_in/2, block1 = dt 3 -> plane t_in/2 - 1 (done).
+        float aO[24], aN[24], d[24];
+#pragma unroll
+        for (int c = 0; c < 24; ++c) { aO[c] = 0.f; aN[c] = 0.f; }
+        for (int t = 0; t < p.in_T; ++t) {
+          const uint32_t ta = wait_d();
+          if (t & 1) {
+            ld_cols24(ta, d);
+#pragma unroll
+            for (int c = 0; c < 24; ++c) aN[c] = d[c];
+            ld_cols24(ta + 24, d);
+#pragma unroll
+            for (int c = 0; c < 24; ++c) aO[c] += d[c];
+            release_d();
+          } else {
+            ld_cols24(ta, d);
+#pragma unroll
+            for (int c = 0; c < 24; ++c) aN[c] += d[c];
+            ld_cols24(ta + 24, d);
+#pragma unroll
+            for (int c = 0; c < 24; ++c) aO[c] += d[c];
+            release_d();
+            const int m = t >> 1;
+            if (m >= 1 && ri.valid) store_voxel(p, s_bias, ri.n, m - 1, ri.h, ri.w, aO);
+#pragma unroll
+            for (int c = 0; c < 24; ++c) aO[c] = aN[c];
           }
         }
+        if (ri.valid) store_voxel(p, s_bias, ri.n, p.out_T - 1, ri.h, ri.w, aO);
+      } else if (MODE == MODE_UP) {
+        // output plane 2*t_in + kt - 1; block kt.  Planes 2t-1 and 2t complete at step t.
+        const int ph = ri.cls >> 1, pw = ri.cls & 1;
+        const int oh = 2 * ri.h + ph, ow = 2 * ri.w + pw;
+        float cX[24], cY[24], d[24];
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          float f[8];
+        for (int c = 0; c < 24; ++c) { cX[c] = 0.f; cY[c] = 0.f; }
+        for (int t = 0; t < p.in_T; ++t) {
+          const uint32_t ta = wait_d();
+          ld_cols24(ta, d);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float v = y[g * 8 + k];
-            if (p.relu) v = fmaxf(v, 0.f);
-            f[k] = (g * 8 + k < p.cout) ? v : 0.f;
-          }
-          p.out[o_base + (long long)(t * p.G + g) * p.out_S] = pack8(f, p.half);
+          for (int c = 0; c < 24; ++c) cX[c] += d[c];
+          if (t >= 1 && ri.valid) store_voxel(p, s_bias, ri.n, 2 * t - 1, oh, ow, cX);
+          ld_cols24(ta + 24, d);
+#pragma unroll
+          for (int c = 0; c < 24; ++c) cY[c] += d[c];
+          if (ri.valid) store_voxel(p, s_bias, ri.n, 2 * t, oh, ow, cY);
+          ld_cols24(ta + 48, cX);
+          ld_cols24(ta + 72, cY);
+          release_d();
         }
-      };
-
-      for (int t = 0; t < p.T; ++t, ++it) {
-        const int buf = it & 1;
-        umma::mbar_wait(&tfull[buf], (it >> 1) & 1);
-        umma::tcgen05_fence_after();
-        const uint32_t ta = lane_addr + buf * kAccStride;
-        float d[24];
-        ld_block24(ta, d);          // dt = 0 -> output plane t+1
-#pragma unroll
-        for (int c = 0; c < 24; ++c) accN[c] = d[c];
-        ld_block24(ta + 24, d);     // dt = 1 -> output plane t
-#pragma unroll
-        for (int c = 0; c < 24; ++c) accC[c] += d[c];
-        ld_block24(ta + 48, d);     // dt = 2 -> output plane t-1
-#pragma unroll
-        for (int c = 0; c < 24; ++c) accP[c] += d[c];
-        umma::tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&tempty[buf]);
-        if (t >= 1) finalize(t - 1, accP);
-#pragma unroll
-        for (int c = 0; c < 24; ++c) { accP[c] = accC[c]; accC[c] = accN[c]; }
+        if (ri.valid) store_voxel(p, s_bias, ri.n, 2 * p.in_T - 1, oh, ow, cX);
       }
-      finalize(p.T - 1, accP);
     }
   }
   umma::tcgen05_fence_before();
@@ -209,41 +382,72 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------
 // plan: tensors of one chunk block
 // ------------------------------------------------------------------------------------------
+enum { LAYOUT_PLAIN = 0, LAYOUT_PARITY = 1, LAYOUT_WFOLD = 2 };
+
 struct TensorPlan {
   int fmt;                 // FMT_F32 / FMT_GP16
+  int layout;
   int T, H, W, C, G, NP, PW, PH, S, GL;
   long long offset_vecs;   // offset inside the chunk block, in 16-byte vectors
   long long size_vecs;
 };
 
 struct LayerPlan {
-  int backend;             // 0 = direct, 1 = conv3_tc
+  int backend;             // 0 = direct, else MODE_*
   float* d_w16;            // fp32 weights rounded through the 16-bit operand format [tap][cin][cout]
-  TcParams tc;             // template parameters (pointers filled per call)
+  SweepParams sp;          // template (pointers filled per call)
+  int smem_bytes;
 };
 
 struct TcPlan {
   int n_layers;
-  TensorPlan in_enc;                    // fp32 chunk input
+  TensorPlan in_enc;                    // chunk input: fp32 (direct first layer) or w-folded GP16
   TensorPlan out[kMaxLayers];           // output tensor of every layer
   LayerPlan layer[kMaxLayers];
   long long block_vecs;                 // 16-byte vectors per chunk block
+  int wfold_k;
 };
 
-TensorPlan make_gp(int T, int H, int W, int C, int pad_hi) {
+TensorPlan make_gp(int T, int H, int W, int C, int pad_hi, int layout) {
   TensorPlan t;
   memset(&t, 0, sizeof(t));
   t.fmt = FMT_GP16;
+  t.layout = layout;
   t.T = T; t.H = H; t.W = W; t.C = C;
   t.G = (C + 7) / 8;
-  t.NP = 1;
-  t.PW = W + 1 + pad_hi;
-  t.PH = H + 1 + pad_hi;
   t.GL = 8;
+  if (layout == LAYOUT_PARITY) {
+    t.NP = 4;
+    t.PW = (W + 2) / 2;
+    t.PH = (H + 2) / 2;
+  } else {
+    t.NP = 1;
+    t.PW = W + 1 + pad_hi;
+    t.PH = H + 1 + pad_hi;
+  }
   // guard: a tile slab may over-read up to 128 + 3*(PW+1) vectors past the last interior line
   t.S = t.GL + t.PH * t.PW + 128 + 3 * (t.PW + 1);
   t.S = (t.S + 7) & ~7;
+  t.size_vecs = (long long)T * t.NP * t.G * t.S;
+  return t;
+}
+
+// chunk input folded along w for a k-tap first layer: vector (h,w) = { x[h][w+dw-pad][ci] }, pitch W
+TensorPlan make_wfold(int T, int H, int W, int C, int k, int pad_lo) {
+  TensorPlan t;
+  memset(&t, 0, sizeof(t));
+  t.fmt = FMT_GP16;
+  t.layout = LAYOUT_WFOLD;
+  t.T = T; t.H = H; t.W = W; t.C = k * C;
+  t.G = (k * C + 7) / 8;
+  t.NP = 1;
+  t.GL = 8;
+  t.PW = W;
+  t.PH = H + k - 1;                 // pad_lo lines above, k-1-pad_lo below
+  t.S = t.GL + t.PH * t.PW + 128 + 16;
+  t.S = (t.S + 7) & ~7;
   t.size_vecs = (long long)T * t.G * t.S;
+  (void)pad_lo;
   return t;
 }
 
@@ -270,9 +474,37 @@ ActView view_of(const TensorPlan& t, void* block_base, long long block_vecs, int
 
 TcPlan* plan_of(const lc_codec* h) { return reinterpret_cast<TcPlan*>(h->tc_plan); }
 
-bool tc_conv3_eligible(const DevLayer& L) {
-  return L.kind == 0 && L.k == 3 && L.stride == 1 && L.cin == L.cout && L.cin > 16 && L.cin <= 24 &&
-         L.in_t == CT && L.in_h == CH && L.in_w == CW;
+unsigned short to_h16_host(float v, int half) {
+  unsigned short u;
+  if (half) { __half hv = __float2half_rn(v); memcpy(&u, &hv, 2); }
+  else { __nv_bfloat16 bv = __float2bfloat16_rn(v); memcpy(&u, &bv, 2); }
+  return u;
+}
+
+// which tensor-core kernel (if any) can run layer i
+int tc_mode_of(const lc_codec* h, int i) {
+  if (getenv("LOSSYCOMP_NO_TC")) return 0;
+  const DevLayer& L = h->layers[i];
+  const int nl = h->n_enc + h->n_dec;
+  const bool full = (L.in_t == CT && L.in_h == CH && L.in_w == CW);
+  const char* only = getenv("LOSSYCOMP_TC_MODES");   // debugging: comma list of mode numbers
+  auto allowed = [&](int m) { return !only || strchr(only, '0' + m) != nullptr; };
+  if (L.kind == 0 && L.k == 3 && L.stride == 1 && L.cin > 16 && L.cin <= 24 && L.cout > 16 && L.cout <= 24 &&
+      full && i != 0 && i != h->n_enc && i != h->n_enc - 1 && i != nl - 1)
+    return allowed(MODE_K3) ? MODE_K3 : 0;
+  if (L.kind == 0 && L.k == 4 && L.stride == 1 && full) {
+    if (i == 0 && 4 * L.cin <= 24 && L.cout > 16 && L.cout <= 24 && h->n_enc > 1)
+      return allowed(MODE_K4) ? MODE_K4 : 0;
+    if (i == nl - 1 && L.cout == 1 && L.cin > 16 && L.cin <= 24 && i != h->n_enc)
+      return allowed(MODE_K4_OUT1) ? MODE_K4_OUT1 : 0;
+  }
+  if (L.kind == 0 && L.k == 4 && L.stride == 2 && L.cin > 16 && L.cin <= 24 && L.cout > 16 && L.cout <= 24 &&
+      L.in_t % 2 == 0 && L.in_h % 2 == 0 && L.in_w % 2 == 0 && L.in_h >= 12 && i != 0 && i != h->n_enc - 1)
+    return allowed(MODE_DOWN) ? MODE_DOWN : 0;
+  if (L.kind == 1 && L.k == 4 && L.stride == 2 && L.cin > 16 && L.cin <= 24 && L.cout > 16 && L.cout <= 24 &&
+      L.in_h >= 6 && i != h->n_enc && i != nl - 1)
+    return allowed(MODE_UP) ? MODE_UP : 0;
+  return 0;
 }
 
 // merge of the decoder's fp32 chunk output (dataLoader.py:484-532), strided chunk blocks
@@ -292,6 +524,7 @@ __global__ void merge_blocks_kernel(const float* __restrict__ dec, long long chu
   }
 }
 
+// K2: standardise channel 0 and gather chunks into fp32 chunk blocks (direct first layer)
 __global__ void gather_blocks_kernel(const float* __restrict__ x, ChunkGeom g, int C, float mean, float stdv,
                                      int chunk_begin, int n_chunks, float* __restrict__ out,
                                      long long chunk_stride) {
@@ -310,36 +543,255 @@ __global__ void gather_blocks_kernel(const float* __restrict__ x, ChunkGeom g, i
   }
 }
 
-int launch_conv3_tc(const lc_codec* h, const LayerPlan& lp, const TensorPlan& tin, const TensorPlan& tout,
-                    const TensorPlan* tskip, void* block_base, long long block_vecs, int n_chunks,
-                    cudaStream_t s) {
-  TcParams p = lp.tc;
-  uint4* base = reinterpret_cast<uint4*>(block_base);
-  p.in = base + tin.offset_vecs;
-  p.out = base + tout.offset_vecs;
-  p.skip = tskip ? base + tskip->offset_vecs : nullptr;
-  if (tskip) { p.skip_S = tskip->S; p.skip_GL = tskip->GL; p.skip_PW = tskip->PW; }
-  p.in_cs = p.out_cs = p.skip_cs = block_vecs;
-  p.n_items = n_chunks * p.tiles_per_chunk;
-  const int stage_bytes = p.G * p.slab_slots * 16;
-  const int smem = ((p.wimg_bytes + 127) & ~127) + kStages * stage_bytes + 128;
+// K2 (tensor-core first layer): standardise, gather and fold the k w-taps into pseudo-channels:
+// vector g of voxel (h,w) holds pseudo-channels pc = dw*C + ci = x[h][w + dw - pad][ci] (0 outside)
+__global__ void gather_wfold_kernel(const float* __restrict__ x, ChunkGeom g, int C, float mean, float stdv,
+                                    int chunk_begin, int n_chunks, ActView out, int k, int pad_lo) {
+  const long long total = (long long)n_chunks * CT * CH * CW * out.G;
+  uint4* o = reinterpret_cast<uint4*>(out.base);
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int lw = (int)(v % CW);
+    long long r = v / CW;
+    const int lh = (int)(r % CH);
+    r /= CH;
+    const int gi = (int)(r % out.G);
+    r /= out.G;
+    const int lt = (int)(r % CT);
+    const int chunk = (int)(r / CT);
+    int t0, h0, w0;
+    g.origin(chunk_begin + chunk, t0, h0, w0);
+    const float* line = x + (((size_t)(t0 + lt) * g.H + (h0 + lh)) * g.W + w0) * C;
+    float f[8];
+#pragma unroll
+    for (int k8 = 0; k8 < 8; ++k8) {
+      const int pc = gi * 8 + k8;
+      const int dw = pc / C, ci = pc - dw * C;
+      const int w = lw + dw - pad_lo;
+      float val = 0.f;
+      if (dw < k && w >= 0 && w < CW) {
+        val = line[(size_t)w * C + ci];
+        if (ci == 0) val = __fdiv_rn(__fsub_rn(val, mean), stdv);
+      }
+      f[k8] = val;
+    }
+    // slot = (h + pad_lo) * PW + w   (no halo columns: the w taps are inside the vector)
+    const long long idx = (long long)chunk * out.chunk_stride + ((long long)lt * out.G + gi) * out.S + out.GL +
+                          (lh + pad_lo) * out.PW + lw;
+    o[idx] = pack8(f, out.half);
+  }
+}
+
+template <int MODE>
+int launch_mode(const lc_codec* h, const SweepParams& p, int smem) {
   static bool attr_done = false;
   if (!attr_done) {
-    LC_CUDA(cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  if (smem > 100 * 1024) {
-    lc_set_error("conv3_tc: %d bytes of shared memory needed", smem);
-    return LC_EUNSUPPORTED;
-  }
-  int grid = 2 * h->num_sms;
+  (void)h;
+  (void)p;
+  (void)smem;
+  return LC_OK;
+}
+
+int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStream_t s) {
+  const int smem = lp.smem_bytes;
+  const int per_sm = (lp.backend == MODE_K3) ? 2 : 1;
+  int grid = per_sm * h->num_sms;
   if (grid > p.n_items) grid = p.n_items;
-  conv3_tc_kernel<<<grid, kTcThreads, smem, s>>>(p);
+  int rc = LC_OK;
+  switch (lp.backend) {
+    case MODE_K3:
+      rc = launch_mode<MODE_K3>(h, p, smem);
+      if (rc == LC_OK) sweep_tc_kernel<MODE_K3><<<grid, kTcThreads, smem, s>>>(p);
+      break;
+    case MODE_K4:
+      rc = launch_mode<MODE_K4>(h, p, smem);
+      if (rc == LC_OK) sweep_tc_kernel<MODE_K4><<<grid, kTcThreads, smem, s>>>(p);
+      break;
+    case MODE_K4_OUT1:
+      rc = launch_mode<MODE_K4_OUT1>(h, p, smem);
+      if (rc == LC_OK) sweep_tc_kernel<MODE_K4_OUT1><<<grid, kTcThreads, smem, s>>>(p);
+      break;
+    case MODE_DOWN:
+      rc = launch_mode<MODE_DOWN>(h, p, smem);
+      if (rc == LC_OK) sweep_tc_kernel<MODE_DOWN><<<grid, kTcThreads, smem, s>>>(p);
+      break;
+    case MODE_UP:
+      rc = launch_mode<MODE_UP>(h, p, smem);
+      if (rc == LC_OK) sweep_tc_kernel<MODE_UP><<<grid, kTcThreads, smem, s>>>(p);
+      break;
+    default:
+      lc_set_error("unknown tensor-core mode %d", lp.backend);
+      return LC_EINVAL;
+  }
+  if (rc != LC_OK) return rc;
   LC_LAUNCH_CHECK();
   return LC_OK;
 }
 
+// One K group = 8 (pseudo-)channels of one shifted view of one plane of the stage.
+struct KGroup {
+  uint32_t a_addr;        // byte offset inside the stage
+  int kt_unused;
+  int tap_h, tap_w;       // kernel indices (kh, kw) this group multiplies with
+  int ci0;                // first input channel of the group (or pseudo-channel for WFOLD)
+};
+
 }  // namespace
+
+// Build the per-layer SweepParams template: geometry, K-step tables and the weight image.
+static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan& tin, const TensorPlan& tout,
+                       const std::vector<float>& w16, int half) {
+  DevLayer& L = h->layers[i];
+  LayerPlan& lp = P->layer[i];
+  SweepParams& p = lp.sp;
+  memset(&p, 0, sizeof(p));
+  p.in_S = tin.S; p.in_GL = tin.GL; p.in_NPG = tin.NP * tin.G; p.in_T = L.in_t;
+  p.bias = L.d_b; p.cout = L.cout; p.relu = L.relu; p.half = half; p.out_T = L.out_t;
+  p.n_classes = 1;
+  const int G = tin.G;
+  const int cin = L.cin, cout = L.cout, k = L.k;
+  // variants: list of K groups (ordered by increasing operand address) and, per N block, the kt tap
+  std::vector<std::vector<KGroup>> groups;       // [variant][group]
+  std::vector<std::vector<int>> block_kt;        // [variant][block] -> kt (or -1)
+  int block_cols = 24;
+  if (mode == MODE_K3 || mode == MODE_K4_OUT1) {
+    // plain input; rows follow the input's padded numbering; taps (dh,dw) -> slab offset dh*PW+dw
+    p.row_PW = tin.PW; p.row0 = tin.PW; p.row_off_h = 1; p.row_off_w = 1;
+    p.rows_H = L.in_h; p.rows_W = L.in_w;
+    p.tiles_per_chunk = (L.in_h * tin.PW + 127) / 128;
+    p.slab_start = -(tin.PW + 1);
+    p.slab_slots = 128 + (k - 1) * (tin.PW + 1);
+    groups.resize(1);
+    for (int g = 0; g < G; ++g)
+      for (int dh = 0; dh < k; ++dh)
+        for (int dw = 0; dw < k; ++dw)
+          groups[0].push_back({(uint32_t)(g * p.slab_slots * 16 + (dh * tin.PW + dw) * 16), 0, dh, dw, g * 8});
+    block_kt.resize(1);
+    for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
+    if (mode == MODE_K4_OUT1) { block_cols = 4; p.N = 16; } else { p.N = 80; }
+  } else if (mode == MODE_K4) {
+    // w-folded input (pitch W, no halo columns): taps dh only, pseudo-channel pc = dw*cin + ci
+    p.row_PW = tin.PW; p.row0 = L.pad_lo * tin.PW; p.row_off_h = L.pad_lo; p.row_off_w = 0;
+    p.rows_H = L.in_h; p.rows_W = L.in_w;
+    p.tiles_per_chunk = (L.in_h * tin.PW + 127) / 128;
+    p.slab_start = -L.pad_lo * tin.PW;
+    p.slab_slots = 128 + (k - 1) * tin.PW;
+    groups.resize(1);
+    for (int g = 0; g < G; ++g)
+      for (int dh = 0; dh < k; ++dh)
+        groups[0].push_back({(uint32_t)(g * p.slab_slots * 16 + dh * tin.PW * 16), 0, dh, -1, g * 8});
+    block_kt.resize(1);
+    for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
+    p.N = 96;
+  } else if (mode == MODE_DOWN) {
+    // parity input: hp = 2*ho + kh -> plane (kh&1, kw&1), slot (ho + kh/2)*PW' + wo + kw/2
+    p.row_PW = tin.PW; p.row0 = 0; p.row_off_h = 0; p.row_off_w = 0;
+    p.rows_H = L.out_h; p.rows_W = L.out_w;
+    p.tiles_per_chunk = (L.out_h * tin.PW + 127) / 128;
+    p.slab_start = 0;
+    p.slab_slots = 128 + tin.PW + 2;
+    groups.resize(2);
+    block_kt.resize(2);
+    for (int var = 0; var < 2; ++var) {
+      for (int par = 0; par < 4; ++par)
+        for (int g = 0; g < G; ++g)
+          for (int dh2 = 0; dh2 < 2; ++dh2)
+            for (int dw2 = 0; dw2 < 2; ++dw2)
+              groups[var].push_back({(uint32_t)((par * G + g) * p.slab_slots * 16 + (dh2 * tin.PW + dw2) * 16), 0,
+                                     2 * dh2 + (par >> 1), 2 * dw2 + (par & 1), g * 8});
+      // var = t_in & 1: odd -> kt {0, 2}; even -> kt {1, 3}
+      block_kt[var] = var ? std::vector<int>{0, 2} : std::vector<int>{1, 3};
+    }
+    p.N = 48;
+  } else if (mode == MODE_UP) {
+    // plain input at input resolution; one variant per output parity class (ph, pw):
+    // p=0: (k=1, i=j), (k=3, i=j-1);  p=1: (k=2, i=j), (k=0, i=j+1)
+    p.row_PW = tin.PW; p.row0 = tin.PW; p.row_off_h = 1; p.row_off_w = 1;
+    p.rows_H = L.in_h; p.rows_W = L.in_w;
+    p.tiles_per_chunk = (L.in_h * tin.PW + 127) / 128;
+    p.n_classes = 4;
+    p.slab_start = -(tin.PW + 1);
+    p.slab_slots = 128 + 2 * (tin.PW + 1);
+    groups.resize(4);
+    block_kt.resize(4);
+    for (int cls = 0; cls < 4; ++cls) {
+      const int ph = cls >> 1, pw = cls & 1;
+      // (offset, k) pairs per axis, in increasing offset order
+      int offh[2], kh[2], offw[2], kw[2];
+      if (ph == 0) { offh[0] = -1; kh[0] = 3; offh[1] = 0; kh[1] = 1; } else { offh[0] = 0; kh[0] = 2; offh[1] = 1; kh[1] = 0; }
+      if (pw == 0) { offw[0] = -1; kw[0] = 3; offw[1] = 0; kw[1] = 1; } else { offw[0] = 0; kw[0] = 2; offw[1] = 1; kw[1] = 0; }
+      for (int g = 0; g < G; ++g)
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b)
+            groups[cls].push_back({(uint32_t)(g * p.slab_slots * 16 + ((tin.PW + 1) + offh[a] * tin.PW + offw[b]) * 16),
+                                   0, kh[a], kw[b], g * 8});
+      block_kt[cls] = {0, 1, 2, 3};
+    }
+    p.N = 96;
+  }
+  p.nvar = (int)groups.size();
+  const int ngroups = (int)groups[0].size();
+  p.nks = (ngroups + 1) / 2;
+  if (p.nks > kMaxKs || p.nvar > kMaxVar) {
+    lc_set_error("layer %d: %d K steps / %d variants exceed the kernel tables", i, p.nks, p.nvar);
+    return LC_EUNSUPPORTED;
+  }
+  const size_t var_elems = (size_t)p.nks * 2 * p.N * 8;
+  std::vector<unsigned short> img(var_elems * p.nvar, 0);
+  for (int var = 0; var < p.nvar; ++var) {
+    p.b_base[var] = (uint32_t)(var * var_elems * 2);
+    for (int ks = 0; ks < p.nks; ++ks) {
+      const int g0 = 2 * ks, g1 = (2 * ks + 1 < ngroups) ? 2 * ks + 1 : 2 * ks;
+      if (groups[var][g1].a_addr < groups[var][g0].a_addr) {
+        lc_set_error("layer %d: K groups are not address ordered", i);
+        return LC_EINVAL;
+      }
+      p.a_off[var][ks] = groups[var][g0].a_addr;
+      p.a_lbo[var][ks] = groups[var][g1].a_addr - groups[var][g0].a_addr;
+    }
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const KGroup& kg = groups[var][gi];
+      for (int n = 0; n < p.N; ++n) {
+        const int blk = n / block_cols, co = n % block_cols;
+        if (blk >= (int)block_kt[var].size() || co >= cout) continue;
+        const int kt = block_kt[var][blk];
+        for (int k8 = 0; k8 < 8; ++k8) {
+          int kh = kg.tap_h, kw = kg.tap_w, ci = kg.ci0 + k8;
+          if (mode == MODE_K4) {   // pseudo-channel -> (dw, ci)
+            kw = ci / cin;
+            ci = ci - kw * cin;
+            if (kw >= k) continue;
+          }
+          if (ci >= cin) continue;
+          const float v = w16[((size_t)((kt * k + kh) * k + kw) * cin + ci) * cout + co];
+          img[var * var_elems + ((size_t)gi * p.N + n) * 8 + k8] = to_h16_host(v, half);
+        }
+      }
+    }
+  }
+  p.wimg_bytes = (int)(img.size() * 2);
+  LC_CUDA(cudaMalloc(&L.d_wtc, img.size() * 2));
+  LC_CUDA(cudaMemcpy(L.d_wtc, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  L.wtc_bytes = img.size() * 2;
+  p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
+  const int stage_bytes = p.in_NPG * p.slab_slots * 16;
+  const int budget = ((mode == MODE_K3) ? 100 : 200) * 1024;
+  const int fixed = ((p.wimg_bytes + 127) & ~127) + 256;
+  int stages = (budget - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    lc_set_error("layer %d: tensor-core kernel does not fit shared memory (%d + n*%d)", i, fixed, stage_bytes);
+    return LC_EUNSUPPORTED;
+  }
+  p.stages = stages;
+  lp.smem_bytes = fixed + stages * stage_bytes;
+  lp.backend = mode;
+  (void)tout;
+  return LC_OK;
+}
 
 int tc_prepare(lc_codec* h) {
   h->tc_plan = nullptr;
@@ -347,14 +799,22 @@ int tc_prepare(lc_codec* h) {
   const int half = (h->precision == LC_PREC_FP16) ? 1 : 0;
   TcPlan* P = new TcPlan();
   memset(P, 0, sizeof(*P));
+  h->tc_plan = P;
   const int nl = h->n_enc + h->n_dec;
   P->n_layers = nl;
+  std::vector<int> mode(nl);
+  for (int i = 0; i < nl; ++i) mode[i] = tc_mode_of(h, i);
   long long off = 0;
   auto place = [&](TensorPlan& t) {
     t.offset_vecs = off;
     off += (t.size_vecs + 7) & ~7LL;
   };
-  P->in_enc = make_f32(CT, CH, CW, h->in_channels);
+  if (mode[0] == MODE_K4) {
+    P->in_enc = make_wfold(CT, CH, CW, h->in_channels, h->layers[0].k, h->layers[0].pad_lo);
+    P->wfold_k = h->layers[0].k;
+  } else {
+    P->in_enc = make_f32(CT, CH, CW, h->in_channels);
+  }
   place(P->in_enc);
   for (int i = 0; i < nl; ++i) {
     const DevLayer& L = h->layers[i];
@@ -364,9 +824,10 @@ int tc_prepare(lc_codec* h) {
     } else {
       const DevLayer& Nx = h->layers[i + 1];
       const int pad_hi = (Nx.kind == 0 && Nx.stride == 1) ? (Nx.k - 1 - Nx.pad_lo) : 1;
-      P->out[i] = make_gp(L.out_t, L.out_h, L.out_w, L.cout, pad_hi < 1 ? 1 : pad_hi);
+      const int layout = (mode[i + 1] == MODE_DOWN) ? LAYOUT_PARITY : LAYOUT_PLAIN;
+      P->out[i] = make_gp(L.out_t, L.out_h, L.out_w, L.cout, pad_hi < 1 ? 1 : pad_hi, layout);
     }
-    if (!last_enc) place(P->out[i]);   // the latent goes straight to the caller's buffer
+    if (!last_enc && !(last_dec && mode[i] == MODE_K4_OUT1)) place(P->out[i]);
   }
   P->block_vecs = (off + 63) & ~63LL;
 
@@ -380,59 +841,12 @@ int tc_prepare(lc_codec* h) {
     LC_CUDA(cudaMalloc(&lp.d_w16, w16.size() * sizeof(float)));
     LC_CUDA(cudaMemcpy(lp.d_w16, w16.data(), w16.size() * sizeof(float), cudaMemcpyHostToDevice));
     lp.backend = 0;
-    const bool in_is_gp = (i != 0) && (i != h->n_enc);
-    const bool out_is_gp = P->out[i].fmt == FMT_GP16;
-    if (tc_conv3_eligible(L) && in_is_gp && out_is_gp && !getenv("LOSSYCOMP_NO_TC")) {
-      const TensorPlan& tin = P->out[i - 1];
-      const TensorPlan& tout = P->out[i];
-      TcParams& p = lp.tc;
-      p.in_S = tin.S; p.in_GL = tin.GL; p.in_PW = tin.PW;
-      p.out_S = tout.S; p.out_GL = tout.GL; p.out_PW = tout.PW;
-      p.G = tin.G; p.T = L.in_t; p.H = L.in_h; p.W = L.in_w;
-      p.cout = L.cout; p.relu = L.relu; p.half = half;
-      p.bias = L.d_b;
-      p.N = 80;
-      p.tiles_per_chunk = (L.in_h * tin.PW + 127) / 128;
-      p.slab_slots = 128 + 2 * (tin.PW + 1);
-      // K groups, group-major so that operand addresses increase: (g, dh, dw)
-      const int ngroups = p.G * 9;
-      p.nks = (ngroups + 1) / 2;
-      auto addr = [&](int gi) {
-        const int g = gi / 9, tap = gi % 9, dh = tap / 3, dw = tap % 3;
-        return (uint32_t)(g * p.slab_slots * 16 + (dh * tin.PW + dw) * 16);
-      };
-      for (int ks = 0; ks < p.nks; ++ks) {
-        const int g0 = 2 * ks, g1 = (2 * ks + 1 < ngroups) ? 2 * ks + 1 : 2 * ks;
-        p.a_off[ks] = addr(g0);
-        p.a_lbo[ks] = addr(g1) - addr(g0);
-      }
-      // weight image [ks][khalf][n][8]; n = dt*24 + co
-      std::vector<unsigned short> img((size_t)p.nks * 2 * p.N * 8, 0);
-      for (int gi = 0; gi < ngroups; ++gi) {
-        const int g = gi / 9, tap = gi % 9, dh = tap / 3, dw = tap % 3;
-        for (int n = 0; n < p.N; ++n) {
-          const int dt = n / 24, co = n % 24;
-          if (dt >= 3 || co >= L.cout) continue;
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const int ci = g * 8 + k8;
-            if (ci >= L.cin) continue;
-            const float v = w16[((size_t)((dt * 3 + dh) * 3 + dw) * L.cin + ci) * L.cout + co];
-            unsigned short u;
-            if (half) { __half hv = __float2half_rn(v); memcpy(&u, &hv, 2); }
-            else { __nv_bfloat16 bv = __float2bfloat16_rn(v); memcpy(&u, &bv, 2); }
-            img[((size_t)gi * p.N + n) * 8 + k8] = u;
-          }
-        }
-      }
-      p.wimg_bytes = (int)(img.size() * 2);
-      LC_CUDA(cudaMalloc(&L.d_wtc, img.size() * 2));
-      LC_CUDA(cudaMemcpy(L.d_wtc, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-      L.wtc_bytes = img.size() * 2;
-      p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
-      lp.backend = 1;
+    if (mode[i]) {
+      const TensorPlan& tin = (i == 0) ? P->in_enc : P->out[i - 1];
+      int rc = build_sweep(h, P, i, mode[i], tin, P->out[i], w16, half);
+      if (rc != LC_OK) return rc;
     }
   }
-  h->tc_plan = P;
   return LC_OK;
 }
 
@@ -457,35 +871,44 @@ int tc_backend_of(const lc_codec* h, int layer) {
 }
 
 static int tc_run(lc_codec* h, int first, int count, const ActView& first_in, void* block_base, int n_chunks,
-                  float* latent_out, cudaStream_t s) {
+                  float* latent_out, float* recon_out, const ChunkGeom* geom, int chunk_begin, cudaStream_t s) {
   TcPlan* P = plan_of(h);
   const int half = (h->precision == LC_PREC_FP16) ? 1 : 0;
   ActView cur = first_in;
-  const TensorPlan* cur_t = nullptr;
-  const TensorPlan* skip_t = nullptr;
   ActView skip_v;
+  memset(&skip_v, 0, sizeof(skip_v));
   for (int i = first; i < first + count; ++i) {
     DevLayer& L = h->layers[i];
     LayerPlan& lp = P->layer[i];
     ActView out;
+    memset(&out, 0, sizeof(out));
     if (i == h->n_enc - 1) {   // latent: contiguous fp32 in the caller's buffer
       out = f32_view(L, true, latent_out);
-    } else {
+    } else if (lp.backend != MODE_K4_OUT1) {
       out = view_of(P->out[i], block_base, P->block_vecs, half);
     }
     prof_begin(h, i, s);
     int rc;
-    if (lp.backend == 1) {
-      rc = launch_conv3_tc(h, lp, *cur_t, P->out[i], L.res_add ? skip_t : nullptr, block_base, P->block_vecs,
-                           n_chunks, s);
+    if (lp.backend) {
+      SweepParams p = lp.sp;
+      p.in = reinterpret_cast<const uint4*>(cur.base);
+      p.in_cs = cur.chunk_stride;
+      p.out = out;
+      if (L.res_add) p.skip = skip_v;
+      p.n_items = n_chunks * p.tiles_per_chunk * p.n_classes;
+      if (lp.backend == MODE_K4_OUT1) {
+        p.out_f32 = recon_out;
+        p.geom = *geom;
+        p.chunk_begin = chunk_begin;
+      }
+      rc = launch_sweep(h, lp, p, s);
     } else {
       rc = conv_direct_views(h, L, lp.d_w16, cur, out, L.res_add ? &skip_v : nullptr, n_chunks, s);
     }
     prof_end(h, s);
     if (rc != LC_OK) return rc;
-    if (L.res_save) { skip_v = out; skip_t = &P->out[i]; }
+    if (L.res_save) skip_v = out;
     cur = out;
-    cur_t = &P->out[i];
   }
   return LC_OK;
 }
@@ -495,22 +918,30 @@ int tc_encode(lc_codec* h, const float* d_x, const ChunkGeom& g, int C, float me
   TcPlan* P = plan_of(h);
   const int half = (h->precision == LC_PREC_FP16) ? 1 : 0;
   ActView in = view_of(P->in_enc, d_ws, P->block_vecs, half);
-  gather_blocks_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count,
-                                                      reinterpret_cast<float*>(in.base), in.chunk_stride);
+  if (P->in_enc.fmt == FMT_F32) {
+    gather_blocks_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count,
+                                                        reinterpret_cast<float*>(in.base), in.chunk_stride);
+  } else {
+    gather_wfold_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count, in,
+                                                       P->wfold_k, h->layers[0].pad_lo);
+  }
   LC_LAUNCH_CHECK();
-  return tc_run(h, 0, h->n_enc, in, d_ws, chunk_count, d_latent, s);
+  return tc_run(h, 0, h->n_enc, in, d_ws, chunk_count, d_latent, nullptr, nullptr, 0, s);
 }
 
 int tc_decode(lc_codec* h, const float* d_latent, const ChunkGeom& g, int chunk_begin, int chunk_count,
               float* d_recon, void* d_ws, cudaStream_t s) {
   TcPlan* P = plan_of(h);
   const int half = (h->precision == LC_PREC_FP16) ? 1 : 0;
+  const int last = h->n_enc + h->n_dec - 1;
   ActView in = f32_view(h->layers[h->n_enc], false, d_latent);
-  int rc = tc_run(h, h->n_enc, h->n_dec, in, d_ws, chunk_count, nullptr, s);
+  int rc = tc_run(h, h->n_enc, h->n_dec, in, d_ws, chunk_count, nullptr, d_recon, &g, chunk_begin, s);
   if (rc != LC_OK) return rc;
-  ActView out = view_of(P->out[h->n_enc + h->n_dec - 1], d_ws, P->block_vecs, half);
-  merge_blocks_kernel<<<h->num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float*>(out.base), out.chunk_stride,
-                                                     g, chunk_begin, chunk_count, d_recon);
-  LC_LAUNCH_CHECK();
+  if (P->layer[last].backend != MODE_K4_OUT1) {
+    ActView out = view_of(P->out[last], d_ws, P->block_vecs, half);
+    merge_blocks_kernel<<<h->num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float*>(out.base), out.chunk_stride,
+                                                       g, chunk_begin, chunk_count, d_recon);
+    LC_LAUNCH_CHECK();
+  }
   return LC_OK;
 }
