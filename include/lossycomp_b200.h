@@ -140,6 +140,11 @@ int lc_verify_bound(const float* d_x, int C, const float* d_xhat, int64_t n_vox,
  * Symbols are bytes (mask stream: packed trits; code stream: clipped first differences with
  * escapes).  Histogram is warp-aggregated in shared memory; d_hist is 256 x uint32. */
 int lc_hist_u8(const uint8_t* d_sym, int64_t n, uint32_t* d_hist, void* stream);
+/* Histograms of both candidate symbolisations of the int32 code stream in one pass:
+ * d_hist[0..255] of (q + bias0), d_hist[256..511] of (q[i]-q[i-1] + bias1); values outside
+ * [0, esc) are counted under `esc`. */
+int lc_hist_codes(const int32_t* d_q, int64_t n, int esc, int bias0, int bias1, uint32_t* d_hist,
+                  void* stream);
 /* Map the int32 code stream (optionally first-differenced on the fly) to byte symbols:
  * sym = v + bias if 0 <= v+bias < esc else esc; escaped values go to d_esc in order. */
 int lc_symbolize_i32(const int32_t* d_q, int64_t n, int diff, int bias, int esc, uint8_t* d_sym,

@@ -167,6 +167,109 @@ __global__ void __launch_bounds__(512, 1) conv_direct_kernel(ConvParams p) {
   }
 }
 
+// Small layers (the innermost levels: <= 128 output voxels per chunk): one warp per output voxel,
+// lane = output channel.  Weights are read straight from L2 (coalesced over cout), the input value is
+// a warp-wide broadcast; no shared-memory staging of the whole kernel per CTA, which is what made
+// the big-tile kernel latency-bound here.  Same arithmetic: fp32 FMA, taps in (kt,kh,kw,ci) order.
+__global__ void __launch_bounds__(256) conv_small_kernel(ConvParams p) {
+  const int lane = threadIdx.x & 31;
+  const int OT = p.out.T, OH = p.out.H, OW = p.out.W;
+  const int IT = p.in.T, IH = p.in.H, IW = p.in.W;
+  const int ovox = OT * OH * OW;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long v = warp0; v < p.total_vox; v += nwarps) {
+    const int chunk = (int)(v / ovox);
+    int r = (int)(v % ovox);
+    const int ow = r % OW;
+    r /= OW;
+    const int oh = r % OH;
+    const int ot = r / OH;
+    const int co = lane;
+    float acc = (co < p.cout) ? p.b[co] : 0.f;
+    for (int kt = 0; kt < p.k; ++kt) {
+      int it;
+      if (p.kind == 0) {
+        it = ot * p.stride + kt - p.pad_lo;
+      } else {
+        const int num = ot + p.pad_lo - kt;
+        if (num < 0 || (num % p.stride) != 0) continue;
+        it = num / p.stride;
+      }
+      if (it < 0 || it >= IT) continue;
+      for (int kh = 0; kh < p.k; ++kh) {
+        int ih;
+        if (p.kind == 0) {
+          ih = oh * p.stride + kh - p.pad_lo;
+        } else {
+          const int num = oh + p.pad_lo - kh;
+          if (num < 0 || (num % p.stride) != 0) continue;
+          ih = num / p.stride;
+        }
+        if (ih < 0 || ih >= IH) continue;
+        for (int kw = 0; kw < p.k; ++kw) {
+          int iw;
+          if (p.kind == 0) {
+            iw = ow * p.stride + kw - p.pad_lo;
+          } else {
+            const int num = ow + p.pad_lo - kw;
+            if (num < 0 || (num % p.stride) != 0) continue;
+            iw = num / p.stride;
+          }
+          if (iw < 0 || iw >= IW) continue;
+          const float* wt = p.w + (size_t)((kt * p.k + kh) * p.k + kw) * p.cin * p.cout;
+          if (p.in.fmt == FMT_F32) {
+            const float* xin = reinterpret_cast<const float*>(p.in.base) + (size_t)chunk * p.in.chunk_stride +
+                               ((size_t)(it * IH + ih) * IW + iw) * p.cin;
+            for (int ci = 0; ci < p.cin; ++ci) {
+              const float x = __ldg(xin + ci);
+              const float w = (co < p.cout) ? __ldg(wt + (size_t)ci * p.cout + co) : 0.f;
+              acc = fmaf(x, w, acc);
+            }
+          } else {
+            const uint4* xin = reinterpret_cast<const uint4*>(p.in.base);
+            for (int g = 0; g < p.in.G; ++g) {
+              float f[8];
+              unpack8(__ldg(xin + gp_vec_index(p.in, chunk, it, ih, iw, g)), p.in.half, f);
+#pragma unroll
+              for (int k8 = 0; k8 < 8; ++k8) {
+                const int ci = g * 8 + k8;
+                if (ci < p.cin) {
+                  const float w = (co < p.cout) ? __ldg(wt + (size_t)ci * p.cout + co) : 0.f;
+                  acc = fmaf(f[k8], w, acc);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // epilogue: lane = channel
+    if (p.skip.base) {
+      float sk = 0.f;
+      if (p.skip.fmt == FMT_F32) {
+        if (co < p.cout)
+          sk = reinterpret_cast<const float*>(p.skip.base)[(size_t)chunk * p.skip.chunk_stride +
+                                                           (size_t)(v % ovox) * p.cout + co];
+      } else if (co < p.skip.G * 8) {
+        const unsigned short* sp = reinterpret_cast<const unsigned short*>(
+            reinterpret_cast<const uint4*>(p.skip.base) + gp_vec_index(p.skip, chunk, ot, oh, ow, co >> 3));
+        sk = h16_to_float(sp[co & 7], p.skip.half);
+      }
+      acc = __fadd_rn(acc, sk);
+    }
+    if (p.relu) acc = fmaxf(acc, 0.f);
+    if (p.out.fmt == FMT_F32) {
+      if (co < p.cout)
+        reinterpret_cast<float*>(p.out.base)[(size_t)chunk * p.out.chunk_stride + (size_t)(v % ovox) * p.cout + co] = acc;
+    } else if (co < p.out.G * 8) {
+      unsigned short* op = reinterpret_cast<unsigned short*>(
+          reinterpret_cast<uint4*>(p.out.base) + gp_vec_index(p.out, chunk, ot, oh, ow, co >> 3));
+      op[co & 7] = float_to_h16(co < p.cout ? acc : 0.f, p.out.half);
+    }
+  }
+}
+
 template <int CO4>
 int launch(const ConvParams& p, int num_sms, cudaStream_t s) {
   const size_t smem = (size_t)p.k * p.k * p.k * p.cin * CO4 * 4 * sizeof(float);
@@ -208,6 +311,15 @@ int conv_direct_views(const lc_codec* h, const DevLayer& L, const float* d_w, co
   p.kind = L.kind; p.k = L.k; p.stride = L.stride; p.cin = L.cin; p.cout = L.cout;
   p.relu = L.relu; p.pad_lo = L.pad_lo;
   p.total_vox = (long long)n_chunks * L.out_t * L.out_h * L.out_w;
+  if (L.out_t * L.out_h * L.out_w <= 128 && L.cout <= 32 && (out.fmt == FMT_F32 || out.G * 8 <= 32) &&
+      !getenv("LOSSYCOMP_NO_SMALL")) {
+    long long blocks = (p.total_vox + 7) / 8;
+    if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+    if (blocks < 1) blocks = 1;
+    conv_small_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+    LC_LAUNCH_CHECK();
+    return LC_OK;
+  }
   const int co4 = (L.cout + 3) / 4;
   switch (co4) {
     case 1: return launch<1>(p, h->num_sms, s);

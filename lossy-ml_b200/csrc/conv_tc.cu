@@ -55,6 +55,7 @@ struct SweepParams {
   // row numbering of a tile: row r of tile j is slot row0 + 128*j + r of a pitch-row_PW image;
   // (hp, wp) = divmod(slot, row_PW); voxel = (hp - row_off, wp - row_off), valid inside [0,H)x[0,W)
   int row_PW, row0, row_off_h, row_off_w, rows_H, rows_W;
+  int row_step, row_shift;       // tile j, row r -> slot row0 + row_step*j + r - row_shift (overlapping tiles)
   int tiles_per_chunk, n_items, n_classes;
   int slab_slots, slab_start;    // the stage holds slots [row0 + 128*j + slab_start, +slab_slots) of every plane
   int stages;
@@ -94,7 +95,7 @@ __device__ __forceinline__ RowInfo row_info(const SweepParams& p, int item, int 
   const int rem = item - r.n * per_chunk;
   r.cls = rem / p.tiles_per_chunk;
   const int tile = rem - r.cls * p.tiles_per_chunk;
-  const int slot = p.row0 + tile * 128 + row;
+  const int slot = p.row0 + tile * p.row_step + row - p.row_shift;
   const int hp = slot / p.row_PW, wp = slot - hp * p.row_PW;
   r.h = hp - p.row_off_h;
   r.w = wp - p.row_off_w;
@@ -103,14 +104,28 @@ __device__ __forceinline__ RowInfo row_info(const SweepParams& p, int item, int 
 }
 
 // y = acc + bias (+ skip) -> ReLU -> 16-bit -> out(n, t, h, w)
-__device__ __forceinline__ void store_voxel(const SweepParams& p, const float* s_bias, int n, int t, int h, int w,
+struct VoxAddr {
+  long long o0, s0;     // vector index of (n, t=0, h, w, g=0) in the output / skip tensor
+  int o_t, s_t;         // vectors per time plane
+};
+
+__device__ __forceinline__ VoxAddr vox_addr(const SweepParams& p, int n, int h, int w) {
+  VoxAddr a;
+  a.o0 = gp_vec_index(p.out, n, 0, h, w, 0);
+  a.o_t = p.out.NP * p.out.G * p.out.S;
+  a.s0 = p.skip.base ? gp_vec_index(p.skip, n, 0, h, w, 0) : 0;
+  a.s_t = p.skip.NP * p.skip.G * p.skip.S;
+  return a;
+}
+
+__device__ __forceinline__ void store_voxel(const SweepParams& p, const float* s_bias, const VoxAddr& va, int t,
                                             const float (&acc)[24]) {
   float y[24];
 #pragma unroll
   for (int c = 0; c < 24; ++c) y[c] = acc[c] + s_bias[c];
   if (p.skip.base) {
     const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base);
-    const long long si = gp_vec_index(p.skip, n, t, h, w, 0);
+    const long long si = va.s0 + (long long)t * va.s_t;
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
       float f[8];
@@ -120,7 +135,7 @@ __device__ __forceinline__ void store_voxel(const SweepParams& p, const float* s
     }
   }
   uint4* o = reinterpret_cast<uint4*>(p.out.base);
-  const long long oi = gp_vec_index(p.out, n, t, h, w, 0);
+  const long long oi = va.o0 + (long long)t * va.o_t;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
     float f[8];
@@ -141,12 +156,20 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2], wbar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[24];
+  __shared__ __align__(8) uint64_t s_da[kMaxVar * kMaxKs], s_db[kMaxVar * kMaxKs];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab_bytes = p.slab_slots * 16;
   const int stage_bytes = p.in_NPG * slab_bytes;
   uint8_t* sB = smem;
   uint8_t* sA = smem + ((p.wimg_bytes + 127) & ~127);
+  // operand descriptors of every (variant, K step) for stage 0; the issuer adds the stage offset
+  for (int i = threadIdx.x; i < p.nvar * p.nks; i += blockDim.x) {
+    const int var = i / p.nks, ks = i - var * p.nks;
+    s_da[var * kMaxKs + ks] = umma::make_desc(umma::smem_u32(sA) + p.a_off[var][ks], p.a_lbo[var][ks], 128);
+    s_db[var * kMaxKs + ks] =
+        umma::make_desc(umma::smem_u32(sB) + p.b_base[var] + ks * (2u * p.N * 16u), p.N * 16u, 128);
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
@@ -171,7 +194,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int n = item / per_chunk;
         const int tile = (item - n * per_chunk) % p.tiles_per_chunk;
-        const long long slab0 = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * 128 + p.slab_start;
+        const long long slab0 = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start;
         for (int t = 0; t < p.in_T; ++t) {
           umma::mbar_wait(&empty[stage], phase ^ 1);
           umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
@@ -188,8 +211,6 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
     if (lane == 0) {
       umma::mbar_wait(&wbar, 0);
       const uint32_t idesc = umma::make_idesc(128, p.N, p.half ? 0 : 1);
-      const uint32_t sA_u = umma::smem_u32(sA), sB_u = umma::smem_u32(sB);
-      const uint32_t kstep_bytes = 2u * p.N * 16u;
       int stage = 0, phase = 0, it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int var = 0;
@@ -197,16 +218,19 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
         for (int t = 0; t < p.in_T; ++t, ++it) {
           if (MODE == MODE_DOWN) var = t & 1;
           const int buf = it & 1;
+          const uint64_t* da = s_da + var * kMaxKs;
+          const uint64_t* db = s_db + var * kMaxKs;
+          const uint64_t stage_add = (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
+          uint64_t da_n = da[0] + stage_add, db_n = db[0];
           umma::mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
           umma::mbar_wait(&full[stage], phase);
           umma::tcgen05_fence_after();
-          const uint32_t a_base = sA_u + stage * stage_bytes;
-          const uint32_t b_base = sB_u + p.b_base[var];
           const uint32_t d_addr = tmem + buf * kAccStride;
+#pragma unroll 2
           for (int ks = 0; ks < p.nks; ++ks) {
-            const uint64_t da = umma::make_desc(a_base + p.a_off[var][ks], p.a_lbo[var][ks], 128);
-            const uint64_t db = umma::make_desc(b_base + ks * kstep_bytes, p.N * 16u, 128);
-            umma::mma_f16(d_addr, da, db, idesc, ks > 0);
+            const uint64_t a = da_n, b = db_n;
+            if (ks + 1 < p.nks) { da_n = da[ks + 1] + stage_add; db_n = db[ks + 1]; }
+            umma::mma_f16(d_addr, a, b, idesc, ks > 0);
           }
           umma::commit(&empty[stage]);
           umma::commit(&tfull[buf]);
@@ -235,6 +259,9 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const RowInfo ri = row_info(p, item, row);
+      VoxAddr va;
+      if (MODE == MODE_UP) va = vox_addr(p, ri.n, 2 * ri.h + (ri.cls >> 1), 2 * ri.w + (ri.cls & 1));
+      else if (MODE != MODE_K4_OUT1) va = vox_addr(p, ri.n, ri.h, ri.w);
       if (MODE == MODE_K3) {
         // block dt -> output plane t_in - dt + 1
         float aP[24], aC[24], aN[24], d[24];
@@ -252,11 +279,11 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 #pragma unroll
           for (int c = 0; c < 24; ++c) aP[c] += d[c];
           release_d();
-          if (t >= 1 && ri.valid) store_voxel(p, s_bias, ri.n, t - 1, ri.h, ri.w, aP);
+          if (t >= 1 && ri.valid) store_voxel(p, s_bias, va, t - 1, aP);
 #pragma unroll
           for (int c = 0; c < 24; ++c) { aP[c] = aC[c]; aC[c] = aN[c]; }
         }
-        if (ri.valid) store_voxel(p, s_bias, ri.n, p.in_T - 1, ri.h, ri.w, aP);
+        if (ri.valid) store_voxel(p, s_bias, va, p.in_T - 1, aP);
       } else if (MODE == MODE_K4) {
         // k=4, pad 1/2: block dt -> output plane t_in - dt + 1  (planes t+1, t, t-1, t-2)
         float a1[24], a2[24], a3[24], a0[24], d[24];
@@ -277,24 +304,29 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 #pragma unroll
           for (int c = 0; c < 24; ++c) a3[c] += d[c];
           release_d();
-          if (t >= 2 && ri.valid) store_voxel(p, s_bias, ri.n, t - 2, ri.h, ri.w, a3);
+          if (t >= 2 && ri.valid) store_voxel(p, s_bias, va, t - 2, a3);
 #pragma unroll
           for (int c = 0; c < 24; ++c) { a3[c] = a2[c]; a2[c] = a1[c]; a1[c] = a0[c]; }
         }
         if (ri.valid) {
-          store_voxel(p, s_bias, ri.n, p.in_T - 2, ri.h, ri.w, a3);
-          store_voxel(p, s_bias, ri.n, p.in_T - 1, ri.h, ri.w, a2);
+          store_voxel(p, s_bias, va, p.in_T - 2, a3);
+          store_voxel(p, s_bias, va, p.in_T - 1, a2);
         }
-      } else if (MODE == MODE_K4_OUT1) {
-        // cout = 1: column dt*4 holds the contribution to plane t_in - dt + 1; fp32 output is
-        // scattered into the merged (T,H,W) field, keeping only what merge_data keeps of this chunk
-        float a0, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      } else if constexpr (MODE == MODE_K4_OUT1) {
+        // cout = 1, taps dt and dw folded into N: column dt*4+dw of row r is the contribution of input
+        // column w_r to output plane t_in-dt+1 at w_r-(dw-1).  The w shift crosses lanes, so the 16
+        // values of every row go through a padded shared-memory tile; rows 1..125 of a tile are outputs
+        // (tiles overlap by 3 rows).  fp32 output is scattered straight into the merged (T,H,W) field,
+        // keeping only what merge_data keeps of this chunk.
+        __shared__ float xch[2][128][17];
+        float a0[1], a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int t0, h0, w0, kt, kh, kw;
         p.geom.origin(p.chunk_begin + ri.n, t0, h0, w0);
         p.geom.keep_from(p.chunk_begin + ri.n, kt, kh, kw);
-        const bool keep_hw = ri.valid && ri.h >= kh && ri.w >= kw;
+        const bool keep_hw = ri.valid && row >= 1 && row <= p.row_step && ri.h >= kh && ri.w >= kw;
         float* dst = p.out_f32 + ((size_t)t0 * p.geom.H + (h0 + ri.h)) * p.geom.W + (w0 + ri.w);
         const size_t plane = (size_t)p.geom.H * p.geom.W;
+        const int rm = max(row - 1, 0), rp1 = min(row + 1, 127), rp2 = min(row + 2, 127);
         auto emit = [&](int t, float acc) {
           if (keep_hw && t >= kt) {
             float y = acc + s_bias[0];
@@ -309,12 +341,20 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           umma::tmem_ld8(ta + 8, v1);
           umma::tmem_ld_wait();
           release_d();
-          a0 = __uint_as_float(v0[0]);
-          a1 += __uint_as_float(v0[4]);
-          a2 += __uint_as_float(v1[0]);
-          a3 += __uint_as_float(v1[4]);
+          float (*x)[17] = xch[t & 1];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { x[row][k] = __uint_as_float(v0[k]); x[row][8 + k] = __uint_as_float(v1[k]); }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float s[4];
+#pragma unroll
+          for (int dt = 0; dt < 4; ++dt)
+            s[dt] = ((x[rm][dt * 4 + 0] + x[row][dt * 4 + 1]) + x[rp1][dt * 4 + 2]) + x[rp2][dt * 4 + 3];
+          a0[0] = s[0];
+          a1 += s[1];
+          a2 += s[2];
+          a3 += s[3];
           if (t >= 2) emit(t - 2, a3);
-          a3 = a2; a2 = a1; a1 = a0;
+          a3 = a2; a2 = a1; a1 = a0[0];
         }
         emit(p.in_T - 2, a3);
         emit(p.in_T - 1, a2);
@@ -343,16 +383,14 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
             for (int c = 0; c < 24; ++c) aO[c] += d[c];
             release_d();
             const int m = t >> 1;
-            if (m >= 1 && ri.valid) store_voxel(p, s_bias, ri.n, m - 1, ri.h, ri.w, aO);
+            if (m >= 1 && ri.valid) store_voxel(p, s_bias, va, m - 1, aO);
 #pragma unroll
             for (int c = 0; c < 24; ++c) aO[c] = aN[c];
           }
         }
-        if (ri.valid) store_voxel(p, s_bias, ri.n, p.out_T - 1, ri.h, ri.w, aO);
+        if (ri.valid) store_voxel(p, s_bias, va, p.out_T - 1, aO);
       } else if (MODE == MODE_UP) {
         // output plane 2*t_in + kt - 1; block kt.  Planes 2t-1 and 2t complete at step t.
-        const int ph = ri.cls >> 1, pw = ri.cls & 1;
-        const int oh = 2 * ri.h + ph, ow = 2 * ri.w + pw;
         float cX[24], cY[24], d[24];
 #pragma unroll
         for (int c = 0; c < 24; ++c) { cX[c] = 0.f; cY[c] = 0.f; }
@@ -361,16 +399,16 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           ld_cols24(ta, d);
 #pragma unroll
           for (int c = 0; c < 24; ++c) cX[c] += d[c];
-          if (t >= 1 && ri.valid) store_voxel(p, s_bias, ri.n, 2 * t - 1, oh, ow, cX);
+          if (t >= 1 && ri.valid) store_voxel(p, s_bias, va, 2 * t - 1, cX);
           ld_cols24(ta + 24, d);
 #pragma unroll
           for (int c = 0; c < 24; ++c) cY[c] += d[c];
-          if (ri.valid) store_voxel(p, s_bias, ri.n, 2 * t, oh, ow, cY);
+          if (ri.valid) store_voxel(p, s_bias, va, 2 * t, cY);
           ld_cols24(ta + 48, cX);
           ld_cols24(ta + 72, cY);
           release_d();
         }
-        if (ri.valid) store_voxel(p, s_bias, ri.n, 2 * p.in_T - 1, oh, ow, cX);
+        if (ri.valid) store_voxel(p, s_bias, va, 2 * p.in_T - 1, cX);
       }
     }
   }
@@ -657,7 +695,8 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   std::vector<std::vector<KGroup>> groups;       // [variant][group]
   std::vector<std::vector<int>> block_kt;        // [variant][block] -> kt (or -1)
   int block_cols = 24;
-  if (mode == MODE_K3 || mode == MODE_K4_OUT1) {
+  p.row_step = 128; p.row_shift = 0;
+  if (mode == MODE_K3) {
     // plain input; rows follow the input's padded numbering; taps (dh,dw) -> slab offset dh*PW+dw
     p.row_PW = tin.PW; p.row0 = tin.PW; p.row_off_h = 1; p.row_off_w = 1;
     p.rows_H = L.in_h; p.rows_W = L.in_w;
@@ -671,7 +710,22 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
           groups[0].push_back({(uint32_t)(g * p.slab_slots * 16 + (dh * tin.PW + dw) * 16), 0, dh, dw, g * 8});
     block_kt.resize(1);
     for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
-    if (mode == MODE_K4_OUT1) { block_cols = 4; p.N = 16; } else { p.N = 80; }
+    p.N = 80;
+  } else if (mode == MODE_K4_OUT1) {
+    // plain input; taps dh only (dt and dw are folded into N = 4x4); tiles advance by 125 rows
+    p.row_PW = tin.PW; p.row0 = tin.PW; p.row_off_h = 1; p.row_off_w = 1;
+    p.rows_H = L.in_h; p.rows_W = L.in_w;
+    p.row_step = 125; p.row_shift = 1;
+    p.tiles_per_chunk = (L.in_h * tin.PW + p.row_step - 1) / p.row_step;
+    p.slab_start = -tin.PW;
+    p.slab_slots = 128 + (k - 1) * tin.PW;
+    groups.resize(1);
+    for (int g = 0; g < G; ++g)
+      for (int dh = 0; dh < k; ++dh)
+        groups[0].push_back({(uint32_t)(g * p.slab_slots * 16 + dh * tin.PW * 16), 0, dh, -2, g * 8});
+    block_kt.resize(1);
+    for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
+    block_cols = 4; p.N = 16;
   } else if (mode == MODE_K4) {
     // w-folded input (pitch W, no halo columns): taps dh only, pseudo-channel pc = dw*cin + ci
     p.row_PW = tin.PW; p.row0 = L.pad_lo * tin.PW; p.row_off_h = L.pad_lo; p.row_off_w = 0;
@@ -755,7 +809,9 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     for (int gi = 0; gi < ngroups; ++gi) {
       const KGroup& kg = groups[var][gi];
       for (int n = 0; n < p.N; ++n) {
-        const int blk = n / block_cols, co = n % block_cols;
+        const int blk = n / block_cols;
+        int co = n % block_cols, kw_fold = -1;
+        if (mode == MODE_K4_OUT1) { kw_fold = co; co = 0; }      // column = dt*4 + dw, single output channel
         if (blk >= (int)block_kt[var].size() || co >= cout) continue;
         const int kt = block_kt[var][blk];
         for (int k8 = 0; k8 < 8; ++k8) {
@@ -765,6 +821,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
             ci = ci - kw * cin;
             if (kw >= k) continue;
           }
+          if (kw_fold >= 0) kw = kw_fold;
           if (ci >= cin) continue;
           const float v = w16[((size_t)((kt * k + kh) * k + kw) * cin + ci) * cout + co];
           img[var * var_elems + ((size_t)gi * p.N + n) * 8 + k8] = to_h16_host(v, half);

@@ -46,6 +46,32 @@ __global__ void __launch_bounds__(256) hist_kernel(const uint8_t* __restrict__ s
   }
 }
 
+// ---------------------------------------------------------------- histograms of the code stream
+// Both candidate symbolisations of the int32 codes in one pass: hist[0..255] of (q + bias0) and
+// hist[256..511] of (q[i] - q[i-1] + bias1), out-of-range values counted under the escape symbol.
+__global__ void __launch_bounds__(256) hist_codes_kernel(const int32_t* __restrict__ q, long long n, int esc,
+                                                         int bias0, int bias1, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[4][512];
+  for (int i = threadIdx.x; i < 4 * 512; i += 256) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  uint32_t* mine = sh[(threadIdx.x >> 5) & 3];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int cur = q[i];
+    const int prev = (i > 0) ? q[i - 1] : 0;
+    int s0 = cur + bias0, s1 = cur - prev + bias1;
+    if (s0 < 0 || s0 >= esc) s0 = esc;
+    if (s1 < 0 || s1 >= esc) s1 = esc;
+    atomicAdd(&mine[s0], 1u);
+    atomicAdd(&mine[256 + s1], 1u);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < 512; s += 256) {
+    const uint32_t t = sh[0][s] + sh[1][s] + sh[2][s] + sh[3][s];
+    if (t) atomicAdd(&hist[s], t);
+  }
+}
+
 // ---------------------------------------------------------------- trits <-> bytes
 __global__ void pack_trits_kernel(const int8_t* __restrict__ m, long long n, uint8_t* __restrict__ out) {
   const long long nb = (n + 4) / 5;
@@ -264,6 +290,19 @@ extern "C" int lc_hist_u8(const uint8_t* d_sym, int64_t n, uint32_t* d_hist, voi
   if (n <= 0) return LC_OK;
   LC_REQUIRE(d_sym, "null argument");
   hist_kernel<<<grid_for(n, 256 * 64), 256, 0, s>>>(d_sym, n, d_hist);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_hist_codes(const int32_t* d_q, int64_t n, int esc, int bias0, int bias1, uint32_t* d_hist,
+                             void* stream) {
+  LC_REQUIRE(d_hist, "null argument");
+  LC_REQUIRE(esc >= 1 && esc <= 255, "escape symbol out of range");
+  cudaStream_t s = as_stream(stream);
+  LC_CUDA(cudaMemsetAsync(d_hist, 0, 512 * sizeof(uint32_t), s));
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_q, "null argument");
+  hist_codes_kernel<<<grid_for(n, 256 * 16), 256, 0, s>>>(d_q, n, esc, bias0, bias1, d_hist);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

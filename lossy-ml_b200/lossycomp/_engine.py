@@ -24,7 +24,8 @@ LATENT_MAGIC = b"LCL1"
 HUFF_MAGIC = b"LCH1"
 SEG = 4096                      # symbols per independently decodable Huffman segment
 ESC = 255                       # escape symbol of the code stream
-DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "128"))
+# 109 chunks x 19 tiles = 7.00 waves of the 296 resident CTAs of the dominant 3x3x3 kernel
+DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "109"))
 
 
 def _ptr(t):
@@ -224,27 +225,30 @@ class Engine:
         self.launches += 1
         return h.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
 
-    def huff_pack(self, sym, table: HF.Table):
-        """Symbols (uint8 device tensor) -> (payload bytes, per-segment bit lengths uint32, total bits)."""
+    def huff_pack(self, sym, table: HF.Table, total_bits=None):
+        """Symbols (uint8 device tensor) -> (payload bytes, per-segment bit lengths uint32, total bits).
+        `total_bits` (known from the histogram) sizes the zero-initialised output exactly."""
         t = self.torch
         n = sym.numel()
         nseg = (n + SEG - 1) // SEG
-        out = t.zeros(self.lib.lc_huff_max_bytes(n), dtype=t.uint8, device=self.dev)
-        segb = t.zeros(max(nseg, 1), dtype=t.int64, device=self.dev)
-        tot = t.zeros(1, dtype=t.int64, device=self.dev)
+        cap = self.lib.lc_huff_max_bytes(n) if total_bits is None else ((total_bits + 31) // 32) * 4 + 16
+        out = t.zeros(cap, dtype=t.uint8, device=self.dev)
+        segb = t.empty(max(nseg, 1) + 1, dtype=t.int64, device=self.dev)
         code = t.from_numpy(table.code.view(np.int32).copy()).to(self.dev)
         ln = t.from_numpy(table.len.copy()).to(self.dev)
         ws = self._buf("scan", self.lib.lc_huff_workspace_bytes(n, SEG))
         N.check(self.lib.lc_huff_encode(_ptr(sym), n, _ptr(code), _ptr(ln), SEG, _ptr(out), _ptr(segb),
-                                        _ptr(tot), _ptr(ws), self._stream()), "lc_huff_encode")
+                                        C.c_void_p(segb.data_ptr() + 8 * max(nseg, 1)), _ptr(ws), self._stream()),
+                "lc_huff_encode")
         self.launches += 1
-        total_bits = int(tot.item())
-        nbytes = (total_bits + 7) // 8
+        offs = segb.cpu().numpy()                      # [segment offsets..., total bits]
+        got_bits = int(offs[-1])
+        assert total_bits is None or got_bits == total_bits
+        nbytes = (got_bits + 7) // 8
         payload = out[:nbytes].cpu().numpy().tobytes()
-        offs = segb.cpu().numpy()
-        lens = np.diff(np.concatenate((offs[:nseg], [total_bits]))).astype(np.uint32) if nseg else \
+        lens = np.diff(np.concatenate((offs[:nseg], [got_bits]))).astype(np.uint32) if nseg else \
             np.zeros(0, np.uint32)
-        return payload, lens, total_bits
+        return payload, lens, got_bits
 
     def huff_unpack(self, payload: bytes, n: int, seg_lens: np.ndarray, table: HF.Table):
         t = self.torch
@@ -264,12 +268,14 @@ class Engine:
         self.launches += 1
         return sym
 
-    def pack_stream(self, sym, extra: dict) -> bytes:
+    def pack_stream(self, sym, extra: dict, hist=None) -> bytes:
         """uint8 symbols -> self-describing 'LCH1' container."""
         n = sym.numel()
-        hist = self.hist(sym) if n else np.zeros(256, np.int64)
+        if hist is None:
+            hist = self.hist(sym) if n else np.zeros(256, np.int64)
         table = HF.build_table(hist)
-        payload, lens, total_bits = self.huff_pack(sym, table) if n else (b"", np.zeros(0, np.uint32), 0)
+        bits = table.encoded_bits(hist)
+        payload, lens, total_bits = self.huff_pack(sym, table, bits) if n else (b"", np.zeros(0, np.uint32), 0)
         meta = dict(extra, n=int(n), seg=SEG, bits=int(total_bits), ref_tree=bool(table.reference_tree))
         mj = json.dumps(meta).encode()
         tb = table.to_bytes()
@@ -308,29 +314,30 @@ class Engine:
     def pack_codes(self, q) -> bytes:
         """int32 quantisation codes -> byte symbols (+ escapes) -> Huffman.  The stream is coded
         either as is or first-differenced (the reference's transform, compress.py:147-151),
-        whichever the histogram says is shorter; the choice is recorded in the header."""
+        whichever the histograms say is shorter; the choice is recorded in the header."""
         t = self.torch
         n = q.numel()
-        best = None
-        for diff, bias in ((0, 0), (1, 127)):
-            if n == 0 and diff:
-                break
-            sym = t.empty(n, dtype=t.uint8, device=self.dev)
-            esc = t.empty(max(n, 1), dtype=t.int32, device=self.dev)
-            nesc = t.zeros(1, dtype=t.int64, device=self.dev)
-            ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(max(n, 1)))
-            N.check(self.lib.lc_symbolize_i32(_ptr(q), n, diff, bias, ESC, _ptr(sym), _ptr(esc), _ptr(nesc),
-                                              _ptr(ws), self._stream()), "lc_symbolize_i32")
-            self.launches += 1
-            hist = self.hist(sym) if n else np.zeros(256, np.int64)
-            ne = int(nesc.item())
-            cost = HF.build_table(hist).encoded_bits(hist) + 32 * ne
-            if best is None or cost < best[0]:
-                best = (cost, diff, bias, sym, esc[:ne])
-        _, diff, bias, sym, esc = best
-        escb = esc.cpu().numpy().astype("<i4").tobytes()
-        body = self.pack_stream(sym, {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC,
-                                      "n_esc": len(escb) // 4})
+        cand = ((0, 0), (1, 127))                      # (diff, bias)
+        h2 = t.empty(512, dtype=t.int32, device=self.dev)
+        N.check(self.lib.lc_hist_codes(_ptr(q), n, ESC, cand[0][1], cand[1][1], _ptr(h2), self._stream()),
+                "lc_hist_codes")
+        self.launches += 1
+        h2 = h2.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        hists = (h2[:256], h2[256:])
+        costs = [HF.build_table(h).encoded_bits(h) + 32 * int(h[ESC]) for h in hists]
+        pick = 0 if (costs[0] <= costs[1] or n == 0) else 1
+        diff, bias = cand[pick]
+        ne = int(hists[pick][ESC])
+        sym = t.empty(n, dtype=t.uint8, device=self.dev)
+        esc = t.empty(max(ne, 1), dtype=t.int32, device=self.dev)
+        nesc = t.zeros(1, dtype=t.int64, device=self.dev)
+        ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(max(n, 1)))
+        N.check(self.lib.lc_symbolize_i32(_ptr(q), n, diff, bias, ESC, _ptr(sym), _ptr(esc), _ptr(nesc),
+                                          _ptr(ws), self._stream()), "lc_symbolize_i32")
+        self.launches += 1
+        body = self.pack_stream(sym, {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne},
+                                hist=hists[pick])
+        escb = esc[:ne].cpu().numpy().astype("<i4").tobytes() if ne else b""
         return body + escb
 
     def unpack_codes(self, blob: bytes):

@@ -56,6 +56,7 @@ SIGNATURES = {
     "lc_reconstruct": (_i, [_p, _p, _p, _i64, _f, _f, _d, _p, _p, _p]),
     "lc_verify_bound": (_i, [_p, _i, _p, _i64, _d, _p, _p, _p]),
     "lc_hist_u8": (_i, [_p, _i64, _p, _p]),
+    "lc_hist_codes": (_i, [_p, _i64, _i, _i, _i, _p, _p]),
     "lc_symbolize_i32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p]),
     "lc_unsymbolize_i32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p]),
     "lc_pack_trits": (_i, [_p, _i64, _p, _p]),

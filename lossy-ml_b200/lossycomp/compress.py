@@ -31,8 +31,25 @@ def _guard(max_abs: float, abs_err: float) -> float:
     return 2.0 * float(np.spacing(np.float32(max_abs + abs_err)))
 
 
+class _StageTimer:
+    """Wall-clock per stage with a device sync at every mark (diagnostics only)."""
+
+    def __init__(self, eng):
+        import time
+        self.eng, self.time, self.ms = eng, time, {}
+        eng.torch.cuda.synchronize()
+        self.t = time.perf_counter()
+
+    def mark(self, name):
+        self.eng.torch.cuda.synchronize()
+        now = self.time.perf_counter()
+        self.ms[name] = self.ms.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+        return True
+
+
 def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff", verify=None,
-                    inject=None, latent_codec="raw", batch=None, return_parts=False):
+                    inject=None, latent_codec="raw", batch=None, return_parts=False, timing=False):
     """x: torch float32 CUDA tensor (T,H,W,2).  Returns (slots list, info dict)."""
     assert err_threshold != 0, "The absolute error can't be 0."                      # compress.py:34
     assert x.dim() == 4 and x.shape[3] == eng.model.arch.in_channels, \
@@ -40,14 +57,18 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     T, H, W, _ = x.shape
     inject = inject or {}
     abs_err = float(err_threshold)
+    tm = _StageTimer(eng) if timing else None
     mean, std, max_abs = eng.stats(x)                                                # compress.py:64-65
+    tm and tm.mark("stats")
     if "mean" in inject:
         mean, std = np.float32(inject["mean"]), np.float32(inject["std"])
     latent = eng.encode(x, mean, std, batch=batch)                                   # compress.py:66-86
+    tm and tm.mark("encode")
     if "recon_std" in inject:
         recon = inject["recon_std"]
     else:
         recon = eng.decode(latent, T, H, W, batch=batch)                             # compress.py:99-111
+    tm and tm.mark("decode")
     thr = abs_err
     info = {"mode": mode, "codec": codec}
     if mode == "strict":
@@ -69,8 +90,10 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
             break
         thr = abs_err - 2.0 * (abs_err - thr)    # widen the guard band and redo the cheap stages
         assert thr > 0.5 * abs_err, "cannot meet the bound in float32"
+    tm and tm.mark("quantize+verify")
     n_out = int(q.numel())
     comp_data = eng.pack_latent(latent, latent_codec)                                # compress.py:142-144
+    tm and tm.mark("latent_pack")
     lshape = (latent.shape[0],) + tuple(eng.model.arch.latent_shape()[1:])
     if codec == "bz2":
         dq = eng.diff(q).cpu().numpy()                                               # compress.py:147-151
@@ -79,12 +102,16 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         comp_mask = bz2.compress(dm.tobytes(), 9)                                    # compress.py:166
     elif codec == "huff":
         comp_error = eng.pack_codes(q)
+        tm and tm.mark("pack_codes")
         comp_mask = eng.pack_mask(mask)
+        tm and tm.mark("pack_mask")
     else:
         raise ValueError("codec must be 'huff' or 'bz2'")
     slots = [comp_data, lshape, (T, H, W, int(x.shape[3])), (n_out,), mean, std, comp_error, comp_mask, thr2]
     info.update(n_out=n_out, thr=thr, latent_bytes=len(comp_data), error_bytes=len(comp_error),
                 mask_bytes=len(comp_mask))
+    if tm:
+        info["timing_ms"] = tm.ms
     if return_parts:
         info.update(latent=latent, recon_std=recon, mask=mask, q=q)
     return slots, info

@@ -18,27 +18,45 @@ MAX_CODE_BITS = 32      # the GPU packer takes codes of at most 32 bits
 LUT_BITS = 12           # direct decode table; longer codes walk the tree
 
 
-def _tree_codes(leaves: Sequence[Tuple[Hashable, int]]) -> Dict[Hashable, str]:
-    """leaves: [(symbol, count)] already ordered by (count, symbol)."""
-    n = len(leaves)
-    parent: Dict[int, Tuple[int, str]] = {}
-    queue: List[Tuple[int, int]] = [(leaves[i][1], i) for i in range(n)]
+def _tree_code_ints(counts: Sequence[int]) -> Tuple[List[int], List[int]]:
+    """counts: leaf counts already ordered by (count, symbol).  Returns (code, length) per leaf.
+
+    The reference re-sorts its queue stably by count before every merge and appends the new parent
+    at the end (huffman.py:20-33).  A stable sort keeps equal counts in queue order and a parent is
+    younger than everything already queued, so the queue order is exactly (count, creation index):
+    a heap on that key pops the same two nodes without the O(n^2) re-sorting.  First popped = left
+    = bit 0 (huffman.py:24-27, 40-43)."""
+    import heapq
+    n = len(counts)
+    heap = [(int(counts[i]), i) for i in range(n)]      # already sorted => already a heap
+    par = [0] * (2 * n)
+    bit = [0] * (2 * n)
     nxt = n
-    while len(queue) > 1:
-        queue.sort(key=lambda it: it[0])
-        (fa, a), (fb, b) = queue.pop(0), queue.pop(0)
-        parent[a] = (nxt, "0")
-        parent[b] = (nxt, "1")
-        queue.append((fa + fb, nxt))
+    while len(heap) > 1:
+        fa, a = heapq.heappop(heap)
+        fb, b = heapq.heappop(heap)
+        par[a] = nxt
+        par[b] = nxt
+        bit[b] = 1
+        heapq.heappush(heap, (fa + fb, nxt))
         nxt += 1
-    codes = {}
-    for i, (sym, _) in enumerate(leaves):
-        bits, node = "", i
-        while node in parent:
-            node, bit = parent[node]
-            bits = bit + bits
-        codes[sym] = bits
-    return codes
+    root = nxt - 1
+    code = [0] * nxt
+    length = [0] * nxt
+    for node in range(root - 1, -1, -1):                # parents are always younger (larger id)
+        p = par[node]
+        code[node] = (code[p] << 1) | bit[node]
+        length[node] = length[p] + 1
+    if n == 1:
+        return [0], [0]
+    return code[:n], length[:n]
+
+
+def _tree_codes(leaves: Sequence[Tuple[Hashable, int]]) -> Dict[Hashable, str]:
+    """leaves: [(symbol, count)] ordered by (count, symbol) -> {symbol: '0101' code string}."""
+    code, length = _tree_code_ints([c for _, c in leaves])
+    return {sym: (format(code[i], "b").zfill(length[i]) if length[i] else "")
+            for i, (sym, _) in enumerate(leaves)}
 
 
 def getHuffmanCode(string):
@@ -66,24 +84,38 @@ def decode_huffman(input_string, char_store, freq_store):
 class Table:
     """A prefix code over byte symbols in the arrays the C-ABI wants."""
 
-    def __init__(self, codes: Dict[int, str], reference_tree: bool):
-        self.codes = codes
+    def __init__(self, codes: Dict[int, str] = None, reference_tree: bool = False, arrays=None):
         self.reference_tree = reference_tree
         self.code = np.zeros(256, dtype=np.uint32)
         self.len = np.zeros(256, dtype=np.uint8)
-        for s, bits in codes.items():
-            assert len(bits) <= MAX_CODE_BITS
-            self.code[s] = int(bits, 2) if bits else 0
-            self.len[s] = len(bits)
+        self.used = np.zeros(256, dtype=bool)
+        if arrays is not None:
+            syms, code, length = arrays
+            assert max(length) <= MAX_CODE_BITS
+            self.code[syms] = code
+            self.len[syms] = length
+            self.used[syms] = True
+        else:
+            for s, bits in codes.items():
+                assert len(bits) <= MAX_CODE_BITS
+                self.code[s] = int(bits, 2) if bits else 0
+                self.len[s] = len(bits)
+                self.used[s] = True
+
+    @property
+    def codes(self) -> Dict[int, str]:
+        return {int(s): (format(int(self.code[s]), "b").zfill(int(self.len[s])) if self.len[s] else "")
+                for s in np.nonzero(self.used)[0]}
 
     # -- decode side ---------------------------------------------------------
     def decode_arrays(self, lut_bits: int = LUT_BITS):
         lut = np.zeros(1 << lut_bits, dtype=np.uint16)
         nodes: List[List[int]] = [[0, 0]]
-        if len(self.codes) == 1:
-            (s,) = self.codes.keys()
+        codes = self.codes
+        if len(codes) == 1:
+            (s,) = codes.keys()
             return lut, np.array([~s, ~s], dtype=np.int32)
-        for s, bits in self.codes.items():
+        for s, bits in codes.items():
             L = len(bits)
             if L <= lut_bits:
                 base = int(bits, 2) << (lut_bits - L)
@@ -102,7 +134,7 @@ class Table:
 
     # -- serialisation (explicit codes: the tree is not canonical) -----------
     def to_bytes(self) -> bytes:
-        syms = sorted(self.codes)
+        syms = [int(v) for v in np.nonzero(self.used)[0]]
         out = bytearray([len(syms) & 0xFF, len(syms) >> 8])
         for s in syms:
             out += bytes([s, int(self.len[s])]) + int(self.code[s]).to_bytes(4, "little")
@@ -131,10 +163,15 @@ def build_table(hist) -> Table:
     shift = 0
     while True:
         h = hist if shift == 0 else np.where(hist > 0, np.maximum(hist >> shift, 1), 0)
-        leaves = sorted(((int(s), int(h[s])) for s in np.nonzero(h)[0]), key=lambda kv: (kv[1], kv[0]))
-        if not leaves:
-            leaves = [(0, 1)]
-        codes = _tree_codes(leaves)
-        if max(len(c) for c in codes.values()) <= MAX_CODE_BITS:
-            return Table(codes, reference_tree=(shift == 0))
+        syms = np.nonzero(h)[0]
+        if syms.size == 0:
+            syms = np.array([0])
+            cnt = np.array([1])
+        else:
+            cnt = h[syms]
+        order = np.lexsort((syms, cnt))                 # by (count, symbol), huffman.py:71
+        syms, cnt = syms[order], cnt[order]
+        code, length = _tree_code_ints(cnt.tolist())
+        if max(length) <= MAX_CODE_BITS:
+            return Table(reference_tree=(shift == 0), arrays=(syms, code, length))
         shift += 1

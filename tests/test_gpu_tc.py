@@ -50,7 +50,8 @@ def test_tc_matches_cuda_core_backend(engines, name):
     T, H, W, _ = g["x"].shape
     la = tc.encode(x, g["mean"], g["std"]).cpu().numpy()
     lb = direct.encode(x, g["mean"], g["std"]).cpu().numpy()
-    assert np.abs(la - lb).max() <= TOL_TC_VS_DIRECT[prec], np.abs(la - lb).max()
+    # one 16-bit ulp of the largest latent value (latents reach ~15)
+    assert np.abs(la - lb).max() <= TOL_TC_VS_DIRECT[prec] * max(1.0, np.abs(lb).max() / 4), np.abs(la - lb).max()
     lat = dev(g["latent"].reshape(la.shape))
     ra = tc.decode(lat, T, H, W).cpu().numpy()
     rb = direct.decode(lat, T, H, W).cpu().numpy()
