@@ -32,11 +32,11 @@
 
 namespace {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;   // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue
+constexpr int kHalf = 12;         // output channels per epilogue thread (two threads share a TMEM lane)
 constexpr int kMaxKs = 24;
 constexpr int kMaxVar = 4;
-constexpr int kTmemCols = 256;
-constexpr int kAccStride = 128;   // TMEM columns between the two accumulator buffers
+constexpr int kMaxBufs = 4;       // TMEM accumulator ring (p.nbuf buffers, p.acc_stride columns apart)
 constexpr int kMaxStages = 4;
 
 enum { MODE_K3 = 1, MODE_K4 = 2, MODE_K4_OUT1 = 3, MODE_DOWN = 4, MODE_UP = 5 };
@@ -59,6 +59,7 @@ struct SweepParams {
   int tiles_per_chunk, n_items, n_classes;
   int slab_slots, slab_start;    // the stage holds slots [row0 + 128*j + slab_start, +slab_slots) of every plane
   int stages;
+  int nbuf, acc_stride, tmem_cols;   // TMEM accumulator ring
   // MMA
   int N, nks, nvar;
   const uint4* wimg;
@@ -67,19 +68,37 @@ struct SweepParams {
   uint32_t a_off[kMaxVar][kMaxKs], a_lbo[kMaxVar][kMaxKs];
   const float* bias;
   int cout, relu, half, out_T;
+  int debug;   // bit0: no MMA issue, bit1: no epilogue TMEM loads, bit2: no stores, bit3: no bulk copies
 };
 
-__device__ __forceinline__ void ld_cols24(uint32_t taddr, float d[24]) {
-  uint32_t v0[8], v1[8], v2[8];
+// 12 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void ld_cols12(uint32_t taddr, float d[kHalf]) {
+  uint32_t v0[8], v1[4];
   umma::tmem_ld8(taddr, v0);
-  umma::tmem_ld8(taddr + 8, v1);
-  umma::tmem_ld8(taddr + 16, v2);
+  umma::tmem_ld4(taddr + 8, v1);
   umma::tmem_ld_wait();
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    d[k] = __uint_as_float(v0[k]);
-    d[8 + k] = __uint_as_float(v1[k]);
-    d[16 + k] = __uint_as_float(v2[k]);
+  for (int k = 0; k < 8; ++k) d[k] = __uint_as_float(v0[k]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) d[8 + k] = __uint_as_float(v1[k]);
+}
+
+// NB dt-blocks (24 columns apart) of 12 columns each: all TMEM loads are issued before the single wait
+template <int NB>
+__device__ __forceinline__ void ld_blocks(uint32_t taddr, float (&d)[NB][kHalf]) {
+  uint32_t v0[NB][8], v1[NB][4];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    umma::tmem_ld8(taddr + b * 24, v0[b]);
+    umma::tmem_ld4(taddr + b * 24 + 8, v1[b]);
+  }
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[b][k] = __uint_as_float(v0[b][k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[b][8 + k] = __uint_as_float(v1[b][k]);
   }
 }
 
@@ -118,42 +137,93 @@ __device__ __forceinline__ VoxAddr vox_addr(const SweepParams& p, int n, int h, 
   return a;
 }
 
+// Channels [12*half, 12*half+12) of one voxel: y = acc + bias (+ skip) -> ReLU -> 16-bit -> out.
+// half 0 owns vector g0 and the low 8 bytes of g1, half 1 the high 8 bytes of g1 and vector g2.
+__device__ __forceinline__ void unpack4(const uint2 v, int half16, float f[4]) {
+  f[0] = h16_to_float((unsigned short)(v.x & 0xffff), half16);
+  f[1] = h16_to_float((unsigned short)(v.x >> 16), half16);
+  f[2] = h16_to_float((unsigned short)(v.y & 0xffff), half16);
+  f[3] = h16_to_float((unsigned short)(v.y >> 16), half16);
+}
+__device__ __forceinline__ uint2 pack4(const float f[4], int half16) {
+  return make_uint2((unsigned)float_to_h16(f[0], half16) | ((unsigned)float_to_h16(f[1], half16) << 16),
+                    (unsigned)float_to_h16(f[2], half16) | ((unsigned)float_to_h16(f[3], half16) << 16));
+}
+
+struct SkipRegs {
+  uint4 a;
+  uint2 b;
+};
+
+__device__ __forceinline__ SkipRegs load_skip(const SweepParams& p, const VoxAddr& va, int t, int half) {
+  SkipRegs r;
+  const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base);
+  const long long si = va.s0 + (long long)t * va.s_t;
+  if (half == 0) {
+    r.a = __ldg(sk + si);
+    r.b = __ldg(reinterpret_cast<const uint2*>(sk + si + p.skip.S));
+  } else {
+    r.b = __ldg(reinterpret_cast<const uint2*>(sk + si + p.skip.S) + 1);
+    r.a = __ldg(sk + si + 2LL * p.skip.S);
+  }
+  return r;
+}
+
 __device__ __forceinline__ void store_voxel(const SweepParams& p, const float* s_bias, const VoxAddr& va, int t,
-                                            const float (&acc)[24]) {
-  float y[24];
+                                            int half, const float (&acc)[kHalf], const SkipRegs* skp) {
+  float y[kHalf];
 #pragma unroll
-  for (int c = 0; c < 24; ++c) y[c] = acc[c] + s_bias[c];
-  if (p.skip.base) {
-    const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base);
-    const long long si = va.s0 + (long long)t * va.s_t;
+  for (int c = 0; c < kHalf; ++c) y[c] = acc[c] + s_bias[half * kHalf + c];
+  // y[0..7]/y[8..11] for half 0 are (vector g0, low half of g1); for half 1 y[0..3]/y[4..11] are
+  // (high half of g1, vector g2)
+  if (skp) {
+    float f8[8], f4[4];
+    unpack8(skp->a, p.half, f8);
+    unpack4(skp->b, p.half, f4);
+    if (half == 0) {
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      float f[8];
-      unpack8(__ldg(sk + si + (long long)g * p.skip.S), p.half, f);
+      for (int k = 0; k < 8; ++k) y[k] = __fadd_rn(y[k], f8[k]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) y[g * 8 + k] = __fadd_rn(y[g * 8 + k], f[k]);
+      for (int k = 0; k < 4; ++k) y[8 + k] = __fadd_rn(y[8 + k], f4[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(y[k], f4[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[4 + k] = __fadd_rn(y[4 + k], f8[k]);
     }
+  }
+#pragma unroll
+  for (int c = 0; c < kHalf; ++c) {
+    float v = y[c];
+    if (p.relu) v = fmaxf(v, 0.f);
+    y[c] = (half * kHalf + c < p.cout) ? v : 0.f;
   }
   uint4* o = reinterpret_cast<uint4*>(p.out.base);
   const long long oi = va.o0 + (long long)t * va.o_t;
+  if (half == 0) {
+    float f8[8], f4[4];
 #pragma unroll
-  for (int g = 0; g < 3; ++g) {
-    float f[8];
+    for (int k = 0; k < 8; ++k) f8[k] = y[k];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float v = y[g * 8 + k];
-      if (p.relu) v = fmaxf(v, 0.f);
-      f[k] = (g * 8 + k < p.cout) ? v : 0.f;
-    }
-    if (g < p.out.G) o[oi + (long long)g * p.out.S] = pack8(f, p.half);
+    for (int k = 0; k < 4; ++k) f4[k] = y[8 + k];
+    o[oi] = pack8(f8, p.half);
+    if (p.out.G > 1) *reinterpret_cast<uint2*>(o + oi + p.out.S) = pack4(f4, p.half);
+  } else {
+    float f8[8], f4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f4[k] = y[k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f8[k] = y[4 + k];
+    if (p.out.G > 1) *(reinterpret_cast<uint2*>(o + oi + p.out.S) + 1) = pack4(f4, p.half);
+    if (p.out.G > 2) o[oi + 2LL * p.out.S] = pack8(f8, p.half);
   }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, (MODE == MODE_K3) ? 2 : 1)
+__global__ void __launch_bounds__(kTcThreads, (MODE == MODE_K3 || MODE == MODE_K4 || MODE == MODE_UP) ? 2 : 1)
 sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2], wbar;
+  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull[kMaxBufs], tempty[kMaxBufs], wbar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[24];
   __shared__ __align__(8) uint64_t s_da[kMaxVar * kMaxKs], s_db[kMaxVar * kMaxKs];
@@ -173,12 +243,12 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < p.nbuf; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], (MODE == MODE_K4_OUT1) ? 4 : 8); }
     umma::mbar_init(&wbar, 1);
     umma::fence_barrier_init();
   }
   if (threadIdx.x < 24) s_bias[threadIdx.x] = (threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
-  if (warp == 1) umma::tmem_alloc(&tmem_base_s, kTmemCols);
+  if (warp == 1) umma::tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
   umma::tcgen05_fence_before();
   __syncthreads();
   umma::tcgen05_fence_after();
@@ -197,6 +267,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
         const long long slab0 = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start;
         for (int t = 0; t < p.in_T; ++t) {
           umma::mbar_wait(&empty[stage], phase ^ 1);
+          if (p.debug & 8) { umma::mbar_arrive(&full[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1; } continue; }
           umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
           for (int g = 0; g < p.in_NPG; ++g)
             umma::bulk_g2s(sA + stage * stage_bytes + g * slab_bytes,
@@ -211,52 +282,63 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
     if (lane == 0) {
       umma::mbar_wait(&wbar, 0);
       const uint32_t idesc = umma::make_idesc(128, p.N, p.half ? 0 : 1);
-      int stage = 0, phase = 0, it = 0;
+      int stage = 0, phase = 0, buf = 0, bphase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int var = 0;
         if (MODE == MODE_UP) var = ((item % per_chunk) / p.tiles_per_chunk);
-        for (int t = 0; t < p.in_T; ++t, ++it) {
+        for (int t = 0; t < p.in_T; ++t) {
           if (MODE == MODE_DOWN) var = t & 1;
-          const int buf = it & 1;
           const uint64_t* da = s_da + var * kMaxKs;
           const uint64_t* db = s_db + var * kMaxKs;
           const uint64_t stage_add = (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
           uint64_t da_n = da[0] + stage_add, db_n = db[0];
-          umma::mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+          umma::mbar_wait(&tempty[buf], bphase ^ 1);
           umma::mbar_wait(&full[stage], phase);
           umma::tcgen05_fence_after();
-          const uint32_t d_addr = tmem + buf * kAccStride;
+          const uint32_t d_addr = tmem + buf * p.acc_stride;
 #pragma unroll 2
-          for (int ks = 0; ks < p.nks; ++ks) {
+          for (int ks = 0; ks < ((p.debug & 1) ? 0 : p.nks); ++ks) {
             const uint64_t a = da_n, b = db_n;
             if (ks + 1 < p.nks) { da_n = da[ks + 1] + stage_add; db_n = db[ks + 1]; }
             umma::mma_f16(d_addr, a, b, idesc, ks > 0);
           }
-          umma::commit(&empty[stage]);
+          // one commit per step (a commit costs the issuing thread ~300 cycles): it signals the epilogue,
+          // which releases the shared-memory stage on the producer's behalf
           umma::commit(&tfull[buf]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++buf == p.nbuf) { buf = 0; bphase ^= 1; }
         }
       }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
+    // 8 warps: warp w reads TMEM lanes 32*(w&3)..+31 (hardware rule); warps 2-5 take output channels
+    // 0..11 of every dt block, warps 6-9 channels 12..23.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    int it = 0;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + half * kHalf;
+    const bool has_skip = p.skip.base != nullptr;
+    int ebuf = 0, ephase = 0;
+    int estage = 0;
     auto wait_d = [&]() -> uint32_t {
-      const int buf = it & 1;
-      umma::mbar_wait(&tfull[buf], (it >> 1) & 1);
+      const int buf = ebuf;
+      umma::mbar_wait(&tfull[buf], ephase);
       umma::tcgen05_fence_after();
-      return lane_addr + buf * kAccStride;
+      // the MMAs that read this step's stage are complete: hand the stage back to the producer
+      if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
+      if (++estage == p.stages) estage = 0;
+      return lane_addr + buf * p.acc_stride;
     };
     auto release_d = [&]() {
       umma::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&tempty[it & 1]);
-      ++it;
+      if (lane == 0) umma::mbar_arrive(&tempty[ebuf]);
+      if (++ebuf == p.nbuf) { ebuf = 0; ephase ^= 1; }
     };
-
+    if (MODE == MODE_K4_OUT1 && half == 1) {
+      // single output channel: the second half of the epilogue warps has nothing to do
+    } else
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const RowInfo ri = row_info(p, item, row);
       VoxAddr va;
@@ -264,53 +346,50 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       else if (MODE != MODE_K4_OUT1) va = vox_addr(p, ri.n, ri.h, ri.w);
       if (MODE == MODE_K3) {
         // block dt -> output plane t_in - dt + 1
-        float aP[24], aC[24], aN[24], d[24];
+        float aP[kHalf], aC[kHalf], aN[kHalf];
 #pragma unroll
-        for (int c = 0; c < 24; ++c) { aP[c] = 0.f; aC[c] = 0.f; }
+        for (int c = 0; c < kHalf; ++c) { aP[c] = 0.f; aC[c] = 0.f; }
+        SkipRegs sk;
         for (int t = 0; t < p.in_T; ++t) {
+          // the skip values of the plane finished in this step are fetched before waiting for the MMA
+          if (has_skip && t >= 1 && ri.valid) sk = load_skip(p, va, t - 1, half);
           const uint32_t ta = wait_d();
-          ld_cols24(ta, d);
+          if (!(p.debug & 2)) {
+            float db[3][kHalf];
+            ld_blocks<3>(ta, db);
+            release_d();
 #pragma unroll
-          for (int c = 0; c < 24; ++c) aN[c] = d[c];
-          ld_cols24(ta + 24, d);
+            for (int c = 0; c < kHalf; ++c) { aN[c] = db[0][c]; aC[c] += db[1][c]; aP[c] += db[2][c]; }
+          } else {
+            release_d();
+          }
+          if (t >= 1 && ri.valid && !(p.debug & 4)) store_voxel(p, s_bias, va, t - 1, half, aP, has_skip ? &sk : nullptr);
 #pragma unroll
-          for (int c = 0; c < 24; ++c) aC[c] += d[c];
-          ld_cols24(ta + 48, d);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) aP[c] += d[c];
-          release_d();
-          if (t >= 1 && ri.valid) store_voxel(p, s_bias, va, t - 1, aP);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) { aP[c] = aC[c]; aC[c] = aN[c]; }
-        }
-        if (ri.valid) store_voxel(p, s_bias, va, p.in_T - 1, aP);
-      } else if (MODE == MODE_K4) {
-        // k=4, pad 1/2: block dt -> output plane t_in - dt + 1  (planes t+1, t, t-1, t-2)
-        float a1[24], a2[24], a3[24], a0[24], d[24];
-#pragma unroll
-        for (int c = 0; c < 24; ++c) { a1[c] = 0.f; a2[c] = 0.f; a3[c] = 0.f; }
-        for (int t = 0; t < p.in_T; ++t) {
-          const uint32_t ta = wait_d();
-          ld_cols24(ta, d);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) a0[c] = d[c];
-          ld_cols24(ta + 24, d);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) a1[c] += d[c];
-          ld_cols24(ta + 48, d);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) a2[c] += d[c];
-          ld_cols24(ta + 72, d);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) a3[c] += d[c];
-          release_d();
-          if (t >= 2 && ri.valid) store_voxel(p, s_bias, va, t - 2, a3);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) { a3[c] = a2[c]; a2[c] = a1[c]; a1[c] = a0[c]; }
+          for (int c = 0; c < kHalf; ++c) { aP[c] = aC[c]; aC[c] = aN[c]; }
         }
         if (ri.valid) {
-          store_voxel(p, s_bias, va, p.in_T - 2, a3);
-          store_voxel(p, s_bias, va, p.in_T - 1, a2);
+          if (has_skip) sk = load_skip(p, va, p.in_T - 1, half);
+          store_voxel(p, s_bias, va, p.in_T - 1, half, aP, has_skip ? &sk : nullptr);
+        }
+      } else if (MODE == MODE_K4) {
+        // k=4, pad 1/2: block dt -> output plane t_in - dt + 1  (planes t+1, t, t-1, t-2)
+        float a1[kHalf], a2[kHalf], a3[kHalf], a0[kHalf];
+#pragma unroll
+        for (int c = 0; c < kHalf; ++c) { a1[c] = 0.f; a2[c] = 0.f; a3[c] = 0.f; }
+        for (int t = 0; t < p.in_T; ++t) {
+          const uint32_t ta = wait_d();
+          float db[4][kHalf];
+          ld_blocks<4>(ta, db);
+          release_d();
+#pragma unroll
+          for (int c = 0; c < kHalf; ++c) { a0[c] = db[0][c]; a1[c] += db[1][c]; a2[c] += db[2][c]; a3[c] += db[3][c]; }
+          if (t >= 2 && ri.valid) store_voxel(p, s_bias, va, t - 2, half, a3, nullptr);
+#pragma unroll
+          for (int c = 0; c < kHalf; ++c) { a3[c] = a2[c]; a2[c] = a1[c]; a1[c] = a0[c]; }
+        }
+        if (ri.valid) {
+          store_voxel(p, s_bias, va, p.in_T - 2, half, a3, nullptr);
+          store_voxel(p, s_bias, va, p.in_T - 1, half, a2, nullptr);
         }
       } else if constexpr (MODE == MODE_K4_OUT1) {
         // cout = 1, taps dt and dw folded into N: column dt*4+dw of row r is the contribution of input
@@ -335,7 +414,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           }
         };
         for (int t = 0; t < p.in_T; ++t) {
-          const uint32_t ta = wait_d();
+          const uint32_t ta = wait_d() - half * kHalf;
           uint32_t v0[8], v1[8];
           umma::tmem_ld8(ta, v0);
           umma::tmem_ld8(ta + 8, v1);
@@ -361,60 +440,51 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       } else if (MODE == MODE_DOWN) {
         // t_in = 2*to + dt - 1.  odd t_in: block0 = dt 0 -> plane (t_in+1)/2 (starts it), block1 = dt 2 ->
         // plane (t_in-1)/2.  even t_in: block0 = dt 1 -> plane t_in/2, block1 = dt 3 -> plane t_in/2 - 1 (done).
-        float aO[24], aN[24], d[24];
+        float aO[kHalf], aN[kHalf];
 #pragma unroll
-        for (int c = 0; c < 24; ++c) { aO[c] = 0.f; aN[c] = 0.f; }
+        for (int c = 0; c < kHalf; ++c) { aO[c] = 0.f; aN[c] = 0.f; }
         for (int t = 0; t < p.in_T; ++t) {
           const uint32_t ta = wait_d();
+          float db[2][kHalf];
+          ld_blocks<2>(ta, db);
+          release_d();
           if (t & 1) {
-            ld_cols24(ta, d);
 #pragma unroll
-            for (int c = 0; c < 24; ++c) aN[c] = d[c];
-            ld_cols24(ta + 24, d);
-#pragma unroll
-            for (int c = 0; c < 24; ++c) aO[c] += d[c];
-            release_d();
+            for (int c = 0; c < kHalf; ++c) { aN[c] = db[0][c]; aO[c] += db[1][c]; }
           } else {
-            ld_cols24(ta, d);
 #pragma unroll
-            for (int c = 0; c < 24; ++c) aN[c] += d[c];
-            ld_cols24(ta + 24, d);
-#pragma unroll
-            for (int c = 0; c < 24; ++c) aO[c] += d[c];
-            release_d();
+            for (int c = 0; c < kHalf; ++c) { aN[c] += db[0][c]; aO[c] += db[1][c]; }
             const int m = t >> 1;
-            if (m >= 1 && ri.valid) store_voxel(p, s_bias, va, m - 1, aO);
+            if (m >= 1 && ri.valid) store_voxel(p, s_bias, va, m - 1, half, aO, nullptr);
 #pragma unroll
-            for (int c = 0; c < 24; ++c) aO[c] = aN[c];
+            for (int c = 0; c < kHalf; ++c) aO[c] = aN[c];
           }
         }
-        if (ri.valid) store_voxel(p, s_bias, va, p.out_T - 1, aO);
+        if (ri.valid) store_voxel(p, s_bias, va, p.out_T - 1, half, aO, nullptr);
       } else if (MODE == MODE_UP) {
         // output plane 2*t_in + kt - 1; block kt.  Planes 2t-1 and 2t complete at step t.
-        float cX[24], cY[24], d[24];
+        float cX[kHalf], cY[kHalf];
 #pragma unroll
-        for (int c = 0; c < 24; ++c) { cX[c] = 0.f; cY[c] = 0.f; }
+        for (int c = 0; c < kHalf; ++c) { cX[c] = 0.f; cY[c] = 0.f; }
         for (int t = 0; t < p.in_T; ++t) {
           const uint32_t ta = wait_d();
-          ld_cols24(ta, d);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) cX[c] += d[c];
-          if (t >= 1 && ri.valid) store_voxel(p, s_bias, va, 2 * t - 1, cX);
-          ld_cols24(ta + 24, d);
-#pragma unroll
-          for (int c = 0; c < 24; ++c) cY[c] += d[c];
-          if (ri.valid) store_voxel(p, s_bias, va, 2 * t, cY);
-          ld_cols24(ta + 48, cX);
-          ld_cols24(ta + 72, cY);
+          float db[4][kHalf];
+          ld_blocks<4>(ta, db);
           release_d();
+#pragma unroll
+          for (int c = 0; c < kHalf; ++c) { cX[c] += db[0][c]; cY[c] += db[1][c]; }
+          if (t >= 1 && ri.valid) store_voxel(p, s_bias, va, 2 * t - 1, half, cX, nullptr);
+          if (ri.valid) store_voxel(p, s_bias, va, 2 * t, half, cY, nullptr);
+#pragma unroll
+          for (int c = 0; c < kHalf; ++c) { cX[c] = db[2][c]; cY[c] = db[3][c]; }
         }
-        if (ri.valid) store_voxel(p, s_bias, va, 2 * p.in_T - 1, cX);
+        if (ri.valid) store_voxel(p, s_bias, va, 2 * p.in_T - 1, half, cX, nullptr);
       }
     }
   }
   umma::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, kTmemCols);
+  if (warp == 1) umma::tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -635,7 +705,7 @@ int launch_mode(const lc_codec* h, const SweepParams& p, int smem) {
 
 int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStream_t s) {
   const int smem = lp.smem_bytes;
-  const int per_sm = (lp.backend == MODE_K3) ? 2 : 1;
+  const int per_sm = (lp.backend == MODE_K3 || lp.backend == MODE_K4 || lp.backend == MODE_UP) ? 2 : 1;
   int grid = per_sm * h->num_sms;
   if (grid > p.n_items) grid = p.n_items;
   int rc = LC_OK;
@@ -671,8 +741,8 @@ int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStr
 
 // One K group = 8 (pseudo-)channels of one shifted view of one plane of the stage.
 struct KGroup {
-  uint32_t a_addr;        // byte offset inside the stage
-  int kt_unused;
+  uint32_t a_addr;        // byte offset inside the stage (filled once the slab size is final)
+  int plane, off_slots;   // plane of the stage, slot offset of the shifted view inside the slab
   int tap_h, tap_w;       // kernel indices (kh, kw) this group multiplies with
   int ci0;                // first input channel of the group (or pseudo-channel for WFOLD)
 };
@@ -707,7 +777,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     for (int g = 0; g < G; ++g)
       for (int dh = 0; dh < k; ++dh)
         for (int dw = 0; dw < k; ++dw)
-          groups[0].push_back({(uint32_t)(g * p.slab_slots * 16 + (dh * tin.PW + dw) * 16), 0, dh, dw, g * 8});
+          groups[0].push_back({0, g, dh * tin.PW + dw, dh, dw, g * 8});
     block_kt.resize(1);
     for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
     p.N = 80;
@@ -722,7 +792,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     groups.resize(1);
     for (int g = 0; g < G; ++g)
       for (int dh = 0; dh < k; ++dh)
-        groups[0].push_back({(uint32_t)(g * p.slab_slots * 16 + dh * tin.PW * 16), 0, dh, -2, g * 8});
+        groups[0].push_back({0, g, dh * tin.PW, dh, -2, g * 8});
     block_kt.resize(1);
     for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
     block_cols = 4; p.N = 16;
@@ -736,7 +806,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     groups.resize(1);
     for (int g = 0; g < G; ++g)
       for (int dh = 0; dh < k; ++dh)
-        groups[0].push_back({(uint32_t)(g * p.slab_slots * 16 + dh * tin.PW * 16), 0, dh, -1, g * 8});
+        groups[0].push_back({0, g, dh * tin.PW, dh, -1, g * 8});
     block_kt.resize(1);
     for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
     p.N = 96;
@@ -754,8 +824,8 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
         for (int g = 0; g < G; ++g)
           for (int dh2 = 0; dh2 < 2; ++dh2)
             for (int dw2 = 0; dw2 < 2; ++dw2)
-              groups[var].push_back({(uint32_t)((par * G + g) * p.slab_slots * 16 + (dh2 * tin.PW + dw2) * 16), 0,
-                                     2 * dh2 + (par >> 1), 2 * dw2 + (par & 1), g * 8});
+              groups[var].push_back({0, par * G + g, dh2 * tin.PW + dw2, 2 * dh2 + (par >> 1), 2 * dw2 + (par & 1),
+                                     g * 8});
       // var = t_in & 1: odd -> kt {0, 2}; even -> kt {1, 3}
       block_kt[var] = var ? std::vector<int>{0, 2} : std::vector<int>{1, 3};
     }
@@ -780,11 +850,20 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
       for (int g = 0; g < G; ++g)
         for (int a = 0; a < 2; ++a)
           for (int b = 0; b < 2; ++b)
-            groups[cls].push_back({(uint32_t)(g * p.slab_slots * 16 + ((tin.PW + 1) + offh[a] * tin.PW + offw[b]) * 16),
-                                   0, kh[a], kw[b], g * 8});
+            groups[cls].push_back({0, g, (tin.PW + 1) + offh[a] * tin.PW + offw[b], kh[a], kw[b], g * 8});
       block_kt[cls] = {0, 1, 2, 3};
     }
     p.N = 96;
+  }
+  // Align the bulk copies: start every slab on a 128-byte boundary of the tensor (the copy engine is
+  // several times slower on 16-byte-aligned sources) and make slabs a multiple of 128 bytes.
+  {
+    const int base = tin.GL + p.row0 - p.row_shift + p.slab_start;
+    const int pad = (p.row_step % 8 == 0 && !getenv("LOSSYCOMP_NO_ALIGN")) ? (((base % 8) + 8) % 8) : 0;
+    p.slab_start -= pad;
+    p.slab_slots = (p.slab_slots + pad + 7) & ~7;
+    for (auto& gv : groups)
+      for (auto& kg : gv) kg.a_addr = (uint32_t)((kg.plane * p.slab_slots + kg.off_slots + pad) * 16);
   }
   p.nvar = (int)groups.size();
   const int ngroups = (int)groups[0].size();
@@ -835,7 +914,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   L.wtc_bytes = img.size() * 2;
   p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
   const int stage_bytes = p.in_NPG * p.slab_slots * 16;
-  const int budget = ((mode == MODE_K3) ? 100 : 200) * 1024;
+  const int budget = ((mode == MODE_K3 || mode == MODE_K4 || mode == MODE_UP) ? 100 : 200) * 1024;
   const int fixed = ((p.wimg_bytes + 127) & ~127) + 256;
   int stages = (budget - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -844,8 +923,17 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     return LC_EUNSUPPORTED;
   }
   p.stages = stages;
+  {
+    const bool two_per_sm = (mode == MODE_K3 || mode == MODE_K4 || mode == MODE_UP);
+    p.tmem_cols = two_per_sm ? 256 : 512;
+    p.acc_stride = (p.N + 7) & ~7;
+    p.nbuf = p.tmem_cols / p.acc_stride;
+    if (p.nbuf > kMaxBufs) p.nbuf = kMaxBufs;
+    if (getenv("LOSSYCOMP_TC_NBUF")) p.nbuf = atoi(getenv("LOSSYCOMP_TC_NBUF"));
+  }
   lp.smem_bytes = fixed + stages * stage_bytes;
   lp.backend = mode;
+  p.debug = getenv("LOSSYCOMP_TC_DEBUG") ? atoi(getenv("LOSSYCOMP_TC_DEBUG")) : 0;
   (void)tout;
   return LC_OK;
 }

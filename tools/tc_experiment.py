@@ -1,0 +1,26 @@
+"""Timing experiments on the K3 tensor-core kernel with parts of the pipeline disabled (diagnostics)."""
+import os, sys, subprocess, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%r, "lossy-ml_b200")); sys.path.insert(0, %r)
+import torch
+from lossycomp import _native as N
+from lossycomp._engine import Engine
+eng = Engine.get(None, "fp16", 0)
+T, H, W = 24, 720, 1440
+x = torch.empty((T, H, W, 2), dtype=torch.float32, device="cuda")
+N.check(eng.lib.lc_synth_field(x.data_ptr(), T, H, W, 0, 0, 1234, None), "synth")
+mean, std, _ = eng.stats(x)
+for i in range(2): lat = eng.encode(x, mean, std)
+eng.profile(True); eng.profile_read()
+for i in range(3): lat = eng.encode(x, mean, std)
+ms, cnt = eng.profile_read()
+print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms[:7]))
+''' % (ROOT, ROOT)
+for dbg, label in [(0, "full"), (2 + 4, "no epilogue loads/stores"), (4, "no stores"), (1, "no MMA"), (8, "no copies"),
+                   (1 + 2 + 4, "no MMA, no epilogue"), (1 + 2 + 4 + 8, "only barriers")]:
+    env = dict(os.environ, LOSSYCOMP_TC_DEBUG=str(dbg))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    print(f"debug={dbg:2d} {label:28s}", line[0] if line else out.stderr[-300:])
