@@ -114,6 +114,15 @@ class Engine:
         return b
 
     # -- stages ------------------------------------------------------------------
+    def stats_raw(self, x):
+        """(sum x, sum x^2, max|x|, n) of channel 0 as Python floats (the quantities ranks all-reduce)."""
+        T, H, W, Cc = x.shape
+        out = self.torch.empty(4, dtype=self.torch.float64, device=self.dev)
+        ws = self._buf("stats", self.lib.lc_stats_workspace_bytes())
+        N.check(self.lib.lc_stats(_ptr(x), T * H * W, Cc, _ptr(out), _ptr(ws), self._stream()), "lc_stats")
+        self.launches += 2
+        return tuple(out.cpu().tolist())
+
     def stats(self, x):
         """compress.py:64-65 -> (mean float32, std float32, max|x|).  Sync (reads 32 bytes)."""
         T, H, W, Cc = x.shape
@@ -304,6 +313,10 @@ class Engine:
 
     def unpack_mask(self, blob: bytes):
         t = self.torch
+        from .dist import unpack_multipart
+        parts = unpack_multipart(blob)
+        if len(parts) > 1:
+            return t.cat([self.unpack_mask(p) for p in parts])
         sym, meta = self.unpack_stream(blob)
         n = meta["n_mask"]
         mask = t.empty(n, dtype=t.int8, device=self.dev)
@@ -342,6 +355,10 @@ class Engine:
 
     def unpack_codes(self, blob: bytes):
         t = self.torch
+        from .dist import unpack_multipart
+        parts = unpack_multipart(blob)
+        if len(parts) > 1:
+            return t.cat([self.unpack_codes(p) for p in parts])
         # the escape list trails the container; its length is in the header
         lm = struct.unpack("<I", blob[4:8])[0]
         meta = json.loads(blob[16:16 + lm])
@@ -369,6 +386,23 @@ class Engine:
         if codec == "bz2":
             raw = bz2.compress(raw, 9)
         return LATENT_MAGIC + struct.pack("<I", len(mj)) + mj + raw
+
+    def join_latents(self, blobs) -> bytes:
+        """Concatenate the latent containers of consecutive chunk ranges (time shards) into one."""
+        metas, raws = [], []
+        for b in blobs:
+            assert b[:4] == LATENT_MAGIC
+            (lm,) = struct.unpack("<I", b[4:8])
+            meta = json.loads(b[8:8 + lm])
+            raw = b[8 + lm:]
+            if meta.get("codec") == "bz2":
+                raw = bz2.decompress(raw)
+            metas.append(meta)
+            raws.append(raw)
+        meta = dict(metas[0], codec="raw")
+        assert all(m["precision"] == meta["precision"] and m["model"] == meta["model"] for m in metas)
+        mj = json.dumps(meta).encode()
+        return LATENT_MAGIC + struct.pack("<I", len(mj)) + mj + b"".join(raws)
 
     def unpack_latent(self, blob: bytes, shape):
         if blob[:4] != LATENT_MAGIC:

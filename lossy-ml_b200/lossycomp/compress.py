@@ -60,8 +60,9 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     tm = _StageTimer(eng) if timing else None
     mean, std, max_abs = eng.stats(x)                                                # compress.py:64-65
     tm and tm.mark("stats")
-    if "mean" in inject:
+    if "mean" in inject:                 # parity tests / global statistics of a time-sharded field
         mean, std = np.float32(inject["mean"]), np.float32(inject["std"])
+        max_abs = float(inject.get("max_abs", max_abs))
     latent = eng.encode(x, mean, std, batch=batch)                                   # compress.py:66-86
     tm and tm.mark("encode")
     if "recon_std" in inject:

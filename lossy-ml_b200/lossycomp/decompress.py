@@ -15,14 +15,25 @@ import numpy as np
 
 from . import _native as N
 from ._engine import HUFF_MAGIC, Engine
+from .dist import MULTI_MAGIC
 
 
-def decompress_device(eng: Engine, slots, *, inject=None, batch=None):
-    """Returns the reconstruction as a torch float32 CUDA tensor (T,H,W)."""
+def decompress_device(eng: Engine, slots, *, inject=None, batch=None, rows=None):
+    """Returns the reconstruction as a torch float32 CUDA tensor (T,H,W).  `rows=(t0, t1)` (a time
+    shard in whole 16-step chunks, see dist.shard_time) decodes only those rows."""
     torch = eng.torch
     comp_data, lshape, array_size, error_shape, mean, std, comp_error, comp_mask, thr2 = slots
     T, H, W = (int(v) for v in array_size[:3])
     latent, meta = eng.unpack_latent(comp_data, lshape)                              # decompress.py:58-60
+    T_all = T
+    if rows is not None:
+        t0, t1 = rows
+        assert t0 % 16 == 0 and (t1 % 16 == 0 or t1 == T_all) and t1 - t0 >= 16
+        per_tc = latent.shape[0] // (-(-T_all // 16))
+        c0 = (t0 // 16) * per_tc
+        c1 = c0 + (-(-(t1 - t0) // 16)) * per_tc
+        latent = latent[c0:c1].contiguous()
+        T = t1 - t0
     if meta["precision"] != eng.precision:
         raise N.NativeError(f"blob was written with decoder precision {meta['precision']!r}, engine is "
                             f"{eng.precision!r}: the error bound only holds with identical decoder numerics")
@@ -30,18 +41,24 @@ def decompress_device(eng: Engine, slots, *, inject=None, batch=None):
         recon = inject["recon_std"]
     else:
         recon = eng.decode(latent, T, H, W, batch=batch)                             # decompress.py:66-72
-    n = T * H * W
-    if comp_error[:4] == HUFF_MAGIC:
+    n = T_all * H * W
+    if comp_error[:4] in (HUFF_MAGIC, MULTI_MAGIC):
         q = eng.unpack_codes(comp_error)
     else:                                                                            # decompress.py:75-78
         dq = np.frombuffer(bz2.decompress(comp_error), dtype=np.int32).reshape(error_shape)
         q = eng.cumsum(torch.from_numpy(dq.copy()).to(eng.dev))
-    if comp_mask[:4] == HUFF_MAGIC:
+    if comp_mask[:4] in (HUFF_MAGIC, MULTI_MAGIC):
         mask = eng.unpack_mask(comp_mask)
     else:                                                                            # decompress.py:81-84
         dm = np.frombuffer(bz2.decompress(comp_mask), dtype=np.int8).reshape((n,))
         mask = eng.cumsum(torch.from_numpy(dm.copy()).to(eng.dev))
     assert q.numel() == int(error_shape[0]) and mask.numel() == n
+    if rows is not None:                 # this shard's part of the global mask / code streams
+        lo, hi = t0 * H * W, t1 * H * W
+        off = int((mask[:lo] > 0).sum().item())
+        cnt = int((mask[lo:hi] > 0).sum().item())
+        mask = mask[lo:hi].contiguous()
+        q = q[off:off + cnt].contiguous()
     return eng.reconstruct(recon, mask, q, mean, std, thr2)                          # decompress.py:86-104
 
 

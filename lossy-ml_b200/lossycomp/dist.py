@@ -1,0 +1,185 @@
+"""Multi-GPU (one process per GPU, torch.distributed) compress / decompress of a time-sharded field.
+
+The reference is single-process; what shards is the chunk list: chunks are independent
+(dataLoader.py:437-481, no halo), and the chunk index is time-major, so cutting the time axis in
+whole 16-step chunks gives every rank a contiguous chunk range whose local chunk grid (including
+the re-anchored tail window, which is anchored at the END of the axis both locally and globally)
+is exactly its part of the global one.  To produce the blob a single compress() call would have
+produced, only three things cross ranks:
+
+  1. the statistics of channel 0 (compress.py:64-65 are global): all-reduce of {sum, sum^2, n} (SUM)
+     and max|x| (MAX) -- 32 bytes;
+  2. the outlier counts (slot 3) -- 8 bytes per rank;
+  3. the blob parts (latent rows, entropy-coded code / mask streams) gathered to rank 0.
+
+The entropy containers of slots 6/7 become multi-part ('LCM1': one self-contained 'LCH1' stream per
+rank, first differences restarting at every part), so no seam values and no shared Huffman table are
+needed; the decoded mask / codes / reconstruction are bit-identical to the single-GPU ones.
+NCCL carries the collectives on GPUs; the same code runs on gloo with CPU tensors for the host-logic
+tests.
+"""
+from __future__ import annotations
+
+import math
+import pickle
+import struct
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+MULTI_MAGIC = b"LCM1"
+CHUNK_T = 16
+
+
+# ------------------------------------------------------------------------------------------
+# pure host logic (unit-tested on CPU)
+# ------------------------------------------------------------------------------------------
+def shard_time(T: int, world: int) -> List[Tuple[int, int]]:
+    """Rows [begin, end) of every rank: whole 16-step chunks, as even as possible (45 chunks on 8
+    ranks -> 6,6,6,6,6,5,5,5).  A ragged tail (T % 16 != 0) goes to the last non-empty rank, whose
+    shard is then long enough (>= 16 rows) to hold the re-anchored tail window."""
+    assert T >= CHUNK_T, "Chunks size cannot be larger than the data size."
+    n_full = T // CHUNK_T
+    tail = T - n_full * CHUNK_T
+    base, extra = divmod(n_full, world)
+    out, t = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((t, t + n * CHUNK_T))
+        t += n * CHUNK_T
+    if tail:
+        last = max(r for r in range(world) if out[r][1] > out[r][0])
+        out[last] = (out[last][0], out[last][1] + tail)
+        for r in range(last + 1, world):
+            out[r] = (T, T)
+    return out
+
+
+def combine_stats(parts: Sequence[Sequence[float]]):
+    """[(sum, sum^2, max|x|, n)] per rank -> (mean float32, std float32, max|x|), the same formula the
+    single-GPU path applies to its own sums (Engine.stats)."""
+    s = sum(p[0] for p in parts)
+    s2 = sum(p[1] for p in parts)
+    mx = max(p[2] for p in parts)
+    n = sum(p[3] for p in parts)
+    mean64 = s / n
+    var = max(s2 / n - mean64 * mean64, 0.0)
+    return np.float32(mean64), np.float32(math.sqrt(var)), mx
+
+
+def pack_multipart(parts: Sequence[bytes]) -> bytes:
+    """Several self-contained entropy streams -> one slot payload."""
+    if len(parts) == 1:
+        return parts[0]
+    return b"".join([MULTI_MAGIC, struct.pack("<I", len(parts)),
+                     struct.pack(f"<{len(parts)}Q", *(len(p) for p in parts))] + list(parts))
+
+
+def unpack_multipart(blob: bytes) -> List[bytes]:
+    if blob[:4] != MULTI_MAGIC:
+        return [blob]
+    (n,) = struct.unpack("<I", blob[4:8])
+    lens = struct.unpack(f"<{n}Q", blob[8:8 + 8 * n])
+    out, p = [], 8 + 8 * n
+    for ln in lens:
+        out.append(blob[p:p + ln])
+        p += ln
+    return out
+
+
+def assemble_blob(rank_slots: Sequence[list], latent_join) -> list:
+    """Per-rank slot lists (each describing its own time shard) -> the slot list of the whole field.
+    `latent_join(list of slot-0 payloads) -> payload` concatenates the latent containers."""
+    first = rank_slots[0]
+    n_chunks = sum(s[1][0] for s in rank_slots)
+    T = sum(s[2][0] for s in rank_slots)
+    n_out = sum(s[3][0] for s in rank_slots)
+    for s in rank_slots:
+        assert s[4] == first[4] and s[5] == first[5] and s[8] == first[8], "ranks disagree on mean/std/threshold"
+        assert tuple(s[2][1:]) == tuple(first[2][1:]) and tuple(s[1][1:]) == tuple(first[1][1:])
+    return [latent_join([s[0] for s in rank_slots]), (n_chunks,) + tuple(first[1][1:]),
+            (T,) + tuple(first[2][1:]), (n_out,), first[4], first[5],
+            pack_multipart([s[6] for s in rank_slots]), pack_multipart([s[7] for s in rank_slots]), first[8]]
+
+
+# ------------------------------------------------------------------------------------------
+# collectives (NCCL on GPUs, gloo on CPU tensors)
+# ------------------------------------------------------------------------------------------
+def all_reduce_stats(local, group=None, device=None):
+    """local = (sum, sum^2, max|x|, n) -> the same tuple over all ranks."""
+    import torch
+    import torch.distributed as dist
+    a = torch.tensor([local[0], local[1], local[3]], dtype=torch.float64, device=device)
+    m = torch.tensor([local[2]], dtype=torch.float64, device=device)
+    dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    a = a.cpu().tolist()
+    return (a[0], a[1], float(m.item()), a[2])
+
+
+def gather_bytes(payload: bytes, dst: int = 0, group=None, device=None) -> Optional[List[bytes]]:
+    """Variable-length byte strings of all ranks -> list on rank `dst` (None elsewhere).
+    Lengths travel in an all-gather, payloads in one padded gather."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = torch.tensor([len(payload)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if payload:
+        buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(buf.device)
+    if rank == dst:
+        recv = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.gather(buf, recv, dst=dst, group=group)
+        return [r[:sizes[i]].cpu().numpy().tobytes() for i, r in enumerate(recv)]
+    dist.gather(buf, None, dst=dst, group=group)
+    return None
+
+
+# ------------------------------------------------------------------------------------------
+# sharded codec
+# ------------------------------------------------------------------------------------------
+def compress_sharded(eng, x_local, err_threshold, *, mode="strict", codec="huff", group=None, dst=0):
+    """Every rank passes its own rows (a time shard made with shard_time) as a CUDA tensor
+    (T_local, H, W, 2); rank `dst` gets the slot list of the WHOLE field (others None), plus an info
+    dict on every rank."""
+    import torch.distributed as dist
+    from .compress import compress_device
+    dev = eng.dev
+    T_local = int(x_local.shape[0])
+    local = eng.stats_raw(x_local) if T_local else (0.0, 0.0, 0.0, 0.0)
+    mean, std, max_abs = combine_stats([all_reduce_stats(local, group, dev)])
+    if T_local:
+        slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec,
+                                      inject={"mean": mean, "std": std, "max_abs": max_abs})
+        mine = pickle.dumps(slots)
+    else:
+        slots, info, mine = None, {"n_out": 0}, b""
+    parts = gather_bytes(mine, dst, group, dev)
+    if dist.get_rank(group) != dst:
+        return None, info
+    rank_slots = [pickle.loads(p) for p in parts if p]
+    return assemble_blob(rank_slots, eng.join_latents), info
+
+
+def decompress_sharded(eng, slots_or_none, *, group=None, src=0):
+    """Rank `src` holds the slot list; every rank decodes the autoencoder for its own time shard only
+    and returns (rows_begin, rows_end, tensor (T_local, H, W)) of the reconstruction."""
+    import torch
+    import torch.distributed as dist
+    from .decompress import decompress_device
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    obj = [slots_or_none]
+    dist.broadcast_object_list(obj, src=src, group=group)
+    slots = obj[0]
+    T, H, W = (int(v) for v in slots[2][:3])
+    t0, t1 = shard_time(T, world)[rank]
+    if t1 <= t0:
+        return t0, t1, torch.empty((0, H, W), dtype=torch.float32, device=eng.dev)
+    out = decompress_device(eng, slots, rows=(t0, t1))
+    return t0, t1, out

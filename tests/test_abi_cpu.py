@@ -1,0 +1,75 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/lossycomp_b200.h
+declares; the ctypes table mirrors the header; the product path refuses to run without CUDA."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lossycomp_b200.h")
+
+
+def declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lc_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from lossycomp import _native
+    if not os.path.exists(_native.LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "lossy-ml_b200", "csrc"), "-j8"])
+    return _native.lib()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from lossycomp import _native
+    names = declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_native.SIGNATURES), set(names) ^ set(_native.SIGNATURES)
+
+
+def test_host_only_entry_points(lib):
+    assert lib.lc_version() >= 100
+    g = (ctypes.c_int * 3)()
+    assert lib.lc_chunk_grid(32, 721, 1440, ctypes.byref(g)) == 0 and list(g) == [2, 16, 30]   # Chunking_data.ipynb cell 8
+    assert lib.lc_chunk_grid(15, 48, 48, ctypes.byref(g)) != 0
+    assert b"Chunks size cannot be larger" in lib.lc_last_error()
+    assert lib.lc_scan_workspace_bytes(1 << 20) > 0 and lib.lc_stats_workspace_bytes() > 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lossycomp import _native
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    with pytest.raises(_native.NativeError):
+        compress(np.zeros((16, 48, 48, 2), np.float32), 0.1)
+    with pytest.raises(_native.NativeError):
+        decompress(b"")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "lossy-ml_b200", "lossycomp")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("the oracle", ""), fn
+
+
+def test_model_spec_matches_survey():
+    from lossycomp.models import MODEL_1_ARCH, load_model
+    m = load_model()
+    macs = m.arch.macs_per_chunk()
+    assert macs == {"Encoder": 1339836480, "Decoder": 1285572672}          # 2625.4 MMAC
+    assert sum(MODEL_1_ARCH.macs_per_chunk().values()) == 2395504800          # SURVEY: 2395.5 MMAC
+    assert [L.name for L in m.layers][:3] == ["conv3d", "conv3d_1", "conv3d_2"]
+    assert sum(L.kernel.size + L.bias.size for L in m.layers) == 332696
+    assert abs(float(m.layers[-1].bias[0]) - 0.10914003) < 1e-7            # Decoder/conv3d_9/bias

@@ -220,3 +220,38 @@ def test_api_errors(torch):
         compress(np.zeros((16, 48, 48, 3), np.float32), 0.1)
     with pytest.raises(AssertionError):
         compress(np.zeros((15, 48, 48, 2), np.float32), 0.1)
+
+
+def test_time_sharded_compress_equals_single_call(eng, torch):
+    """shards made of whole 16-step chunks + shared statistics reproduce the single-call
+    mask / codes / reconstruction bit for bit (ranks emulated one after the other on one GPU)."""
+    from lossycomp import dist as D
+    from lossycomp.compress import compress_device
+    from lossycomp.decompress import decompress_device
+    g = golden_case("odd_all_axes")
+    x = dev(torch, g["x"])
+    T = x.shape[0]
+    thr = float(g["abs_err"])
+    ref_slots, ref_info = compress_device(eng, x, thr, mode="strict", codec="huff", return_parts=True)
+    shards = D.shard_time(T, 2)
+    assert shards == [(0, 16), (16, 33)]
+    raw = [eng.stats_raw(x[a:b].contiguous()) for a, b in shards]
+    mean, std, mx = D.combine_stats(raw)
+    assert mean == ref_slots[4] and std == ref_slots[5]
+    rank_slots = []
+    for a, b in shards:
+        s, _ = compress_device(eng, x[a:b].contiguous(), thr, mode="strict", codec="huff",
+                               inject={"mean": mean, "std": std, "max_abs": mx})
+        rank_slots.append(pickle.loads(pickle.dumps(s)))
+    slots = D.assemble_blob(rank_slots, eng.join_latents)
+    assert slots[1] == ref_slots[1] and slots[2] == ref_slots[2] and slots[3] == ref_slots[3]
+    assert slots[8] == ref_slots[8]
+    np.testing.assert_array_equal(eng.unpack_mask(slots[7]).cpu().numpy(), ref_info["mask"].cpu().numpy())
+    np.testing.assert_array_equal(eng.unpack_codes(slots[6]).cpu().numpy(), ref_info["q"].cpu().numpy())
+    whole = decompress_device(eng, slots).cpu().numpy()
+    np.testing.assert_array_equal(whole, decompress_device(eng, ref_slots).cpu().numpy())
+    # sharded decode: every rank reconstructs only its rows
+    for a, b in shards:
+        part = decompress_device(eng, slots, rows=(a, b)).cpu().numpy()
+        np.testing.assert_array_equal(part, whole[a:b])
+    assert np.abs(g["x"][..., 0].astype(np.float64) - whole).max() <= thr
