@@ -55,12 +55,19 @@ __device__ __forceinline__ void unpack8(const uint4 v, int half, float f[8]) {
     f[2 * i + 1] = h16_to_float((unsigned short)(w[i] >> 16), half);
   }
 }
+// two floats -> one packed 16-bit pair with a single F2FP instruction (same round-to-nearest-even
+// results as two scalar conversions; fp16 saturates at +-65504 like float_to_h16)
+__device__ __forceinline__ unsigned pack2(float a, float b, int half) {
+  if (half) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<const unsigned*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const unsigned*>(&h);
+}
 __device__ __forceinline__ uint4 pack8(const float f[8], int half) {
-  unsigned w[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    w[i] = (unsigned)float_to_h16(f[2 * i], half) | ((unsigned)float_to_h16(f[2 * i + 1], half) << 16);
-  return make_uint4(w[0], w[1], w[2], w[3]);
+  return make_uint4(pack2(f[0], f[1], half), pack2(f[2], f[3], half), pack2(f[4], f[5], half),
+                    pack2(f[6], f[7], half));
 }
 
 // round a float through the 16-bit operand format (host side, for weights)

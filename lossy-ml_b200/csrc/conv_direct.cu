@@ -168,9 +168,11 @@ __global__ void __launch_bounds__(512, 1) conv_direct_kernel(ConvParams p) {
 }
 
 // Small layers (the innermost levels: <= 128 output voxels per chunk): one warp per output voxel,
-// lane = output channel.  Weights are read straight from L2 (coalesced over cout), the input value is
-// a warp-wide broadcast; no shared-memory staging of the whole kernel per CTA, which is what made
-// the big-tile kernel latency-bound here.  Same arithmetic: fp32 FMA, taps in (kt,kh,kw,ci) order.
+// lane = INPUT channel.  Every lane accumulates its channel's contribution to all output channels over
+// all taps (independent weight loads -> plenty of memory-level parallelism, unlike a serial k loop),
+// then the 32 partial sums of each output channel are added by a fixed butterfly.  Deterministic;
+// the summation order differs from conv_direct_kernel, but a layer always runs on the same kernel.
+template <int CO>
 __global__ void __launch_bounds__(256) conv_small_kernel(ConvParams p) {
   const int lane = threadIdx.x & 31;
   const int OT = p.out.T, OH = p.out.H, OW = p.out.W;
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(256) conv_small_kernel(ConvParams p) {
   const int ovox = OT * OH * OW;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int ci = lane;
   for (long long v = warp0; v < p.total_vox; v += nwarps) {
     const int chunk = (int)(v / ovox);
     int r = (int)(v % ovox);
@@ -185,8 +188,9 @@ __global__ void __launch_bounds__(256) conv_small_kernel(ConvParams p) {
     r /= OW;
     const int oh = r % OH;
     const int ot = r / OH;
-    const int co = lane;
-    float acc = (co < p.cout) ? p.b[co] : 0.f;
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
     for (int kt = 0; kt < p.k; ++kt) {
       int it;
       if (p.kind == 0) {
@@ -217,34 +221,37 @@ __global__ void __launch_bounds__(256) conv_small_kernel(ConvParams p) {
             iw = num / p.stride;
           }
           if (iw < 0 || iw >= IW) continue;
-          const float* wt = p.w + (size_t)((kt * p.k + kh) * p.k + kw) * p.cin * p.cout;
-          if (p.in.fmt == FMT_F32) {
-            const float* xin = reinterpret_cast<const float*>(p.in.base) + (size_t)chunk * p.in.chunk_stride +
-                               ((size_t)(it * IH + ih) * IW + iw) * p.cin;
-            for (int ci = 0; ci < p.cin; ++ci) {
-              const float x = __ldg(xin + ci);
-              const float w = (co < p.cout) ? __ldg(wt + (size_t)ci * p.cout + co) : 0.f;
-              acc = fmaf(x, w, acc);
+          float x = 0.f;
+          if (ci < p.cin) {
+            if (p.in.fmt == FMT_F32) {
+              x = __ldg(reinterpret_cast<const float*>(p.in.base) + (size_t)chunk * p.in.chunk_stride +
+                        ((size_t)(it * IH + ih) * IW + iw) * p.cin + ci);
+            } else {
+              const unsigned short* xp = reinterpret_cast<const unsigned short*>(
+                  reinterpret_cast<const uint4*>(p.in.base) + gp_vec_index(p.in, chunk, it, ih, iw, ci >> 3));
+              x = h16_to_float(xp[ci & 7], p.in.half);
             }
-          } else {
-            const uint4* xin = reinterpret_cast<const uint4*>(p.in.base);
-            for (int g = 0; g < p.in.G; ++g) {
-              float f[8];
-              unpack8(__ldg(xin + gp_vec_index(p.in, chunk, it, ih, iw, g)), p.in.half, f);
+            const float* wt = p.w + ((size_t)((kt * p.k + kh) * p.k + kw) * p.cin + ci) * p.cout;
 #pragma unroll
-              for (int k8 = 0; k8 < 8; ++k8) {
-                const int ci = g * 8 + k8;
-                if (ci < p.cin) {
-                  const float w = (co < p.cout) ? __ldg(wt + (size_t)ci * p.cout + co) : 0.f;
-                  acc = fmaf(f[k8], w, acc);
-                }
-              }
-            }
+            for (int c = 0; c < CO; ++c)
+              if (c < p.cout) acc[c] = fmaf(x, __ldg(wt + c), acc[c]);
           }
         }
       }
     }
-    // epilogue: lane = channel
+    // butterfly over the input channels; afterwards every lane holds all sums
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    // epilogue: lane = output channel
+    float y = 0.f;
+#pragma unroll
+    for (int c = 0; c < CO; ++c)
+      if (c == lane) y = acc[c];
+    const int co = lane;
+    if (co < p.cout) y += p.b[co];
     if (p.skip.base) {
       float sk = 0.f;
       if (p.skip.fmt == FMT_F32) {
@@ -256,16 +263,16 @@ __global__ void __launch_bounds__(256) conv_small_kernel(ConvParams p) {
             reinterpret_cast<const uint4*>(p.skip.base) + gp_vec_index(p.skip, chunk, ot, oh, ow, co >> 3));
         sk = h16_to_float(sp[co & 7], p.skip.half);
       }
-      acc = __fadd_rn(acc, sk);
+      y = __fadd_rn(y, sk);
     }
-    if (p.relu) acc = fmaxf(acc, 0.f);
+    if (p.relu) y = fmaxf(y, 0.f);
     if (p.out.fmt == FMT_F32) {
       if (co < p.cout)
-        reinterpret_cast<float*>(p.out.base)[(size_t)chunk * p.out.chunk_stride + (size_t)(v % ovox) * p.cout + co] = acc;
+        reinterpret_cast<float*>(p.out.base)[(size_t)chunk * p.out.chunk_stride + (size_t)(v % ovox) * p.cout + co] = y;
     } else if (co < p.out.G * 8) {
       unsigned short* op = reinterpret_cast<unsigned short*>(
           reinterpret_cast<uint4*>(p.out.base) + gp_vec_index(p.out, chunk, ot, oh, ow, co >> 3));
-      op[co & 7] = float_to_h16(co < p.cout ? acc : 0.f, p.out.half);
+      op[co & 7] = float_to_h16(co < p.cout ? y : 0.f, p.out.half);
     }
   }
 }
@@ -311,12 +318,13 @@ int conv_direct_views(const lc_codec* h, const DevLayer& L, const float* d_w, co
   p.kind = L.kind; p.k = L.k; p.stride = L.stride; p.cin = L.cin; p.cout = L.cout;
   p.relu = L.relu; p.pad_lo = L.pad_lo;
   p.total_vox = (long long)n_chunks * L.out_t * L.out_h * L.out_w;
-  if (L.out_t * L.out_h * L.out_w <= 128 && L.cout <= 32 && (out.fmt == FMT_F32 || out.G * 8 <= 32) &&
+  if (L.out_t * L.out_h * L.out_w <= 128 && L.cout <= 24 && L.cin <= 32 && (out.fmt == FMT_F32 || out.G * 8 <= 32) &&
       !getenv("LOSSYCOMP_NO_SMALL")) {
     long long blocks = (p.total_vox + 7) / 8;
     if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
     if (blocks < 1) blocks = 1;
-    conv_small_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+    if (L.cout <= 8) conv_small_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(p);
+    else conv_small_kernel<24><<<(unsigned)blocks, 256, 0, s>>>(p);
     LC_LAUNCH_CHECK();
     return LC_OK;
   }

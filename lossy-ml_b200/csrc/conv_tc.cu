@@ -32,7 +32,7 @@
 
 namespace {
 
-constexpr int kTcThreads = 320;   // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue
+constexpr int kTcThreads = 352;   // warp 0 producer, warps 1 and 10 MMA issuers (alternate planes), warps 2-9 epilogue
 constexpr int kHalf = 12;         // output channels per epilogue thread (two threads share a TMEM lane)
 constexpr int kMaxKs = 24;
 constexpr int kMaxVar = 4;
@@ -60,6 +60,7 @@ struct SweepParams {
   int slab_slots, slab_start;    // the stage holds slots [row0 + 128*j + slab_start, +slab_slots) of every plane
   int stages;
   int nbuf, acc_stride, tmem_cols;   // TMEM accumulator ring
+  int skip_tile;                     // K3 with residual add: the skip tile of the plane rides in the stage (bulk copy)
   // MMA
   int N, nks, nvar;
   const uint4* wimg;
@@ -146,8 +147,7 @@ __device__ __forceinline__ void unpack4(const uint2 v, int half16, float f[4]) {
   f[3] = h16_to_float((unsigned short)(v.y >> 16), half16);
 }
 __device__ __forceinline__ uint2 pack4(const float f[4], int half16) {
-  return make_uint2((unsigned)float_to_h16(f[0], half16) | ((unsigned)float_to_h16(f[1], half16) << 16),
-                    (unsigned)float_to_h16(f[2], half16) | ((unsigned)float_to_h16(f[3], half16) << 16));
+  return make_uint2(pack2(f[0], f[1], half16), pack2(f[2], f[3], half16));
 }
 
 struct SkipRegs {
@@ -169,11 +169,25 @@ __device__ __forceinline__ SkipRegs load_skip(const SweepParams& p, const VoxAdd
   return r;
 }
 
-__device__ __forceinline__ void store_voxel(const SweepParams& p, const float* s_bias, const VoxAddr& va, int t,
+// skip tile in shared memory: [group][128 rows][16 bytes]
+__device__ __forceinline__ SkipRegs load_skip_smem(const uint8_t* tile, int row, int half) {
+  SkipRegs r;
+  const uint4* g0 = reinterpret_cast<const uint4*>(tile) + row;
+  if (half == 0) {
+    r.a = g0[0];
+    r.b = *reinterpret_cast<const uint2*>(g0 + 128);
+  } else {
+    r.b = *(reinterpret_cast<const uint2*>(g0 + 128) + 1);
+    r.a = g0[256];
+  }
+  return r;
+}
+
+__device__ __forceinline__ void store_voxel(const SweepParams& p, const float (&bias_r)[kHalf], const VoxAddr& va, int t,
                                             int half, const float (&acc)[kHalf], const SkipRegs* skp) {
   float y[kHalf];
 #pragma unroll
-  for (int c = 0; c < kHalf; ++c) y[c] = acc[c] + s_bias[half * kHalf + c];
+  for (int c = 0; c < kHalf; ++c) y[c] = acc[c] + bias_r[c];
   // y[0..7]/y[8..11] for half 0 are (vector g0, low half of g1); for half 1 y[0..3]/y[4..11] are
   // (high half of g1, vector g2)
   if (skp) {
@@ -230,7 +244,8 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab_bytes = p.slab_slots * 16;
-  const int stage_bytes = p.in_NPG * slab_bytes;
+  const int skip_bytes = p.skip_tile ? p.skip.G * 128 * 16 : 0;
+  const int stage_bytes = p.in_NPG * slab_bytes + skip_bytes;
   uint8_t* sB = smem;
   uint8_t* sA = smem + ((p.wimg_bytes + 127) & ~127);
   // operand descriptors of every (variant, K step) for stage 0; the issuer adds the stage offset
@@ -273,44 +288,58 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
             umma::bulk_g2s(sA + stage * stage_bytes + g * slab_bytes,
                            p.in + slab0 + (long long)(t * p.in_NPG + g) * p.in_S, (uint32_t)slab_bytes,
                            &full[stage]);
+          if (p.skip_tile) {   // rows of this tile of skip plane t (consumed when output plane t is finalised)
+            const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride +
+                              p.skip.GL + p.row0 + tile * 128;
+            for (int g = 0; g < p.skip.G; ++g)
+              umma::bulk_g2s(sA + stage * stage_bytes + p.in_NPG * slab_bytes + g * 2048,
+                             sk + (long long)(t * p.skip.G + g) * p.skip.S, 2048u, &full[stage]);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: one elected thread =====================
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers: one elected thread each =====================
+    // Two issuers take alternate planes (different TMEM accumulators, so their MMAs may interleave
+    // freely on the tensor pipe): the ~400-1000 clk of waits + commit one issuer spends per plane
+    // overlap the other's MMAs instead of draining the pipe.
     if (lane == 0) {
+      const int me = (warp == 10) ? 1 : 0;
+      const int n_issuers = (p.debug & 16) ? 1 : 2;
       umma::mbar_wait(&wbar, 0);
       const uint32_t idesc = umma::make_idesc(128, p.N, p.half ? 0 : 1);
-      int stage = 0, phase = 0, buf = 0, bphase = 0;
+      int stage = 0, phase = 0, buf = 0, bphase = 0, step = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int var = 0;
         if (MODE == MODE_UP) var = ((item % per_chunk) / p.tiles_per_chunk);
-        for (int t = 0; t < p.in_T; ++t) {
+        for (int t = 0; t < p.in_T; ++t, ++step) {
           if (MODE == MODE_DOWN) var = t & 1;
-          const uint64_t* da = s_da + var * kMaxKs;
-          const uint64_t* db = s_db + var * kMaxKs;
-          const uint64_t stage_add = (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
-          uint64_t da_n = da[0] + stage_add, db_n = db[0];
-          umma::mbar_wait(&tempty[buf], bphase ^ 1);
-          umma::mbar_wait(&full[stage], phase);
-          umma::tcgen05_fence_after();
-          const uint32_t d_addr = tmem + buf * p.acc_stride;
+          const bool mine = (n_issuers == 1) ? (me == 0) : ((step & 1) == me);
+          if (mine) {
+            const uint64_t* da = s_da + var * kMaxKs;
+            const uint64_t* db = s_db + var * kMaxKs;
+            const uint64_t stage_add = (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
+            uint64_t da_n = da[0] + stage_add, db_n = db[0];
+            umma::mbar_wait(&tempty[buf], bphase ^ 1);
+            umma::mbar_wait(&full[stage], phase);
+            umma::tcgen05_fence_after();
+            const uint32_t d_addr = tmem + buf * p.acc_stride;
 #pragma unroll 2
-          for (int ks = 0; ks < ((p.debug & 1) ? 0 : p.nks); ++ks) {
-            const uint64_t a = da_n, b = db_n;
-            if (ks + 1 < p.nks) { da_n = da[ks + 1] + stage_add; db_n = db[ks + 1]; }
-            umma::mma_f16(d_addr, a, b, idesc, ks > 0);
+            for (int ks = 0; ks < ((p.debug & 1) ? 0 : p.nks); ++ks) {
+              const uint64_t a = da_n, b = db_n;
+              if (ks + 1 < p.nks) { da_n = da[ks + 1] + stage_add; db_n = db[ks + 1]; }
+              umma::mma_f16(d_addr, a, b, idesc, ks > 0);
+            }
+            // one commit per plane: it signals the epilogue, which releases the smem stage
+            umma::commit(&tfull[buf]);
           }
-          // one commit per step (a commit costs the issuing thread ~300 cycles): it signals the epilogue,
-          // which releases the shared-memory stage on the producer's behalf
-          umma::commit(&tfull[buf]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
           if (++buf == p.nbuf) { buf = 0; bphase ^= 1; }
         }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     // 8 warps: warp w reads TMEM lanes 32*(w&3)..+31 (hardware rule); warps 2-5 take output channels
     // 0..11 of every dt block, warps 6-9 channels 12..23.
@@ -319,6 +348,9 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + half * kHalf;
     const bool has_skip = p.skip.base != nullptr;
+    float bias_r[kHalf];
+#pragma unroll
+    for (int c = 0; c < kHalf; ++c) bias_r[c] = s_bias[half * kHalf + c];
     int ebuf = 0, ephase = 0;
     int estage = 0;
     auto wait_d = [&]() -> uint32_t {
@@ -326,8 +358,11 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       umma::mbar_wait(&tfull[buf], ephase);
       umma::tcgen05_fence_after();
       // the MMAs that read this step's stage are complete: hand the stage back to the producer
-      if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
-      if (++estage == p.stages) estage = 0;
+      // (K3 with a skip tile keeps it one step longer and releases it itself after reading the tile)
+      if (!p.skip_tile) {
+        if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
+        if (++estage == p.stages) estage = 0;
+      }
       return lane_addr + buf * p.acc_stride;
     };
     auto release_d = [&]() {
@@ -352,7 +387,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
         SkipRegs sk;
         for (int t = 0; t < p.in_T; ++t) {
           // the skip values of the plane finished in this step are fetched before waiting for the MMA
-          if (has_skip && t >= 1 && ri.valid) sk = load_skip(p, va, t - 1, half);
+          if (has_skip && !p.skip_tile && t >= 1 && ri.valid) sk = load_skip(p, va, t - 1, half);
           const uint32_t ta = wait_d();
           if (!(p.debug & 2)) {
             float db[3][kHalf];
@@ -363,14 +398,27 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           } else {
             release_d();
           }
-          if (t >= 1 && ri.valid && !(p.debug & 4)) store_voxel(p, s_bias, va, t - 1, half, aP, has_skip ? &sk : nullptr);
+          if (p.skip_tile && t >= 1) {
+            // skip tile of plane t-1 sits in the previous step's stage: read it, then release that stage
+            sk = load_skip_smem(sA + estage * stage_bytes + p.in_NPG * slab_bytes, row, half);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
+            if (++estage == p.stages) estage = 0;
+          }
+          if (t >= 1 && ri.valid && !(p.debug & 4)) store_voxel(p, bias_r, va, t - 1, half, aP, has_skip ? &sk : nullptr);
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { aP[c] = aC[c]; aC[c] = aN[c]; }
         }
         if (ri.valid) {
-          if (has_skip) sk = load_skip(p, va, p.in_T - 1, half);
-          store_voxel(p, s_bias, va, p.in_T - 1, half, aP, has_skip ? &sk : nullptr);
+          if (has_skip && !p.skip_tile) sk = load_skip(p, va, p.in_T - 1, half);
         }
+        if (p.skip_tile) {
+          sk = load_skip_smem(sA + estage * stage_bytes + p.in_NPG * slab_bytes, row, half);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
+          if (++estage == p.stages) estage = 0;
+        }
+        if (ri.valid) store_voxel(p, bias_r, va, p.in_T - 1, half, aP, has_skip ? &sk : nullptr);
       } else if (MODE == MODE_K4) {
         // k=4, pad 1/2: block dt -> output plane t_in - dt + 1  (planes t+1, t, t-1, t-2)
         float a1[kHalf], a2[kHalf], a3[kHalf], a0[kHalf];
@@ -383,13 +431,13 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           release_d();
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { a0[c] = db[0][c]; a1[c] += db[1][c]; a2[c] += db[2][c]; a3[c] += db[3][c]; }
-          if (t >= 2 && ri.valid) store_voxel(p, s_bias, va, t - 2, half, a3, nullptr);
+          if (t >= 2 && ri.valid) store_voxel(p, bias_r, va, t - 2, half, a3, nullptr);
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { a3[c] = a2[c]; a2[c] = a1[c]; a1[c] = a0[c]; }
         }
         if (ri.valid) {
-          store_voxel(p, s_bias, va, p.in_T - 2, half, a3, nullptr);
-          store_voxel(p, s_bias, va, p.in_T - 1, half, a2, nullptr);
+          store_voxel(p, bias_r, va, p.in_T - 2, half, a3, nullptr);
+          store_voxel(p, bias_r, va, p.in_T - 1, half, a2, nullptr);
         }
       } else if constexpr (MODE == MODE_K4_OUT1) {
         // cout = 1, taps dt and dw folded into N: column dt*4+dw of row r is the contribution of input
@@ -455,12 +503,12 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 #pragma unroll
             for (int c = 0; c < kHalf; ++c) { aN[c] += db[0][c]; aO[c] += db[1][c]; }
             const int m = t >> 1;
-            if (m >= 1 && ri.valid) store_voxel(p, s_bias, va, m - 1, half, aO, nullptr);
+            if (m >= 1 && ri.valid) store_voxel(p, bias_r, va, m - 1, half, aO, nullptr);
 #pragma unroll
             for (int c = 0; c < kHalf; ++c) aO[c] = aN[c];
           }
         }
-        if (ri.valid) store_voxel(p, s_bias, va, p.out_T - 1, half, aO, nullptr);
+        if (ri.valid) store_voxel(p, bias_r, va, p.out_T - 1, half, aO, nullptr);
       } else if (MODE == MODE_UP) {
         // output plane 2*t_in + kt - 1; block kt.  Planes 2t-1 and 2t complete at step t.
         float cX[kHalf], cY[kHalf];
@@ -473,12 +521,12 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           release_d();
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { cX[c] += db[0][c]; cY[c] += db[1][c]; }
-          if (t >= 1 && ri.valid) store_voxel(p, s_bias, va, 2 * t - 1, half, cX, nullptr);
-          if (ri.valid) store_voxel(p, s_bias, va, 2 * t, half, cY, nullptr);
+          if (t >= 1 && ri.valid) store_voxel(p, bias_r, va, 2 * t - 1, half, cX, nullptr);
+          if (ri.valid) store_voxel(p, bias_r, va, 2 * t, half, cY, nullptr);
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { cX[c] = db[2][c]; cY[c] = db[3][c]; }
         }
-        if (ri.valid) store_voxel(p, s_bias, va, 2 * p.in_T - 1, half, cX, nullptr);
+        if (ri.valid) store_voxel(p, bias_r, va, 2 * p.in_T - 1, half, cX, nullptr);
       }
     }
   }
@@ -913,8 +961,10 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   LC_CUDA(cudaMemcpy(L.d_wtc, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   L.wtc_bytes = img.size() * 2;
   p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
-  const int stage_bytes = p.in_NPG * p.slab_slots * 16;
-  const int budget = ((mode == MODE_K3 || mode == MODE_K4 || mode == MODE_UP) ? 100 : 200) * 1024;
+  const bool want_skip_tile = (mode == MODE_K3) && L.res_add && !getenv("LOSSYCOMP_NO_SKIP_TILE");
+  p.skip_tile = want_skip_tile ? 1 : 0;
+  const int stage_bytes = p.in_NPG * p.slab_slots * 16 + (want_skip_tile ? 3 * 2048 : 0);
+  const int budget = ((mode == MODE_K3 || mode == MODE_K4 || mode == MODE_UP) ? 110 : 200) * 1024;
   const int fixed = ((p.wimg_bytes + 127) & ~127) + 256;
   int stages = (budget - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1040,6 +1090,7 @@ static int tc_run(lc_codec* h, int first, int count, const ActView& first_in, vo
       p.in_cs = cur.chunk_stride;
       p.out = out;
       if (L.res_add) p.skip = skip_v;
+      if (p.skip_tile && (!L.res_add || p.skip.PW != p.row_PW || p.skip.G != 3 || p.skip.NP != 1)) p.skip_tile = 0;
       p.n_items = n_chunks * p.tiles_per_chunk * p.n_classes;
       if (lp.backend == MODE_K4_OUT1) {
         p.out_f32 = recon_out;
