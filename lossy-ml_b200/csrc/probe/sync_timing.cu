@@ -14,7 +14,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-__global__ void __launch_bounds__(128) sync_kernel(int reps, int nmma, int mode, long long* out) {
+__global__ void __launch_bounds__(128) sync_kernel(int reps, int nmma, int mode, long long* out, int a_shift = 0, int k_stride = 32) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t barA, barB;
   __shared__ uint32_t tmem_base_s;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) sync_kernel(int reps, int nmma, int mode,
     if (lane == 0 && warp < W) {
       long long t0 = clock64();
       for (int r = 0; r < reps; ++r)
-        for (int k = 0; k < nmma; ++k) umma::mma_f16(tmem + warp * 80, da + (uint64_t)(k * 2), db80, idesc80, k > 0);
+        for (int k = 0; k < nmma; ++k) umma::mma_f16(tmem + warp * 80, da + (uint64_t)((a_shift + k * k_stride) >> 4), db80, idesc80, k > 0);
       umma::commit(warp == 0 ? &barA : &barB);
       if (warp == 0) { umma::mbar_wait(&barA, 0); out[0] = clock64() - t0; }
     }
@@ -147,6 +147,12 @@ int main() {
     {11, 14, "1 warp issuing 14 MMAs/step (N=80)"}, {12, 14, "2 warps issuing concurrently, 14 MMAs/step each"},
     {13, 14, "3 warps issuing concurrently"}, {14, 14, "4 warps issuing concurrently"},
     {4, 0, "pipeline 2 buffers, 0 MMAs/step"}, {4, 28, "pipeline 2 buffers, 28 MMAs/step"}, {4, 6, "pipeline 2 buffers, 6 MMAs/step"}};
+  for (int shift : {0, 16, 64, 112}) for (int ks : {0, 32, 128, 816}) {
+    sync_kernel<<<1, 128, 48 * 1024>>>(reps, 14, 12, d, shift, ks);
+    cudaDeviceSynchronize();
+    long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("2 issuers, A start shift %3d B, per-MMA A stride %4d B: %6.1f cycles per MMA (aggregate)\n", shift, ks, (double)h / reps / 28);
+  }
   for (auto& c : cases) {
     sync_kernel<<<1, 128, 48 * 1024>>>(reps, c.nmma, c.mode, d);
     cudaError_t e = cudaDeviceSynchronize();

@@ -18,8 +18,8 @@ for i in range(3): lat = eng.encode(x, mean, std)
 ms, cnt = eng.profile_read()
 print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms[:7]))
 ''' % (ROOT, ROOT)
-for dbg, label in [(0, "full"), (16, "single issuer"), (2 + 4, "no epilogue loads/stores"), (1, "no MMA"),
-                   (1 + 2 + 4 + 8, "only barriers")]:
+for dbg, label in [(0, "full"), (6, "no epilogue loads/stores"), (1, "no MMA"), (15, "only barriers"),
+                   ]:
     env = dict(os.environ, LOSSYCOMP_TC_DEBUG=str(dbg))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]

@@ -1,0 +1,13 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lossy-ml_b200")); sys.path.insert(0, ROOT)
+import torch
+from lossycomp import _native as N
+from lossycomp._engine import Engine
+eng = Engine.get(None, "fp16", 0)
+T, H, W = 24, 720, 1440
+x = torch.empty((T, H, W, 2), dtype=torch.float32, device="cuda")
+N.check(eng.lib.lc_synth_field(x.data_ptr(), T, H, W, 0, 0, 1234, None), "synth")
+mean, std, _ = eng.stats(x)
+lat = eng.encode(x, mean, std)
+torch.cuda.synchronize()
