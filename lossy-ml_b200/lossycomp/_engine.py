@@ -377,6 +377,95 @@ class Engine:
         self.launches += 2 if meta["diff"] else 1
         return q
 
+    # -- fused entropy stage: both streams, two host syncs in total --------------------------
+    def _pinned(self, name, nbytes):
+        b = self._small.get("pin_" + name)
+        if b is None or b.numel() < nbytes:
+            b = self.torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=self.torch.uint8, pin_memory=True)
+            self._small["pin_" + name] = b
+        return b
+
+    def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str):
+        """Enqueue the Huffman packing of `sym` and the device->pinned-host copies; no sync."""
+        t = self.torch
+        n = sym.numel()
+        nseg = (n + SEG - 1) // SEG
+        cap = ((bits + 31) // 32) * 4 + 16
+        out = t.zeros(cap, dtype=t.uint8, device=self.dev)
+        segb = t.empty(max(nseg, 1) + 1, dtype=t.int64, device=self.dev)
+        tab = np.concatenate((table.code.view(np.uint8), table.len))            # 1024 + 256 bytes, one H2D
+        d_tab = t.from_numpy(tab.copy()).to(self.dev, non_blocking=True)
+        ws = self._buf("scan_" + tag, self.lib.lc_huff_workspace_bytes(n, SEG))
+        N.check(self.lib.lc_huff_encode(_ptr(sym), n, C.c_void_p(d_tab.data_ptr()),
+                                        C.c_void_p(d_tab.data_ptr() + 1024), SEG, _ptr(out), _ptr(segb),
+                                        C.c_void_p(segb.data_ptr() + 8 * max(nseg, 1)), _ptr(ws), self._stream()),
+                "lc_huff_encode")
+        self.launches += 1
+        nbytes = (bits + 7) // 8
+        h_out = self._pinned("pay_" + tag, nbytes)
+        h_seg = self._pinned("seg_" + tag, 8 * (nseg + 1))
+        h_out[:nbytes].copy_(out[:nbytes], non_blocking=True)
+        h_seg[:8 * (nseg + 1)].copy_(segb[:nseg + 1].view(t.uint8), non_blocking=True)
+        return dict(n=n, nseg=nseg, bits=bits, nbytes=nbytes, h_out=h_out, h_seg=h_seg, table=table, keep=(out, segb, d_tab))
+
+    def _finish_pack(self, job, extra: dict, tail: bytes = b"") -> bytes:
+        """After the sync: assemble the 'LCH1' container with a single copy of the payload."""
+        nseg, bits = job["nseg"], job["bits"]
+        offs = np.frombuffer(job["h_seg"].numpy(), dtype=np.int64, count=nseg + 1)
+        assert int(offs[nseg]) == bits
+        lens = np.diff(offs[:nseg + 1]).astype(np.uint32) if nseg else np.zeros(0, np.uint32)
+        meta = dict(extra, n=int(job["n"]), seg=SEG, bits=int(bits), ref_tree=bool(job["table"].reference_tree))
+        mj = json.dumps(meta).encode()
+        tb = job["table"].to_bytes()
+        return b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), lens.size), mj, tb, lens.tobytes(),
+                         memoryview(job["h_out"].numpy())[:job["nbytes"]], tail])
+
+    def pack_streams(self, mask, q):
+        """Entropy-code the mask and the code stream together -> (comp_error, comp_mask).
+        Same containers as pack_codes()/pack_mask(); the two pipelines share their host syncs."""
+        t = self.torch
+        n_m, n_q = mask.numel(), q.numel()
+        if n_q == 0 or n_m == 0:
+            return self.pack_codes(q), self.pack_mask(mask)
+        # ---- pass 1 (async): symbols of the mask, histograms of everything
+        sym_m = t.empty((n_m + 4) // 5, dtype=t.uint8, device=self.dev)
+        N.check(self.lib.lc_pack_trits(_ptr(mask), n_m, _ptr(sym_m), self._stream()), "lc_pack_trits")
+        h3 = t.empty(768, dtype=t.int32, device=self.dev)
+        N.check(self.lib.lc_hist_u8(_ptr(sym_m), sym_m.numel(), _ptr(h3), self._stream()), "lc_hist_u8")
+        cand = ((0, 0), (1, 127))
+        N.check(self.lib.lc_hist_codes(_ptr(q), n_q, ESC, cand[0][1], cand[1][1],
+                                       C.c_void_p(h3.data_ptr() + 1024), self._stream()), "lc_hist_codes")
+        self.launches += 3
+        hh = h3.cpu().numpy().astype(np.int64) & 0xFFFFFFFF                       # sync 1
+        hist_m, hists_q = hh[:256], (hh[256:512], hh[512:])
+        # ---- host: tables
+        tab_m = HF.build_table(hist_m)
+        tabs_q = [HF.build_table(h) for h in hists_q]
+        costs = [tb.encoded_bits(h) + 32 * int(h[ESC]) for tb, h in zip(tabs_q, hists_q)]
+        pick = 0 if costs[0] <= costs[1] else 1
+        diff, bias = cand[pick]
+        ne = int(hists_q[pick][ESC])
+        # ---- pass 2 (async): symbolise the codes, pack both streams, copy out
+        sym_q = t.empty(n_q, dtype=t.uint8, device=self.dev)
+        esc = t.empty(max(ne, 1), dtype=t.int32, device=self.dev)
+        nesc = t.zeros(1, dtype=t.int64, device=self.dev)
+        ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n_q))
+        N.check(self.lib.lc_symbolize_i32(_ptr(q), n_q, diff, bias, ESC, _ptr(sym_q), _ptr(esc), _ptr(nesc),
+                                          _ptr(ws), self._stream()), "lc_symbolize_i32")
+        self.launches += 1
+        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m")
+        job_q = self._launch_pack(sym_q, tabs_q[pick], tabs_q[pick].encoded_bits(hists_q[pick]), "q")
+        h_esc = None
+        if ne:
+            h_esc = self._pinned("esc", 4 * ne)
+            h_esc[:4 * ne].copy_(esc[:ne].view(t.uint8), non_blocking=True)
+        self.torch.cuda.current_stream(self.dev).synchronize()                    # sync 2
+        escb = bytes(memoryview(h_esc.numpy())[:4 * ne]) if ne else b""
+        comp_mask = self._finish_pack(job_m, {"kind": "mask5", "n_mask": int(n_m)})
+        comp_error = self._finish_pack(job_q, {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne},
+                                       tail=escb)
+        return comp_error, comp_mask
+
     # -- latent slot (compress.py:142-144; fpzip is replaced by a tagged container) -----
     def pack_latent(self, latent, codec="raw") -> bytes:
         meta = {"precision": self.precision, "model": self.model.arch.name,

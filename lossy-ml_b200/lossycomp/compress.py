@@ -102,10 +102,8 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         comp_error = bz2.compress(dq.tobytes(), 9)                                   # compress.py:156
         comp_mask = bz2.compress(dm.tobytes(), 9)                                    # compress.py:166
     elif codec == "huff":
-        comp_error = eng.pack_codes(q)
-        tm and tm.mark("pack_codes")
-        comp_mask = eng.pack_mask(mask)
-        tm and tm.mark("pack_mask")
+        comp_error, comp_mask = eng.pack_streams(mask, q)
+        tm and tm.mark("pack_streams")
     else:
         raise ValueError("codec must be 'huff' or 'bz2'")
     slots = [comp_data, lshape, (T, H, W, int(x.shape[3])), (n_out,), mean, std, comp_error, comp_mask, thr2]
