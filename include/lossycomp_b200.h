@@ -156,7 +156,7 @@ int lc_pack_trits(const int8_t* d_mask, int64_t n, uint8_t* d_sym, void* stream)
 int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* stream);
 
 /* Huffman bit packing from a host-built table: code[s] (right-aligned, MSB of the code is
- * emitted first) and len[s] (0..32).  The stream is cut into segments of `seg` symbols; each
+ * emitted first) and len[s] (0..32).  The stream is cut into segments of `seg` (= 1024) symbols; each
  * segment starts at the bit offset d_seg_bits[i] (uint64, exclusive scan written by the call),
  * bits are big-endian within bytes exactly like the '0101..' strings of huffman.py.
  * d_total_bits receives the stream length in bits.  d_out must be zero-initialised and hold

@@ -159,9 +159,11 @@ unsymbolize_kernel(const uint8_t* __restrict__ sym, long long n, int bias, int e
 }
 
 // ---------------------------------------------------------------- Huffman pack
-// one tile == one segment of kSeg symbols; thread owns 16 consecutive symbols
+// one tile = 256 threads x 16 consecutive symbols = 4 independently decodable segments of kSeg symbols
 constexpr int kSegItems = 16;
-constexpr int kSeg = kThreads * kSegItems;   // 4096
+constexpr int kTileSyms = kThreads * kSegItems;   // 4096
+constexpr int kSeg = 1024;                        // symbols per segment (64 threads)
+constexpr int kSegPerTile = kTileSyms / kSeg;
 
 __global__ void __launch_bounds__(kThreads)
 huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t* __restrict__ code,
@@ -173,7 +175,7 @@ huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t*
   s_code[threadIdx.x] = code[threadIdx.x];
   s_len[threadIdx.x] = len[threadIdx.x];
   const int tile = take_ticket(ws);   // contains a __syncthreads
-  const long long i0 = (long long)tile * kSeg + (long long)threadIdx.x * kSegItems;
+  const long long i0 = (long long)tile * kTileSyms + (long long)threadIdx.x * kSegItems;
   uint8_t s[kSegItems];
   if (i0 + kSegItems <= n && (reinterpret_cast<uintptr_t>(sym) & 15) == 0) {
     const uint4 v = *reinterpret_cast<const uint4*>(sym + i0);
@@ -190,10 +192,9 @@ huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t*
   int total;
   const int texcl = block_exclusive<int>(bits, total);
   const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
-  if (threadIdx.x == 0) {
-    seg_bits[tile] = base;
-    if ((long long)(tile + 1) * kSeg >= n) *total_bits = base + (unsigned long long)total;
-  }
+  if ((threadIdx.x & (kSeg / kSegItems - 1)) == 0 && i0 < n)
+    seg_bits[(long long)tile * kSegPerTile + threadIdx.x / (kSeg / kSegItems)] = base + (unsigned long long)texcl;
+  if (threadIdx.x == 0 && (long long)(tile + 1) * kTileSyms >= n) *total_bits = base + (unsigned long long)total;
   // emit: big-endian bit order within the byte stream == big-endian within 32-bit words that are
   // byte-swapped on store.  Accumulate into a 64-bit window and flush 32 bits at a time.
   unsigned long long pos = base + (unsigned long long)texcl;
@@ -225,19 +226,11 @@ huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t*
 }
 
 // ---------------------------------------------------------------- Huffman unpack
-__device__ __forceinline__ unsigned long long load_be64(const uint8_t* p, unsigned long long byte,
-                                                        unsigned long long nbytes) {
-  unsigned long long v = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const unsigned long long b = byte + k;
-    v = (v << 8) | (unsigned long long)(b < nbytes ? p[b] : 0);
-  }
-  return v;
-}
-
+// One thread per segment: a 64-bit bit window refilled with aligned 32-bit words (the stream is
+// big-endian within bytes), 12-bit direct table in shared memory, tree walk for longer codes,
+// symbols stored four at a time.
 __global__ void __launch_bounds__(128)
-huff_decode_kernel(const uint8_t* __restrict__ bits, unsigned long long nbytes, long long n, int seg,
+huff_decode_kernel(const uint32_t* __restrict__ words, long long n, int seg,
                    const unsigned long long* __restrict__ seg_bits, const uint16_t* __restrict__ lut,
                    int lut_bits, const int32_t* __restrict__ tree, uint8_t* __restrict__ sym) {
   extern __shared__ uint16_t s_lut[];
@@ -246,20 +239,25 @@ huff_decode_kernel(const uint8_t* __restrict__ bits, unsigned long long nbytes, 
   const long long nseg = (n + seg - 1) / seg;
   const long long sg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sg >= nseg) return;
-  unsigned long long pos = seg_bits[sg];
+  const unsigned long long pos = seg_bits[sg];
+  const uint32_t* wp = words + (pos >> 5);
+  unsigned long long buf = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
+  wp += 2;
+  int used = (int)(pos & 31);
   const long long i0 = sg * seg;
   const long long i1 = (i0 + seg < n) ? i0 + seg : n;
+  const bool one_symbol = (tree[0] < 0 && tree[1] < 0 && tree[0] == tree[1]);
+  uint32_t pack = 0;
   for (long long i = i0; i < i1; ++i) {
-    const unsigned long long win = load_be64(bits, pos >> 3, nbytes) << (pos & 7);   // >= 57 valid bits
+    const unsigned long long win = buf << used;          // >= 33 valid bits at the top
     const uint16_t e = s_lut[win >> (64 - lut_bits)];
     int l = e >> 8;
     int s = e & 0xff;
     if (l == 0) {   // code longer than lut_bits (or the empty code of a one-symbol alphabet)
-      int node = 0;
-      l = 0;
-      if (tree[0] < 0 && tree[1] < 0 && tree[0] == tree[1]) {
-        s = ~tree[0];   // degenerate one-symbol table: zero-length code
+      if (one_symbol) {
+        s = ~tree[0];
       } else {
+        int node = 0;
         while (true) {
           const int bit = (int)((win >> (63 - l)) & 1);
           ++l;
@@ -269,9 +267,20 @@ huff_decode_kernel(const uint8_t* __restrict__ bits, unsigned long long nbytes, 
         }
       }
     }
-    sym[i] = (uint8_t)s;
-    pos += l;
+    used += l;
+    if (used >= 32) {
+      buf = (buf << 32) | __byte_perm(*wp++, 0, 0x0123);
+      used -= 32;
+    }
+    const int k = (int)(i - i0) & 3;
+    pack |= (uint32_t)s << (8 * k);
+    if (k == 3) {
+      *reinterpret_cast<uint32_t*>(sym + i - 3) = pack;
+      pack = 0;
+    }
   }
+  const int rem = (int)(i1 - i0) & 3;
+  for (int k = 0; k < rem; ++k) sym[i1 - rem + k] = (uint8_t)(pack >> (8 * k));
 }
 
 inline unsigned grid_for(long long n, int per_block) {
@@ -357,7 +366,7 @@ extern "C" size_t lc_huff_max_bytes(int64_t n) { return (size_t)(n < 0 ? 0 : n) 
 
 extern "C" size_t lc_huff_workspace_bytes(int64_t n, int seg) {
   (void)seg;
-  const long long nt = ((n < 1 ? 1 : n) + kSeg - 1) / kSeg;
+  const long long nt = ((n < 1 ? 1 : n) + kTileSyms - 1) / kTileSyms;
   return ws_bytes(nt);
 }
 
@@ -365,13 +374,13 @@ extern "C" int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d
                               int seg, uint8_t* d_out, unsigned long long* d_seg_bits,
                               unsigned long long* d_total_bits, void* d_ws, void* stream) {
   LC_REQUIRE(d_total_bits && d_ws, "null argument");
-  LC_REQUIRE(seg == kSeg, "segment length must be 4096 symbols");
+  LC_REQUIRE(seg == kSeg, "segment length must be 1024 symbols");
   cudaStream_t s = as_stream(stream);
   LC_CUDA(cudaMemsetAsync(d_total_bits, 0, sizeof(unsigned long long), s));
   if (n <= 0) return LC_OK;
   LC_REQUIRE(d_sym && d_code && d_len && d_out && d_seg_bits, "null argument");
   LC_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 3) == 0, "output must be 4-byte aligned");
-  const long long nt = (n + kSeg - 1) / kSeg;
+  const long long nt = (n + kTileSyms - 1) / kTileSyms;
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
   huff_encode_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, d_code, d_len,
                                                        reinterpret_cast<uint32_t*>(d_out), d_seg_bits,
@@ -390,9 +399,11 @@ extern "C" int lc_huff_decode(const uint8_t* d_bits, int64_t n, int seg, const u
   const long long nseg = (n + seg - 1) / seg;
   // the caller guarantees the bit buffer is readable up to the last byte holding a code bit and
   // zero padded to 8 more bytes; pass the conservative size bound
+  LC_REQUIRE((reinterpret_cast<uintptr_t>(d_bits) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_sym) & 3) == 0 &&
+                 seg % 4 == 0, "bit stream and symbol buffers must be 4-byte aligned");
   huff_decode_kernel<<<(unsigned)((nseg + 127) / 128), 128, (size_t)(1 << lut_bits) * 2,
-                       as_stream(stream)>>>(d_bits, ~0ull, n, seg, d_seg_bits, d_lut, lut_bits, d_tree,
-                                            d_sym);
+                       as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(d_bits), n, seg, d_seg_bits, d_lut,
+                                            lut_bits, d_tree, d_sym);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

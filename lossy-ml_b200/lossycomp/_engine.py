@@ -22,10 +22,11 @@ from .models import CHUNK, Model, load_model
 
 LATENT_MAGIC = b"LCL1"
 HUFF_MAGIC = b"LCH1"
-SEG = 4096                      # symbols per independently decodable Huffman segment
+SEG = 1024                      # symbols per independently decodable Huffman segment
 ESC = 255                       # escape symbol of the code stream
-# 109 chunks x 19 tiles = 7.00 waves of the 296 resident CTAs of the dominant 3x3x3 kernel
-DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "109"))
+# chunks per convolution launch: large batches amortise kernel prologues and tails (900 chunks x 19 tiles =
+# 57.8 waves of the 296 resident CTAs); the activation workspace is 19.4 MB per chunk
+DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "1024"))
 
 
 def _ptr(t):
@@ -255,8 +256,8 @@ class Engine:
         assert total_bits is None or got_bits == total_bits
         nbytes = (got_bits + 7) // 8
         payload = out[:nbytes].cpu().numpy().tobytes()
-        lens = np.diff(np.concatenate((offs[:nseg], [got_bits]))).astype(np.uint32) if nseg else \
-            np.zeros(0, np.uint32)
+        lens = np.diff(np.concatenate((offs[:nseg], [got_bits]))).astype(np.uint16) if nseg else \
+            np.zeros(0, np.uint16)
         return payload, lens, got_bits
 
     def huff_unpack(self, payload: bytes, n: int, seg_lens: np.ndarray, table: HF.Table):
@@ -264,7 +265,7 @@ class Engine:
         sym = t.empty(n, dtype=t.uint8, device=self.dev)
         if n == 0:
             return sym
-        bits = t.zeros(len(payload) + 16, dtype=t.uint8, device=self.dev)
+        bits = t.zeros(((len(payload) + 3) // 4) * 4 + 16, dtype=t.uint8, device=self.dev)
         if payload:
             bits[:len(payload)] = t.frombuffer(bytearray(payload), dtype=t.uint8).to(self.dev)
         offs = np.concatenate(([0], np.cumsum(seg_lens.astype(np.int64))[:-1])).astype(np.int64)
@@ -284,7 +285,7 @@ class Engine:
             hist = self.hist(sym) if n else np.zeros(256, np.int64)
         table = HF.build_table(hist)
         bits = table.encoded_bits(hist)
-        payload, lens, total_bits = self.huff_pack(sym, table, bits) if n else (b"", np.zeros(0, np.uint32), 0)
+        payload, lens, total_bits = self.huff_pack(sym, table, bits) if n else (b"", np.zeros(0, np.uint16), 0)
         meta = dict(extra, n=int(n), seg=SEG, bits=int(total_bits), ref_tree=bool(table.reference_tree))
         mj = json.dumps(meta).encode()
         tb = table.to_bytes()
@@ -297,7 +298,7 @@ class Engine:
         p = 16
         meta = json.loads(blob[p:p + lm]); p += lm
         table, _ = HF.Table.from_bytes(blob[p:p + ltb]); p += ltb
-        lens = np.frombuffer(blob, dtype=np.uint32, count=nl, offset=p); p += 4 * nl
+        lens = np.frombuffer(blob, dtype=np.uint16, count=nl, offset=p); p += 2 * nl
         payload = blob[p:]
         sym = self.huff_unpack(payload, meta["n"], lens, table)
         return sym, meta
@@ -413,7 +414,7 @@ class Engine:
         nseg, bits = job["nseg"], job["bits"]
         offs = np.frombuffer(job["h_seg"].numpy(), dtype=np.int64, count=nseg + 1)
         assert int(offs[nseg]) == bits
-        lens = np.diff(offs[:nseg + 1]).astype(np.uint32) if nseg else np.zeros(0, np.uint32)
+        lens = np.diff(offs[:nseg + 1]).astype(np.uint16) if nseg else np.zeros(0, np.uint16)   # <= 1024*32 bits
         meta = dict(extra, n=int(job["n"]), seg=SEG, bits=int(bits), ref_tree=bool(job["table"].reference_tree))
         mj = json.dumps(meta).encode()
         tb = job["table"].to_bytes()

@@ -117,25 +117,32 @@ def all_reduce_stats(local, group=None, device=None):
     return (a[0], a[1], float(m.item()), a[2])
 
 
-def gather_bytes(payload: bytes, dst: int = 0, group=None, device=None) -> Optional[List[bytes]]:
+def gather_bytes(payload: bytes, dst: int = 0, group=None, device=None, to_host: bool = True):
     """Variable-length byte strings of all ranks -> list on rank `dst` (None elsewhere).
-    Lengths travel in an all-gather, payloads in one padded gather."""
+    Lengths travel in an all-gather, payloads in one padded gather (NCCL over NVLink on GPUs).
+    With to_host=False rank `dst` keeps the parts as uint8 tensors on its device (no PCIe trip)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = torch.tensor([len(payload)], dtype=torch.int64, device=device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, n, group=group) if hasattr(dist, "all_gather_into_tensor") and \
+        dist.get_backend(group) == "nccl" else dist.all_gather(list(sizes.split(1)), n, group=group)
+    sizes = [int(v) for v in sizes.cpu().tolist()]
     cap = max(max(sizes), 1)
-    buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+    buf = torch.empty(cap, dtype=torch.uint8, device=device)
     if payload:
-        buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(buf.device)
+        src = torch.frombuffer(memoryview(payload), dtype=torch.uint8) if not isinstance(payload, bytearray) \
+            else torch.frombuffer(payload, dtype=torch.uint8)
+        buf[:len(payload)].copy_(src, non_blocking=True)
     if rank == dst:
-        recv = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
-        dist.gather(buf, recv, dst=dst, group=group)
-        return [r[:sizes[i]].cpu().numpy().tobytes() for i, r in enumerate(recv)]
+        recv = torch.empty((world, cap), dtype=torch.uint8, device=device)
+        dist.gather(buf, list(recv.unbind(0)), dst=dst, group=group)
+        if not to_host:
+            return [recv[i, :sizes[i]] for i in range(world)]
+        host = recv.cpu()
+        return [host[i, :sizes[i]].numpy().tobytes() for i in range(world)]
     dist.gather(buf, None, dst=dst, group=group)
     return None
 

@@ -12,13 +12,15 @@ T, H, W = 24, 720, 1440
 x = torch.empty((T, H, W, 2), dtype=torch.float32, device="cuda")
 N.check(eng.lib.lc_synth_field(x.data_ptr(), T, H, W, 0, 0, 1234, None), "synth")
 mean, std, _ = eng.stats(x)
-for i in range(2): lat = eng.encode(x, mean, std)
+for i in range(2):
+    lat = eng.encode(x, mean, std); rec = eng.decode(lat, T, H, W)
 eng.profile(True); eng.profile_read()
-for i in range(3): lat = eng.encode(x, mean, std)
+for i in range(3):
+    lat = eng.encode(x, mean, std); rec = eng.decode(lat, T, H, W)
 ms, cnt = eng.profile_read()
-print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms[:7]))
+print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms))
 ''' % (ROOT, ROOT)
-for dbg, label in [(0, "full"), (6, "no epilogue loads/stores"), (1, "no MMA"), (15, "only barriers"),
+for dbg, label in [(0, "full"), (16, "single issuer"), (1, "no MMA"), (8, "no copies"), (9, "no MMA no copies"),
                    ]:
     env = dict(os.environ, LOSSYCOMP_TC_DEBUG=str(dbg))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
