@@ -195,7 +195,7 @@ def run_ours(args):
         slots, info = compress_device(eng, x, ABS_ERR, mode="strict", codec=args.codec)
         if world > 1:
             # rank 0 keeps the other ranks' blobs in its HBM; only e2e pays the PCIe trips
-            info["gathered"] = LD.gather_bytes(pickle.dumps(slots), 0, None, eng.dev, to_host=False)
+            info["gathered"] = LD.gather_bytes(LD.frame_slots(slots), 0, None, eng.dev, to_host=False)
         return slots, info
 
     for _ in range(args.warmup):

@@ -102,6 +102,30 @@ def assemble_blob(rank_slots: Sequence[list], latent_join) -> list:
             pack_multipart([s[6] for s in rank_slots]), pack_multipart([s[7] for s in rank_slots]), first[8]]
 
 
+def frame_slots(slots) -> list:
+    """Slot list -> [small pickled header, payload 0, payload 6, payload 7]: the three large byte strings
+    travel unpickled, so framing costs no extra copy of the payloads."""
+    big = (0, 6, 7)
+    head = list(slots)
+    for i in big:
+        head[i] = len(slots[i])
+    h = pickle.dumps(head)
+    return [struct.pack("<I", len(h)), h] + [slots[i] for i in big]
+
+
+def unframe_slots(buf) -> list:
+    """Inverse of frame_slots on a bytes-like object."""
+    mv = memoryview(buf)
+    (hl,) = struct.unpack("<I", mv[:4])
+    head = pickle.loads(mv[4:4 + hl])
+    p = 4 + hl
+    for i in (0, 6, 7):
+        n = head[i]
+        head[i] = bytes(mv[p:p + n])
+        p += n
+    return head
+
+
 # ------------------------------------------------------------------------------------------
 # collectives (NCCL on GPUs, gloo on CPU tensors)
 # ------------------------------------------------------------------------------------------
@@ -117,32 +141,55 @@ def all_reduce_stats(local, group=None, device=None):
     return (a[0], a[1], float(m.item()), a[2])
 
 
-def gather_bytes(payload: bytes, dst: int = 0, group=None, device=None, to_host: bool = True):
-    """Variable-length byte strings of all ranks -> list on rank `dst` (None elsewhere).
-    Lengths travel in an all-gather, payloads in one padded gather (NCCL over NVLink on GPUs).
-    With to_host=False rank `dst` keeps the parts as uint8 tensors on its device (no PCIe trip)."""
+_pinned = {}
+
+
+def _stage(parts, device):
+    """Concatenate byte strings straight into a (reused) pinned host tensor and start the copy to `device`."""
+    import torch
+    total = sum(len(p) for p in parts)
+    use_pin = device is not None and torch.device(device).type == "cuda"
+    key = str(device)
+    host = _pinned.get(key)
+    if host is None or host.numel() < total:
+        host = torch.empty(max(int(total * 1.25), 1 << 16), dtype=torch.uint8, pin_memory=use_pin)
+        _pinned[key] = host
+    hv = host.numpy()
+    off = 0
+    for p in parts:
+        n = len(p)
+        if n:
+            hv[off:off + n] = np.frombuffer(p, dtype=np.uint8)
+        off += n
+    return host, total
+
+
+def gather_bytes(payload, dst: int = 0, group=None, device=None, to_host: bool = True):
+    """Variable-length byte strings of all ranks -> list on rank `dst` (None elsewhere).  `payload` is a
+    bytes object or a list of bytes objects (sent as their concatenation).  Lengths travel in an
+    all-gather, payloads in one padded gather (NCCL over NVLink on GPUs).  With to_host=False rank `dst`
+    keeps the parts as uint8 tensors on its device (no PCIe trip)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    n = torch.tensor([len(payload)], dtype=torch.int64, device=device)
-    sizes = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(sizes, n, group=group) if hasattr(dist, "all_gather_into_tensor") and \
-        dist.get_backend(group) == "nccl" else dist.all_gather(list(sizes.split(1)), n, group=group)
-    sizes = [int(v) for v in sizes.cpu().tolist()]
+    parts = payload if isinstance(payload, (list, tuple)) else [payload]
+    host, total = _stage(parts, device)
+    n = torch.tensor([total], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(v) for v in torch.cat(sizes).cpu().tolist()]
     cap = max(max(sizes), 1)
     buf = torch.empty(cap, dtype=torch.uint8, device=device)
-    if payload:
-        src = torch.frombuffer(memoryview(payload), dtype=torch.uint8) if not isinstance(payload, bytearray) \
-            else torch.frombuffer(payload, dtype=torch.uint8)
-        buf[:len(payload)].copy_(src, non_blocking=True)
+    if total:
+        buf[:total].copy_(host[:total], non_blocking=True)
     if rank == dst:
         recv = torch.empty((world, cap), dtype=torch.uint8, device=device)
         dist.gather(buf, list(recv.unbind(0)), dst=dst, group=group)
         if not to_host:
             return [recv[i, :sizes[i]] for i in range(world)]
-        host = recv.cpu()
-        return [host[i, :sizes[i]].numpy().tobytes() for i in range(world)]
+        hostr = recv.cpu()
+        return [hostr[i, :sizes[i]].numpy().tobytes() for i in range(world)]
     dist.gather(buf, None, dst=dst, group=group)
     return None
 
@@ -163,13 +210,13 @@ def compress_sharded(eng, x_local, err_threshold, *, mode="strict", codec="huff"
     if T_local:
         slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec,
                                       inject={"mean": mean, "std": std, "max_abs": max_abs})
-        mine = pickle.dumps(slots)
+        mine = frame_slots(slots)
     else:
         slots, info, mine = None, {"n_out": 0}, b""
     parts = gather_bytes(mine, dst, group, dev)
     if dist.get_rank(group) != dst:
         return None, info
-    rank_slots = [pickle.loads(p) for p in parts if p]
+    rank_slots = [unframe_slots(p) for p in parts if p]
     return assemble_blob(rank_slots, eng.join_latents), info
 
 

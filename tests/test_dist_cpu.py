@@ -56,6 +56,7 @@ def test_multipart_roundtrip_and_blob_assembly():
     s = D.assemble_blob([a, b], lambda xs: b"".join(xs))
     assert s[0] == b"AB" and s[1] == (30, 1, 3, 3) and s[2] == (48, 96, 96, 2) and s[3] == (150,)
     assert D.unpack_multipart(s[6]) == [b"LCH1x", b"LCH1z"] and s[8] == 0.2
+    assert D.unframe_slots(b"".join(D.frame_slots(a))) == a
     b[8] = 0.3
     with pytest.raises(AssertionError):
         D.assemble_blob([a, b], lambda xs: b"".join(xs))
@@ -78,7 +79,7 @@ def _worker(rank, world, port, q):
         lo, hi = (0, 1500) if rank == 0 else (1500, 4000)
         a = x[lo:hi]
         tot = D.all_reduce_stats((a.sum(), (a * a).sum(), float(np.abs(a).max()), float(a.size)))
-        payload = bytes([rank]) * (10 + 1000 * rank)
+        payload = [bytes([rank]) * 10, b"", bytes([rank]) * (1000 * rank)]     # a list is sent concatenated
         got = D.gather_bytes(payload, dst=0)
         empty = D.gather_bytes(b"" if rank == 1 else b"xy", dst=0)
         q.put((rank, tot, got, empty))
