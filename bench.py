@@ -34,6 +34,8 @@ UNIT = "GB/s"
 ABS_ERR = 0.1
 FIELD = (24, 720, 1440)          # configs[1] of BASELINE.json
 CPU_SAMPLE = (24, 336, 720)      # bounded sample of the same field for the CPU legs (~10-20 s)
+# DRAM bytes per chunk per launch of the dominant kernel, from the ncu --set full capture under profiles/
+NCU_DRAM_BYTES_PER_CHUNK = {"sweep_tc_kernel<K3>": 4.13e6}   # mean of its 4 layers: 3.05 MB (plain), 5.2 MB (with skip)
 
 
 def parse():
@@ -274,32 +276,46 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel(s): the convolution stack
+    # ---- roofline of the dominant kernel: the tcgen05 plane-sweep kernel of the 3x3x3 layers
     pk, pk_src = peaks()
     macs = eng.model.arch.macs_per_chunk()
     layers = eng.model.layers
+    backends = eng.layer_backends()
     shape = (16, 48, 48)
-    per_layer = []
+    per_layer, groups = [], {}
     for i, L in enumerate(layers):
-        fl = 2.0 * L.macs(shape) * n_chunks * args.steps       # algorithmic (direct conv) flops issued
+        fl = 2.0 * L.macs(shape) * n_chunks * args.steps       # algorithmic (direct conv) flops
         shape = L.out_shape(shape)
-        per_layer.append({"layer": f"{L.part}/{L.name}", "ms": layer_ms[i], "launches": layer_cnt[i],
+        kname = eng.BACKENDS[backends[i]]
+        per_layer.append({"layer": f"{L.part}/{L.name}", "kernel": kname, "ms": layer_ms[i], "launches": layer_cnt[i],
                           "tflops": (fl / (layer_ms[i] * 1e-3) / 1e12) if layer_ms[i] > 0 else None})
-    dom = max(range(len(layers)), key=lambda i: layer_ms[i])
+        g = groups.setdefault(kname, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        g["ms"] += layer_ms[i]; g["flops"] += fl; g["launches"] += layer_cnt[i]
     conv_ms = sum(layer_ms)
     conv_flops = 2.0 * (macs["Encoder"] + macs["Decoder"]) * n_chunks * args.steps
     if args.precision == "fp32":
         peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA peak (148 SM x 128 lanes x 1.965 GHz), CUDA-core path"
     else:
-        peak, peak_note = pk["bf16_tflops_sustained"], f"bf16 dense sustained, {pk_src}"
-    dom_l = per_layer[dom]
+        peak, peak_note = pk["bf16_tflops_sustained"], f"dense 16-bit tensor, sustained, {pk_src}"
+    dom_name = max(groups, key=lambda k: groups[k]["ms"])
+    dom = groups[dom_name]
+    achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else None
+    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/), per chunk
+    traffic_per_chunk = NCU_DRAM_BYTES_PER_CHUNK.get(dom_name)
+    chunks_per_launch = n_chunks * args.steps * sum(1 for b in backends if eng.BACKENDS[b] == dom_name) / max(dom["launches"], 1)
     roofline = {
-        "bound": "tensor", "kernel": dom_l["layer"], "achieved": dom_l["tflops"], "peak": peak, "unit": "TFLOP/s",
-        "frac": (dom_l["tflops"] / peak) if dom_l["tflops"] else None, "traffic": None,
-        "peak_source": peak_note,
-        "launch_ms": dom_l["ms"] / max(dom_l["launches"], 1), "launches": dom_l["launches"],
+        "bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": (achieved / peak) if achieved else None,
+        "traffic": (traffic_per_chunk * chunks_per_launch) if traffic_per_chunk else None,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                        "(profiles/r01_ncu_sweep_final.txt), scaled to the chunks one launch processes",
+        "peak_source": peak_note, "launch_ms": dom["ms"] / max(dom["launches"], 1), "launches": dom["launches"],
+        "algorithmic_flops_per_launch": dom["flops"] / max(dom["launches"], 1),
+        "share_of_step": dom["ms"] / ms,
         "conv_stack": {"achieved": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None, "ms_per_step":
                        conv_ms / args.steps, "share_of_step": conv_ms / ms, "flops_per_chunk": 2.0 * (macs["Encoder"] + macs["Decoder"])},
+        "per_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else None,
+                           "launches": v["launches"]} for k, v in groups.items()},
         "per_layer": per_layer,
     }
     line = {

@@ -67,7 +67,10 @@ int lc_version(void);
 int lc_create(const lc_layer_t* layers, int n_enc, int n_dec, int in_channels, int precision,
               int device, lc_handle_t* out);
 int lc_destroy(lc_handle_t h);
-int lc_latent_floats(lc_handle_t h); /* floats per chunk in the latent, e.g. 1*3*3*23 */
+int lc_latent_floats(lc_handle_t h);
+/* Which kernel runs layer i: 0 = CUDA-core direct conv, 1 = tcgen05 k3, 2 = k4 first layer, 3 = k4 last
+ * layer (+ merge), 4 = stride-2 down, 5 = transposed up. */
+int lc_layer_backend(lc_handle_t h, int layer); /* floats per chunk in the latent, e.g. 1*3*3*23 */
 
 /* Per-layer kernel timing for bench.py's roofline: when enabled, every convolution launch is
  * bracketed by a CUDA event pair on the launching stream; lc_profile_read (sync) returns and

@@ -158,6 +158,11 @@ extern "C" int lc_profile_read(lc_handle_t h, double* h_ms, long long* h_launche
   return LC_OK;
 }
 
+extern "C" int lc_layer_backend(lc_handle_t h, int layer) {
+  if (!h || layer < 0 || layer >= h->n_enc + h->n_dec) return LC_EINVAL;
+  return tc_backend_of(h, layer);
+}
+
 extern "C" int lc_latent_floats(lc_handle_t h) { return h ? h->latent_floats : LC_EINVAL; }
 
 // ---------------------------------------------------------------------------------------

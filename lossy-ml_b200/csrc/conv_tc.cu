@@ -184,8 +184,9 @@ __device__ __forceinline__ SkipRegs load_skip_smem(const uint8_t* tile, int row,
   return r;
 }
 
-__device__ __forceinline__ void store_voxel(const SweepParams& p, const float (&bias_r)[kHalf], const VoxAddr& va, int t,
-                                            int half, const float (&acc)[kHalf], const SkipRegs* skp) {
+__device__ __forceinline__ void store_voxel(const SweepParams& p, const int h16, const float (&bias_r)[kHalf],
+                                            const VoxAddr& va, int t, int half, const float (&acc)[kHalf],
+                                            const SkipRegs* skp) {
   float y[kHalf];
 #pragma unroll
   for (int c = 0; c < kHalf; ++c) y[c] = acc[c] + bias_r[c];
@@ -193,8 +194,8 @@ __device__ __forceinline__ void store_voxel(const SweepParams& p, const float (&
   // (high half of g1, vector g2)
   if (skp) {
     float f8[8], f4[4];
-    unpack8(skp->a, p.half, f8);
-    unpack4(skp->b, p.half, f4);
+    unpack8(skp->a, h16, f8);
+    unpack4(skp->b, h16, f4);
     if (half == 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) y[k] = __fadd_rn(y[k], f8[k]);
@@ -221,20 +222,20 @@ __device__ __forceinline__ void store_voxel(const SweepParams& p, const float (&
     for (int k = 0; k < 8; ++k) f8[k] = y[k];
 #pragma unroll
     for (int k = 0; k < 4; ++k) f4[k] = y[8 + k];
-    o[oi] = pack8(f8, p.half);
-    if (p.out.G > 1) *reinterpret_cast<uint2*>(o + oi + p.out.S) = pack4(f4, p.half);
+    o[oi] = pack8(f8, h16);
+    if (p.out.G > 1) *reinterpret_cast<uint2*>(o + oi + p.out.S) = pack4(f4, h16);
   } else {
     float f8[8], f4[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) f4[k] = y[k];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f8[k] = y[4 + k];
-    if (p.out.G > 1) *(reinterpret_cast<uint2*>(o + oi + p.out.S) + 1) = pack4(f4, p.half);
-    if (p.out.G > 2) o[oi + 2LL * p.out.S] = pack8(f8, p.half);
+    if (p.out.G > 1) *(reinterpret_cast<uint2*>(o + oi + p.out.S) + 1) = pack4(f4, h16);
+    if (p.out.G > 2) o[oi + 2LL * p.out.S] = pack8(f8, h16);
   }
 }
 
-template <int MODE>
+template <int MODE, int H16>
 __global__ void __launch_bounds__(kTcThreads, (MODE == MODE_K3 || MODE == MODE_K4 || MODE == MODE_UP) ? 2 : 1)
 sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -304,7 +305,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       const int me = (warp == 10) ? 1 : 0;
       const int n_issuers = (p.debug & 16) ? 1 : 2;
       umma::mbar_wait(&wbar, 0);
-      const uint32_t idesc = umma::make_idesc(128, p.N, p.half ? 0 : 1);
+      const uint32_t idesc = umma::make_idesc(128, p.N, H16 ? 0 : 1);
       const uint64_t sA_add = (uint64_t)(umma::smem_u32(sA) >> 4), sB_add = (uint64_t)(umma::smem_u32(sB) >> 4);
       int stage = 0, phase = 0, buf = 0, bphase = 0, step = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -404,7 +405,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
             if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
             if (++estage == p.stages) { estage = 0; efphase ^= 1; }
           }
-          if (t >= 1 && ri.valid && !(p.debug & 4)) store_voxel(p, bias_r, va, t - 1, half, aP, has_skip ? &sk : nullptr);
+          if (t >= 1 && ri.valid && !(p.debug & 4)) store_voxel(p, H16, bias_r, va, t - 1, half, aP, has_skip ? &sk : nullptr);
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { aP[c] = aC[c]; aC[c] = aN[c]; }
         }
@@ -418,7 +419,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
           if (++estage == p.stages) { estage = 0; efphase ^= 1; }
         }
-        if (ri.valid) store_voxel(p, bias_r, va, p.in_T - 1, half, aP, has_skip ? &sk : nullptr);
+        if (ri.valid) store_voxel(p, H16, bias_r, va, p.in_T - 1, half, aP, has_skip ? &sk : nullptr);
       } else if (MODE == MODE_K4) {
         // k=4, pad 1/2: block dt -> output plane t_in - dt + 1  (planes t+1, t, t-1, t-2)
         float a1[kHalf], a2[kHalf], a3[kHalf], a0[kHalf];
@@ -431,13 +432,13 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           release_d();
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { a0[c] = db[0][c]; a1[c] += db[1][c]; a2[c] += db[2][c]; a3[c] += db[3][c]; }
-          if (t >= 2 && ri.valid) store_voxel(p, bias_r, va, t - 2, half, a3, nullptr);
+          if (t >= 2 && ri.valid) store_voxel(p, H16, bias_r, va, t - 2, half, a3, nullptr);
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { a3[c] = a2[c]; a2[c] = a1[c]; a1[c] = a0[c]; }
         }
         if (ri.valid) {
-          store_voxel(p, bias_r, va, p.in_T - 2, half, a3, nullptr);
-          store_voxel(p, bias_r, va, p.in_T - 1, half, a2, nullptr);
+          store_voxel(p, H16, bias_r, va, p.in_T - 2, half, a3, nullptr);
+          store_voxel(p, H16, bias_r, va, p.in_T - 1, half, a2, nullptr);
         }
       } else if constexpr (MODE == MODE_K4_OUT1) {
         // cout = 1, taps dt and dw folded into N: column dt*4+dw of row r is the contribution of input
@@ -503,12 +504,12 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 #pragma unroll
             for (int c = 0; c < kHalf; ++c) { aN[c] += db[0][c]; aO[c] += db[1][c]; }
             const int m = t >> 1;
-            if (m >= 1 && ri.valid) store_voxel(p, bias_r, va, m - 1, half, aO, nullptr);
+            if (m >= 1 && ri.valid) store_voxel(p, H16, bias_r, va, m - 1, half, aO, nullptr);
 #pragma unroll
             for (int c = 0; c < kHalf; ++c) aO[c] = aN[c];
           }
         }
-        if (ri.valid) store_voxel(p, bias_r, va, p.out_T - 1, half, aO, nullptr);
+        if (ri.valid) store_voxel(p, H16, bias_r, va, p.out_T - 1, half, aO, nullptr);
       } else if (MODE == MODE_UP) {
         // output plane 2*t_in + kt - 1; block kt.  Planes 2t-1 and 2t complete at step t.
         float cX[kHalf], cY[kHalf];
@@ -521,12 +522,12 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           release_d();
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { cX[c] += db[0][c]; cY[c] += db[1][c]; }
-          if (t >= 1 && ri.valid) store_voxel(p, bias_r, va, 2 * t - 1, half, cX, nullptr);
-          if (ri.valid) store_voxel(p, bias_r, va, 2 * t, half, cY, nullptr);
+          if (t >= 1 && ri.valid) store_voxel(p, H16, bias_r, va, 2 * t - 1, half, cX, nullptr);
+          if (ri.valid) store_voxel(p, H16, bias_r, va, 2 * t, half, cY, nullptr);
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { cX[c] = db[2][c]; cY[c] = db[3][c]; }
         }
-        if (ri.valid) store_voxel(p, bias_r, va, 2 * p.in_T - 1, half, cX, nullptr);
+        if (ri.valid) store_voxel(p, H16, bias_r, va, 2 * p.in_T - 1, half, cX, nullptr);
       }
     }
   }
@@ -739,15 +740,16 @@ __global__ void gather_wfold_kernel(const float* __restrict__ x, ChunkGeom g, in
 }
 
 template <int MODE>
-int launch_mode(const lc_codec* h, const SweepParams& p, int smem) {
+int launch_mode(const lc_codec* h, const SweepParams& p, int grid, int smem, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
   (void)h;
-  (void)p;
-  (void)smem;
+  if (p.half) sweep_tc_kernel<MODE, 1><<<grid, kTcThreads, smem, s>>>(p);
+  else sweep_tc_kernel<MODE, 0><<<grid, kTcThreads, smem, s>>>(p);
   return LC_OK;
 }
 
@@ -759,24 +761,19 @@ int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStr
   int rc = LC_OK;
   switch (lp.backend) {
     case MODE_K3:
-      rc = launch_mode<MODE_K3>(h, p, smem);
-      if (rc == LC_OK) sweep_tc_kernel<MODE_K3><<<grid, kTcThreads, smem, s>>>(p);
+      rc = launch_mode<MODE_K3>(h, p, grid, smem, s);
       break;
     case MODE_K4:
-      rc = launch_mode<MODE_K4>(h, p, smem);
-      if (rc == LC_OK) sweep_tc_kernel<MODE_K4><<<grid, kTcThreads, smem, s>>>(p);
+      rc = launch_mode<MODE_K4>(h, p, grid, smem, s);
       break;
     case MODE_K4_OUT1:
-      rc = launch_mode<MODE_K4_OUT1>(h, p, smem);
-      if (rc == LC_OK) sweep_tc_kernel<MODE_K4_OUT1><<<grid, kTcThreads, smem, s>>>(p);
+      rc = launch_mode<MODE_K4_OUT1>(h, p, grid, smem, s);
       break;
     case MODE_DOWN:
-      rc = launch_mode<MODE_DOWN>(h, p, smem);
-      if (rc == LC_OK) sweep_tc_kernel<MODE_DOWN><<<grid, kTcThreads, smem, s>>>(p);
+      rc = launch_mode<MODE_DOWN>(h, p, grid, smem, s);
       break;
     case MODE_UP:
-      rc = launch_mode<MODE_UP>(h, p, smem);
-      if (rc == LC_OK) sweep_tc_kernel<MODE_UP><<<grid, kTcThreads, smem, s>>>(p);
+      rc = launch_mode<MODE_UP>(h, p, grid, smem, s);
       break;
     default:
       lc_set_error("unknown tensor-core mode %d", lp.backend);

@@ -88,6 +88,12 @@ class Engine:
     def profile(self, on: bool):
         N.check(self.lib.lc_profile_enable(self.h, int(on)), "lc_profile_enable")
 
+    BACKENDS = {0: "conv_direct/conv_small (CUDA core)", 1: "sweep_tc_kernel<K3>", 2: "sweep_tc_kernel<K4>",
+                3: "sweep_tc_kernel<K4_OUT1>", 4: "sweep_tc_kernel<DOWN>", 5: "sweep_tc_kernel<UP>"}
+
+    def layer_backends(self):
+        return [self.lib.lc_layer_backend(self.h, i) for i in range(len(self.model.layers))]
+
     def profile_read(self):
         n = len(self.model.layers)
         ms = (C.c_double * n)()

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lc_create": (_i, [C.POINTER(LcLayer), _i, _i, _i, _i, _i, C.POINTER(_p)]),
     "lc_destroy": (_i, [_p]),
     "lc_latent_floats": (_i, [_p]),
+    "lc_layer_backend": (_i, [_p, _i]),
     "lc_profile_enable": (_i, [_p, _i]),
     "lc_profile_read": (_i, [_p, _p, _p, _i]),
     "lc_chunk_grid": (_i, [_i, _i, _i, C.POINTER(_i * 3)]),
