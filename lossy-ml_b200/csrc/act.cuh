@@ -65,6 +65,23 @@ __device__ __forceinline__ unsigned pack2(float a, float b, int half) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const unsigned*>(&h);
 }
+// Fused (ReLU +) saturate + round-to-nearest-even + pack: one F2FP per pair.  Identical results to
+// relu -> clamp -> convert done separately (.relu maps negatives to +0, .satfinite clamps to +-65504).
+__device__ __forceinline__ unsigned pack2_act(float a, float b, int half, int relu) {
+  unsigned r;
+  if (half) {
+    if (relu) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  } else {
+    if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack8_act(const float f[8], int half, int relu) {
+  return make_uint4(pack2_act(f[0], f[1], half, relu), pack2_act(f[2], f[3], half, relu),
+                    pack2_act(f[4], f[5], half, relu), pack2_act(f[6], f[7], half, relu));
+}
 __device__ __forceinline__ uint4 pack8(const float f[8], int half) {
   return make_uint4(pack2(f[0], f[1], half), pack2(f[2], f[3], half), pack2(f[4], f[5], half),
                     pack2(f[6], f[7], half));

@@ -208,30 +208,23 @@ __device__ __forceinline__ void store_voxel(const SweepParams& p, const int h16,
       for (int k = 0; k < 8; ++k) y[4 + k] = __fadd_rn(y[4 + k], f8[k]);
     }
   }
+  // channels beyond cout are stored as zeros (only the last vector of the second half can contain them)
 #pragma unroll
-  for (int c = 0; c < kHalf; ++c) {
-    float v = y[c];
-    if (p.relu) v = fmaxf(v, 0.f);
-    y[c] = (half * kHalf + c < p.cout) ? v : 0.f;
-  }
+  for (int c = 0; c < kHalf; ++c)
+    if (half * kHalf + c >= p.cout) y[c] = 0.f;
   uint4* o = reinterpret_cast<uint4*>(p.out.base);
   const long long oi = va.o0 + (long long)t * va.o_t;
+  const int relu = p.relu;
   if (half == 0) {
-    float f8[8], f4[4];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f8[k] = y[k];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f4[k] = y[8 + k];
-    o[oi] = pack8(f8, h16);
-    if (p.out.G > 1) *reinterpret_cast<uint2*>(o + oi + p.out.S) = pack4(f4, h16);
+    o[oi] = pack8_act(&y[0], h16, relu);
+    if (p.out.G > 1)
+      *reinterpret_cast<uint2*>(o + oi + p.out.S) =
+          make_uint2(pack2_act(y[8], y[9], h16, relu), pack2_act(y[10], y[11], h16, relu));
   } else {
-    float f8[8], f4[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f4[k] = y[k];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f8[k] = y[4 + k];
-    if (p.out.G > 1) *(reinterpret_cast<uint2*>(o + oi + p.out.S) + 1) = pack4(f4, h16);
-    if (p.out.G > 2) o[oi + 2LL * p.out.S] = pack8(f8, h16);
+    if (p.out.G > 1)
+      *(reinterpret_cast<uint2*>(o + oi + p.out.S) + 1) =
+          make_uint2(pack2_act(y[0], y[1], h16, relu), pack2_act(y[2], y[3], h16, relu));
+    if (p.out.G > 2) o[oi + 2LL * p.out.S] = pack8_act(&y[4], h16, relu);
   }
 }
 
