@@ -76,7 +76,9 @@ def decompress(compressed_data, verbose=False, *, precision=None, model=None, de
     T, H, W = (int(v) for v in slots[2][:3])
     if verbose:
         print("Done.")
-    return out.cpu().numpy().reshape(T, H, W, 1)                                     # decompress.py:104-108
+    host = np.empty((T, H, W, 1), dtype=np.float32)                                  # decompress.py:104-108
+    eng.torch.from_numpy(host.reshape(T, H, W)).copy_(out)
+    return host
 
 
 def _peek_precision(comp_data: bytes):
