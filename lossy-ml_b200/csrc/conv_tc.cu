@@ -732,6 +732,42 @@ __global__ void gather_wfold_kernel(const float* __restrict__ x, ChunkGeom g, in
   }
 }
 
+// fast path of gather_wfold_kernel for the shipped models' input (C = 2, k = 4, one group): one thread per
+// voxel, four 8-byte loads (neighbours overlap in L1), one 16-byte store
+__global__ void __launch_bounds__(256) gather_wfold_c2k4_kernel(const float* __restrict__ x, ChunkGeom g, float mean,
+                                                                float stdv, int chunk_begin, int n_chunks, ActView out,
+                                                                int pad_lo) {
+  const long long total = (long long)n_chunks * CT * CH * CW;
+  uint4* o = reinterpret_cast<uint4*>(out.base);
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int lw = (int)(v % CW);
+    const int r1 = (int)(v / CW);
+    const int lh = r1 % CH;
+    const int r2 = r1 / CH;
+    const int lt = r2 % CT;
+    const int chunk = r2 / CT;
+    int t0, h0, w0;
+    g.origin(chunk_begin + chunk, t0, h0, w0);
+    const float2* line = reinterpret_cast<const float2*>(x) + ((size_t)(t0 + lt) * g.H + (h0 + lh)) * g.W + w0;
+    float f[8];
+#pragma unroll
+    for (int dw = 0; dw < 4; ++dw) {
+      const int w = lw + dw - pad_lo;
+      float2 val = make_float2(0.f, 0.f);
+      if (w >= 0 && w < CW) {
+        val = __ldg(line + w);
+        val.x = __fdiv_rn(__fsub_rn(val.x, mean), stdv);
+      }
+      f[2 * dw] = val.x;
+      f[2 * dw + 1] = val.y;
+    }
+    const long long idx = (long long)chunk * out.chunk_stride + (long long)lt * out.S + out.GL +
+                          (lh + pad_lo) * out.PW + lw;
+    o[idx] = pack8(f, out.half);
+  }
+}
+
 template <int MODE>
 int launch_mode(const lc_codec* h, const SweepParams& p, int grid, int smem, cudaStream_t s) {
   static bool attr_done = false;
@@ -1120,8 +1156,12 @@ int tc_encode(lc_codec* h, const float* d_x, const ChunkGeom& g, int C, float me
     gather_blocks_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count,
                                                         reinterpret_cast<float*>(in.base), in.chunk_stride);
   } else {
-    gather_wfold_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count, in,
-                                                       P->wfold_k, h->layers[0].pad_lo);
+    if (C == 2 && P->wfold_k == 4 && in.G == 1 && (reinterpret_cast<uintptr_t>(d_x) & 7) == 0)
+      gather_wfold_c2k4_kernel<<<h->num_sms * 16, 256, 0, s>>>(d_x, g, mean, stdv, chunk_begin, chunk_count, in,
+                                                                h->layers[0].pad_lo);
+    else
+      gather_wfold_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count, in,
+                                                         P->wfold_k, h->layers[0].pad_lo);
   }
   LC_LAUNCH_CHECK();
   return tc_run(h, 0, h->n_enc, in, d_ws, chunk_count, d_latent, nullptr, nullptr, 0, s);
