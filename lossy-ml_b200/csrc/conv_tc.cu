@@ -939,6 +939,20 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     for (auto& gv : groups)
       for (auto& kg : gv) kg.a_addr = (uint32_t)((kg.plane * p.slab_slots + kg.off_slots + pad) * 16);
   }
+  {   // every bulk copy must stay inside its own plane (guards included)
+    const int first = tin.GL + p.row0 - p.row_shift + p.slab_start;
+    const int last = first + (p.tiles_per_chunk - 1) * p.row_step + p.slab_slots;
+    if (first < 0 || last > tin.S) {
+      lc_set_error("layer %d: tile slabs [%d, %d) leave the input plane of %d vectors", i, first, last, tin.S);
+      return LC_EINVAL;
+    }
+    for (auto& gv : groups)
+      for (auto& kg : gv)
+        if (kg.off_slots < 0 || (int)(kg.a_addr / 16) - kg.plane * p.slab_slots + 128 > p.slab_slots) {
+          lc_set_error("layer %d: operand view leaves its slab", i);
+          return LC_EINVAL;
+        }
+  }
   p.nvar = (int)groups.size();
   const int ngroups = (int)groups[0].size();
   p.nks = (ngroups + 1) / 2;

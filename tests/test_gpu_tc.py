@@ -111,3 +111,30 @@ def test_blob_records_decoder_precision():
     with pytest.raises(N.NativeError):
         decompress(blob, precision="fp32")
     assert decompress(blob).shape == (16, 48, 48, 1)      # picks bf16 from the blob header
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 3e-4), ("fp16", 2e-2)])
+def test_other_architectures_run_and_match_oracle(prec, tol):
+    """results/models/landsea_model (2-ch, F=20, k=4, no ResBlock) with its shipped weights and the model_1
+    architecture (F=20, k=5, res=1; weights not shipped -> seeded random): layers without a tensor-core
+    kernel fall back to the CUDA-core back end inside the same precision mode."""
+    import os
+    from lossycomp._engine import Engine
+    from lossycomp.models import MODEL_1_ARCH, Model
+    from oracle import lossycomp_oracle as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    models = [Model.load(os.path.join(root, "lossy-ml_b200", "weights", "landsea_model.lcw")),
+              Model.random(MODEL_1_ARCH, seed=3)]
+    g = golden_case("ragged_tails")
+    x = g["x"]
+    for m in models:
+        eng = Engine(m, prec, 0)
+        xs, mean, std = O.standardise(x)
+        chunks = O.chunk_data(xs)
+        lat_ref = O.encoder_forward(m, chunks)
+        rec_ref = O.merge_data(O.decoder_forward(m, lat_ref), x.shape)[..., 0]
+        lat = eng.encode(dev(x), mean, std).cpu().numpy()
+        scale = max(1.0, float(np.abs(lat_ref).max()))
+        assert np.abs(lat - lat_ref.reshape(lat.shape)).max() <= tol * scale, m.arch.name
+        rec = eng.decode(dev(lat_ref.reshape(lat.shape)), *x.shape[:3]).cpu().numpy()
+        assert np.abs(rec - rec_ref).max() <= tol * max(1.0, float(np.abs(rec_ref).max())), m.arch.name
