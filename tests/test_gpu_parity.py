@@ -255,3 +255,32 @@ def test_time_sharded_compress_equals_single_call(eng, torch):
         part = decompress_device(eng, slots, rows=(a, b)).cpu().numpy()
         np.testing.assert_array_equal(part, whole[a:b])
     assert np.abs(g["x"][..., 0].astype(np.float64) - whole).max() <= thr
+
+
+@pytest.mark.parametrize("abs_err", [1e-3, 1e-2, 0.3, 1.0])
+def test_abs_error_sweep_strict_bound(abs_err):
+    """BASELINE.json configs[3]: abs_err sweep 1e-3 ... 1; the hard bound holds at every setting."""
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    g = golden_case("two_by_three")
+    x = g["x"]
+    blob = compress(x, abs_err)
+    xhat = decompress(blob)
+    err = np.abs(x[..., 0].astype(np.float64) - xhat[..., 0].astype(np.float64))
+    assert err.max() <= abs_err, f"{(err > abs_err).sum()} violations at {abs_err}"
+    assert len(blob) < x[..., 0].nbytes
+
+
+def test_multi_level_field_container():
+    """(time, level, lat, lon) variable = independent per-level problems with per-level bounds."""
+    from lossycomp.field import compress_field, decompress_field
+    from oracle import lossycomp_oracle as O
+    levels = [O.synthetic_field(16, 96, 96, seed=7, level=l, h0=250, w0=600) for l in range(3)]
+    var = np.stack([f[..., 0] for f in levels], axis=1)          # (T, L, H, W)
+    lsm = levels[0][0, :, :, 1]
+    errs = [0.05, 0.1, 0.5]
+    c = compress_field(var, lsm, errs)
+    back = decompress_field(c)
+    assert back.shape == var.shape
+    for l, e in enumerate(errs):
+        assert np.abs(var[:, l].astype(np.float64) - back[:, l]).max() <= e
