@@ -342,6 +342,16 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_leg(1, 1)
         line["cpu_baseline"] = cb
+        # compression factor on the SAME input as the CPU oracle (north_star: within 1 % of the reference)
+        from oracle import lossycomp_oracle as O
+        xs = O.synthetic_field(*CPU_SAMPLE, seed=1234)
+        nb = xs[..., 0].nbytes
+        line["cf_same_input"] = {
+            "oracle_bz2": cb["compression_factor"],
+            "gpu_parity_mode_bz2_codec": nb / len(compress(xs, ABS_ERR, precision=args.precision, codec="bz2", mode="parity")),
+            "gpu_strict_mode_bz2_codec": nb / len(compress(xs, ABS_ERR, precision=args.precision, codec="bz2")),
+            "gpu_strict_mode_huff_codec": nb / len(compress(xs, ABS_ERR, precision=args.precision, codec="huff")),
+            "input": "oracle.synthetic_field%s, abs_err %g" % (str(CPU_SAMPLE), ABS_ERR)}
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))

@@ -49,7 +49,7 @@ class _StageTimer:
 
 
 def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff", verify=None,
-                    inject=None, latent_codec="raw", batch=None, return_parts=False, timing=False):
+                    inject=None, latent_codec=None, batch=None, return_parts=False, timing=False):
     """x: torch float32 CUDA tensor (T,H,W,2).  Returns (slots list, info dict)."""
     assert err_threshold != 0, "The absolute error can't be 0."                      # compress.py:34
     assert x.dim() == 4 and x.shape[3] == eng.model.arch.in_channels, \
@@ -93,6 +93,8 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         assert thr > 0.5 * abs_err, "cannot meet the bound in float32"
     tm and tm.mark("quantize+verify")
     n_out = int(q.numel())
+    if latent_codec is None:      # compat codec: lossless host coder for the latent too (fpzip's role, compress.py:144)
+        latent_codec = "bz2" if codec == "bz2" else "raw"
     comp_data = eng.pack_latent(latent, latent_codec)                                # compress.py:142-144
     tm and tm.mark("latent_pack")
     lshape = (latent.shape[0],) + tuple(eng.model.arch.latent_shape()[1:])
