@@ -81,6 +81,10 @@ int lc_profile_read(lc_handle_t h, double* h_ms, long long* h_launches, int n);
 /* chunk grid of dataLoader.py:449: ceil(T/16), ceil(H/48), ceil(W/48) */
 int lc_chunk_grid(int T, int H, int W, int grid[3]);
 
+/* Host-only view of the same index map: out = {t0, h0, w0 (window origin, dataLoader.py:457-481),
+ * kt, kh, kw (first local index merge_data keeps, dataLoader.py:503-532)} of chunk `idx`. */
+int lc_chunk_window(int T, int H, int W, int idx, int out[6]);
+
 /* dataLoader.py:437-481 chunk_data: (T,H,W,C) -> (N,16,48,48,C), N = product of lc_chunk_grid,
  * chunk index lon-fastest, tail windows re-anchored at axis_len-size (overlap, no padding). */
 int lc_chunk_gather(const float* d_x, int T, int H, int W, int C, float* d_chunks, void* stream);

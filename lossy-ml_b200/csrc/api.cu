@@ -22,6 +22,16 @@ extern "C" int lc_chunk_grid(int T, int H, int W, int grid[3]) {
   return LC_OK;
 }
 
+// Host-only: the chunk index map the kernels use (dataLoader.py:457-481 origins, :503-532 kept part).
+extern "C" int lc_chunk_window(int T, int H, int W, int idx, int out[6]) {
+  LC_REQUIRE(T >= CT && H >= CH && W >= CW, "Chunks size cannot be larger than the data size.");
+  ChunkGeom g = make_geom(T, H, W);
+  LC_REQUIRE(idx >= 0 && idx < g.gt * g.gh * g.gw && out, "chunk index out of range");
+  g.origin(idx, out[0], out[1], out[2]);
+  g.keep_from(idx, out[3], out[4], out[5]);
+  return LC_OK;
+}
+
 static int same_pad_lo(int n, int k, int s) {
   int out = (n + s - 1) / s;
   int total = (out - 1) * s + k - n;

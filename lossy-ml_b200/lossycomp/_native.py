@@ -43,6 +43,7 @@ SIGNATURES = {
     "lc_profile_enable": (_i, [_p, _i]),
     "lc_profile_read": (_i, [_p, _p, _p, _i]),
     "lc_chunk_grid": (_i, [_i, _i, _i, C.POINTER(_i * 3)]),
+    "lc_chunk_window": (_i, [_i, _i, _i, _i, C.POINTER(_i * 6)]),
     "lc_stats_workspace_bytes": (_sz, []),
     "lc_stats": (_i, [_p, _i64, _i, _p, _p, _p]),
     "lc_ae_workspace_bytes": (_sz, [_p, _i]),

@@ -73,3 +73,30 @@ def test_model_spec_matches_survey():
     assert [L.name for L in m.layers][:3] == ["conv3d", "conv3d_1", "conv3d_2"]
     assert sum(L.kernel.size + L.bias.size for L in m.layers) == 332696
     assert abs(float(m.layers[-1].bias[0]) - 0.10914003) < 1e-7            # Decoder/conv3d_9/bias
+
+
+def test_chunk_index_map_matches_oracle_property(lib):
+    """The kernels' chunk window / merge map (host view: lc_chunk_window) against the oracle's restatement of
+    dataLoader.py:437-532 on random shapes: every voxel is kept by exactly one chunk, at the right place."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import lossycomp_oracle as O
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(16, 70), st.integers(48, 150), st.integers(48, 150))
+    def check(T, H, W):
+        g = (ctypes.c_int * 3)()
+        assert lib.lc_chunk_grid(T, H, W, ctypes.byref(g)) == 0
+        assert tuple(g) == O.chunk_grid((T, H, W))
+        cover = np.zeros((T, H, W), dtype=np.int32)
+        out = (ctypes.c_int * 6)()
+        for idx in range(g[0] * g[1] * g[2]):
+            assert lib.lc_chunk_window(T, H, W, idx, ctypes.byref(out)) == 0
+            t0, h0, w0, kt, kh, kw = out
+            assert (t0, h0, w0) == O.chunk_origin(idx, (T, H, W))
+            cover[t0 + kt:t0 + 16, h0 + kh:h0 + 48, w0 + kw:w0 + 48] += 1
+        assert cover.min() == 1 and cover.max() == 1
+
+    check()
+    # and the merge really is the inverse of chunk on the kept parts
+    a = np.arange(33 * 100 * 97, dtype=np.float32).reshape(33, 100, 97, 1)
+    assert np.array_equal(O.merge_data(O.chunk_data(a), a.shape), a)
