@@ -21,6 +21,7 @@ import pickle
 
 import numpy as np
 
+from . import _hostio
 from . import _native as N
 from ._engine import Engine
 
@@ -131,7 +132,7 @@ def compress(array, err_threshold, verbose=False, *, mode="strict", codec="huff"
     assert array.shape[0] >= 16 and array.shape[1] >= 48 and array.shape[2] >= 48, \
         "Chunks size cannot be larger than the data size."                           # dataLoader.py:447
     eng = Engine.get(model, precision, device)
-    x = torch.from_numpy(np.ascontiguousarray(array)).to(eng.dev, non_blocking=False)
+    x = _hostio.h2d(eng, array)
     slots, info = compress_device(eng, x, err_threshold, mode=mode, codec=codec, verify=verify)
     out = pickle.dumps(slots)                                                        # compress.py:168
     if verbose:

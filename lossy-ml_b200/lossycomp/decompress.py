@@ -13,6 +13,7 @@ import pickle
 
 import numpy as np
 
+from . import _hostio
 from . import _native as N
 from ._engine import HUFF_MAGIC, Engine
 from .dist import MULTI_MAGIC
@@ -62,8 +63,9 @@ def decompress_device(eng: Engine, slots, *, inject=None, batch=None, rows=None)
     return eng.reconstruct(recon, mask, q, mean, std, thr2)                          # decompress.py:86-104
 
 
-def decompress(compressed_data, verbose=False, *, precision=None, model=None, device=None):
-    """Decompression method (reference: decompress.py:21).  Returns the reconstructed data."""
+def decompress(compressed_data, verbose=False, *, precision=None, model=None, device=None, out=None):
+    """Decompression method (reference: decompress.py:21).  Returns the reconstructed data.
+    `out` (optional, float32, T*H*W elements) is filled and returned instead of a new array."""
     N.require_cuda()
     slots = pickle.loads(compressed_data)                                            # decompress.py:54
     if precision is None:
@@ -72,13 +74,11 @@ def decompress(compressed_data, verbose=False, *, precision=None, model=None, de
         except Exception:
             precision = None
     eng = Engine.get(model, precision, device)
-    out = decompress_device(eng, slots)
+    dev_out = decompress_device(eng, slots)
     T, H, W = (int(v) for v in slots[2][:3])
     if verbose:
         print("Done.")
-    host = np.empty((T, H, W, 1), dtype=np.float32)                                  # decompress.py:104-108
-    eng.torch.from_numpy(host.reshape(T, H, W)).copy_(out)
-    return host
+    return _hostio.d2h(eng, dev_out, (T, H, W, 1), out=out)                          # decompress.py:104-108
 
 
 def _peek_precision(comp_data: bytes):

@@ -284,3 +284,25 @@ def test_multi_level_field_container():
     assert back.shape == var.shape
     for l, e in enumerate(errs):
         assert np.abs(var[:, l].astype(np.float64) - back[:, l]).max() <= e
+
+
+def test_host_io_paths_agree(torch):
+    """Pinned and pageable inputs give the same blob; decompress(out=...) fills the caller's array and
+    equals the freshly allocated result (the staged multi-threaded copies lose or reorder nothing)."""
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    from oracle import lossycomp_oracle as O
+    x = O.synthetic_field(35, 130, 151, seed=11)                 # odd sizes: slices end unaligned
+    pinned = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+    pinned.copy_(torch.from_numpy(x))
+    b_page = compress(x, 0.05)
+    b_pin = compress(pinned.numpy(), 0.05)
+    assert b_page == b_pin
+    fresh = decompress(b_page)
+    mine = np.full(x.shape[:3] + (1,), np.nan, dtype=np.float32)
+    got = decompress(b_page, out=mine)
+    assert got.base is mine or got is mine
+    assert np.array_equal(fresh, mine)
+    assert np.abs(x[..., 0].astype(np.float64) - fresh[..., 0]).max() <= 0.05
+    with pytest.raises(AssertionError):
+        decompress(b_page, out=np.empty(7, dtype=np.float32))
