@@ -124,6 +124,13 @@ size_t lc_scan_workspace_bytes(int64_t n);
 int lc_quantize(const float* d_x, int C, const float* d_recon, int64_t n_vox, float mean, float std,
                 float thr, float thr2, int8_t* d_mask, int32_t* d_q, unsigned long long* d_count,
                 void* d_ws, void* stream);
+/* lc_quantize plus the strict mode's bound check in the same pass: every element is also decoded exactly
+ * as lc_reconstruct will decode it (decompress.py:86-104, thr2_dec = the double stored in blob slot 8) and
+ * compared with x in fp64.  d_out3[0] = outliers, d_out3[1] = elements with |x - xhat| > abs_err (NaN counts),
+ * d_out3[2] = bits of the largest |x - xhat| (a non-negative double). */
+int lc_quantize_checked(const float* d_x, int C, const float* d_recon, int64_t n_vox, float mean, float std,
+                        float thr, float thr2, double thr2_dec, double abs_err, int8_t* d_mask, int32_t* d_q,
+                        unsigned long long* d_out3, void* d_ws, void* stream);
 
 /* compress.py:147-151,159-163 -- first difference [v0, v1-v0, ...] (int8 wraps like NumPy). */
 int lc_diff_i32(const int32_t* d_in, int64_t n, int32_t* d_out, void* stream);
@@ -169,6 +176,12 @@ int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* strea
  * d_total_bits receives the stream length in bits.  d_out must be zero-initialised and hold
  * lc_huff_max_bytes(n) bytes. */
 size_t lc_huff_max_bytes(int64_t n);
+/* Host only: the prefix code of a 256-bin histogram with the reference's tree construction and tie-breaking
+ * (lossycomp/huffman.py:20-45,71: leaves by (count, symbol), stable re-sort before each merge, first popped
+ * = left = '0').  When that tree is deeper than max_bits the counts are flattened (>> k, floor 1) just enough
+ * and *reference_tree = 0.  code/len/used: 256 entries each. */
+int lc_huff_build_table(const int64_t* hist, int max_bits, uint32_t* code, uint8_t* len, uint8_t* used,
+                        int* reference_tree);
 size_t lc_huff_workspace_bytes(int64_t n, int seg);
 int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d_code, const uint8_t* d_len,
                    int seg, uint8_t* d_out, unsigned long long* d_seg_bits,

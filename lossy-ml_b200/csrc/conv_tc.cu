@@ -367,7 +367,11 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const RowInfo ri = row_info(p, item, row);
       VoxAddr va;
-      if (MODE == MODE_UP) va = vox_addr(p, ri.n, 2 * ri.h + (ri.cls >> 1), 2 * ri.w + (ri.cls & 1));
+      VoxAddr vb;   // experiment (debug bit 64): the neighbouring column
+      if (MODE == MODE_UP) {
+        va = vox_addr(p, ri.n, 2 * ri.h + (ri.cls >> 1), (p.debug & 32) ? ri.w + p.rows_W * (ri.cls & 1) : 2 * ri.w + (ri.cls & 1));
+        vb = vox_addr(p, ri.n, 2 * ri.h + (ri.cls >> 1), 2 * ri.w + 1 - (ri.cls & 1));
+      }
       else if (MODE != MODE_K4_OUT1) va = vox_addr(p, ri.n, ri.h, ri.w);
       if (MODE == MODE_K3) {
         // block dt -> output plane t_in - dt + 1
@@ -511,12 +515,22 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
         for (int t = 0; t < p.in_T; ++t) {
           const uint32_t ta = wait_d();
           float db[4][kHalf];
-          ld_blocks<4>(ta, db);
+          if (!(p.debug & 2)) {
+            ld_blocks<4>(ta, db);
+          } else {
+#pragma unroll
+            for (int c = 0; c < kHalf; ++c) { db[0][c] = 0.f; db[1][c] = 0.f; db[2][c] = 0.f; db[3][c] = 0.f; }
+          }
           release_d();
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { cX[c] += db[0][c]; cY[c] += db[1][c]; }
-          if (t >= 1 && ri.valid) store_voxel(p, H16, bias_r, va, 2 * t - 1, half, cX, nullptr);
-          if (ri.valid) store_voxel(p, H16, bias_r, va, 2 * t, half, cY, nullptr);
+          const bool st = ri.valid && !(p.debug & 4);
+          if (t >= 1 && st) store_voxel(p, H16, bias_r, va, 2 * t - 1, half, cX, nullptr);
+          if (st) store_voxel(p, H16, bias_r, va, 2 * t, half, cY, nullptr);
+          if (p.debug & 64) {
+            if (t >= 1 && st) store_voxel(p, H16, bias_r, vb, 2 * t - 1, half, cX, nullptr);
+            if (st) store_voxel(p, H16, bias_r, vb, 2 * t, half, cY, nullptr);
+          }
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { cX[c] = db[2][c]; cY[c] = db[3][c]; }
         }

@@ -47,11 +47,28 @@ __device__ __forceinline__ int classify(float x0, float r, float mean, float std
   return e > 0.f ? 1 : 2;                                 // compress.py:122-123
 }
 
+// decompress.py:86-104 for one element: the value the decoder adds to the de-standardised reconstruction
+__device__ __forceinline__ float decoded_value(float r, float mean, float stdv, int m, int q, double thr2) {
+  // val = float32(mask); val[val>0] = float64(q)*thr2 -> float32; negated where mask == 2
+  float val = (float)m;
+  if (m > 0) {
+    val = (float)((double)q * thr2);
+    if (m == 2) val = -val;
+  }
+  const float rr = __fadd_rn(__fmul_rn(r, stdv), mean);   // decompress.py:98
+  return __fadd_rn(rr, val);                              // decompress.py:104
+}
+
+// CHECK: also decode every element exactly as reconstruct_kernel will and count |x - xhat| > abs_err in
+// fp64 (out3[1]) with the largest error (out3[2], bits of a non-negative double) -- the strict mode's bound
+// check without a second pass over the field.
+template <bool CHECK>
 __global__ void __launch_bounds__(kThreads)
 quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ recon, long long n,
                 float mean, float stdv, float thr, float thr2, int8_t* __restrict__ mask,
                 int32_t* __restrict__ qout, unsigned long long* __restrict__ count,
-                unsigned long long* ws, bool vec_x, bool vec_r, bool vec_m) {
+                unsigned long long* ws, bool vec_x, bool vec_r, bool vec_m, double thr2_dec,
+                double abs_err) {
   const int tile = take_ticket(ws);
   const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
   float xv[kItems], rv[kItems];
@@ -74,6 +91,34 @@ quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ re
 #pragma unroll
     for (int k = 0; k < kItems; ++k)
       if (i0 + k < n) mask[i0 + k] = (int8_t)m[k];
+  }
+  if (CHECK) {
+    int bad = 0;
+    double worst = 0.0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      if (i0 + k < n) {
+        const float y = decoded_value(rv[k], mean, stdv, m[k], q[k], thr2_dec);
+        const double d = fabs((double)xv[k] - (double)y);
+        if (!(d <= abs_err)) ++bad;            // NaN counts as a violation
+        worst = fmax(worst, d);
+      }
+    }
+    __shared__ double s_worst[kThreads / 32];
+    __shared__ int s_bad[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bad += __shfl_xor_sync(0xffffffffu, bad, o);
+      worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_worst[threadIdx.x >> 5] = worst; s_bad[threadIdx.x >> 5] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < kThreads / 32; ++w) { worst = fmax(worst, s_worst[w]); bad += s_bad[w]; }
+      if (bad) atomicAdd(count + 1, (unsigned long long)bad);
+      if (worst > 0.0) atomicMax(count + 2, (unsigned long long)__double_as_longlong(worst));
+    }
   }
   int total;
   const int texcl = block_exclusive<int>(cnt, total);
@@ -113,14 +158,8 @@ reconstruct_kernel(const float* __restrict__ recon, const int8_t* __restrict__ m
   float y[kItems];
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    // decompress.py:86-95: val = float32(mask); val[val>0] = float64(q)*thr2 -> float32; negate where mask==2
-    float val = (float)m[k];
-    if (m[k] > 0) {
-      val = (float)((double)q[o++] * thr2);
-      if (m[k] == 2) val = -val;
-    }
-    const float rr = __fadd_rn(__fmul_rn(rv[k], stdv), mean);   // decompress.py:98
-    y[k] = __fadd_rn(rr, val);                                  // decompress.py:104
+    const int qk = (m[k] > 0) ? q[o++] : 0;
+    y[k] = decoded_value(rv[k], mean, stdv, m[k], qk, thr2);
   }
   if (i0 + kItems <= n && vec_o) {
     float4* po = reinterpret_cast<float4*>(out + i0);
@@ -181,10 +220,27 @@ extern "C" int lc_quantize(const float* d_x, int C, const float* d_recon, int64_
   cudaStream_t s = as_stream(stream);
   const long long nt = tiles_for(n_vox);
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
-  quantize_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_x, C, d_recon, n_vox, mean, stdv, thr, thr2,
-                                                    d_mask, d_q, d_count,
-                                                    reinterpret_cast<unsigned long long*>(d_ws),
-                                                    aligned16(d_x), aligned16(d_recon), aligned8(d_mask));
+  quantize_kernel<false><<<(unsigned)nt, kThreads, 0, s>>>(
+      d_x, C, d_recon, n_vox, mean, stdv, thr, thr2, d_mask, d_q, d_count,
+      reinterpret_cast<unsigned long long*>(d_ws), aligned16(d_x), aligned16(d_recon), aligned8(d_mask), 0.0, 0.0);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_quantize_checked(const float* d_x, int C, const float* d_recon, int64_t n_vox, float mean,
+                                   float stdv, float thr, float thr2, double thr2_dec, double abs_err,
+                                   int8_t* d_mask, int32_t* d_q, unsigned long long* d_out3, void* d_ws,
+                                   void* stream) {
+  LC_REQUIRE(d_x && d_recon && d_mask && d_q && d_out3 && d_ws, "null argument");
+  LC_REQUIRE(n_vox > 0 && C >= 1, "empty input");
+  cudaStream_t s = as_stream(stream);
+  const long long nt = tiles_for(n_vox);
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  LC_CUDA(cudaMemsetAsync(d_out3, 0, 3 * sizeof(unsigned long long), s));
+  quantize_kernel<true><<<(unsigned)nt, kThreads, 0, s>>>(
+      d_x, C, d_recon, n_vox, mean, stdv, thr, thr2, d_mask, d_q, d_out3,
+      reinterpret_cast<unsigned long long*>(d_ws), aligned16(d_x), aligned16(d_recon), aligned8(d_mask),
+      thr2_dec, abs_err);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

@@ -180,23 +180,32 @@ class Engine:
             self.launches += 1 + len(self.model.decoder)
         return recon
 
-    def quantize(self, x, recon, mean, std, thr):
+    def quantize(self, x, recon, mean, std, thr, check_abs_err=None):
         """compress.py:114-135.  thr is the (possibly guard-banded) absolute bound as a Python float;
-        the float32 forms are made here exactly as NumPy makes them.  Sync (reads the count)."""
+        the float32 forms are made here exactly as NumPy makes them.  Sync (reads the count).
+        With check_abs_err the same pass also decodes every element the way reconstruct() will and
+        returns (mask, q, violations of |x - xhat| <= check_abs_err, max |x - xhat|)."""
         T, H, W, Cc = x.shape
         n = T * H * W
         mask = self.torch.empty(n, dtype=self.torch.int8, device=self.dev)
         q = self.torch.empty(n, dtype=self.torch.int32, device=self.dev)
-        cnt = self.torch.zeros(1, dtype=self.torch.int64, device=self.dev)
         ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n))
         thr32 = np.float32(thr)
         thr2_32 = np.float32(thr * 2.0)
-        N.check(self.lib.lc_quantize(_ptr(x), Cc, _ptr(recon), n, float(mean), float(std), float(thr32),
-                                     float(thr2_32), _ptr(mask), _ptr(q), _ptr(cnt), _ptr(ws), self._stream()),
-                "lc_quantize")
         self.launches += 1
-        n_out = int(cnt.item())
-        return mask, q[:n_out]
+        if check_abs_err is None:
+            cnt = self.torch.zeros(1, dtype=self.torch.int64, device=self.dev)
+            N.check(self.lib.lc_quantize(_ptr(x), Cc, _ptr(recon), n, float(mean), float(std), float(thr32),
+                                         float(thr2_32), _ptr(mask), _ptr(q), _ptr(cnt), _ptr(ws), self._stream()),
+                    "lc_quantize")
+            n_out = int(cnt.item())
+            return mask, q[:n_out]
+        out3 = self.torch.empty(3, dtype=self.torch.int64, device=self.dev)
+        N.check(self.lib.lc_quantize_checked(_ptr(x), Cc, _ptr(recon), n, float(mean), float(std), float(thr32),
+                                             float(thr2_32), float(thr * 2.0), float(check_abs_err), _ptr(mask),
+                                             _ptr(q), _ptr(out3), _ptr(ws), self._stream()), "lc_quantize_checked")
+        n_out, viol, bits = out3.cpu().tolist()
+        return mask, q[:n_out], int(viol), struct.unpack("<d", struct.pack("<q", bits))[0]
 
     def reconstruct(self, recon, mask, q, mean, std, thr2):
         """decompress.py:86-104 -> (T,H,W) float32."""
@@ -292,7 +301,7 @@ class Engine:
         n = sym.numel()
         if hist is None:
             hist = self.hist(sym) if n else np.zeros(256, np.int64)
-        table = HF.build_table(hist)
+        table = HF.build_table_native(hist)
         bits = table.encoded_bits(hist)
         payload, lens, total_bits = self.huff_pack(sym, table, bits) if n else (b"", np.zeros(0, np.uint16), 0)
         meta = dict(extra, n=int(n), seg=SEG, bits=int(total_bits), ref_tree=bool(table.reference_tree))
@@ -347,7 +356,7 @@ class Engine:
         self.launches += 1
         h2 = h2.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
         hists = (h2[:256], h2[256:])
-        costs = [HF.build_table(h).encoded_bits(h) + 32 * int(h[ESC]) for h in hists]
+        costs = [HF.build_table_native(h).encoded_bits(h) + 32 * int(h[ESC]) for h in hists]
         pick = 0 if (costs[0] <= costs[1] or n == 0) else 1
         diff, bias = cand[pick]
         ne = int(hists[pick][ESC])
@@ -449,8 +458,8 @@ class Engine:
         hh = h3.cpu().numpy().astype(np.int64) & 0xFFFFFFFF                       # sync 1
         hist_m, hists_q = hh[:256], (hh[256:512], hh[512:])
         # ---- host: tables
-        tab_m = HF.build_table(hist_m)
-        tabs_q = [HF.build_table(h) for h in hists_q]
+        tab_m = HF.build_table_native(hist_m)
+        tabs_q = [HF.build_table_native(h) for h in hists_q]
         costs = [tb.encoded_bits(h) + 32 * int(h[ESC]) for tb, h in zip(tabs_q, hists_q)]
         pick = 0 if costs[0] <= costs[1] else 1
         diff, bias = cand[pick]
@@ -477,14 +486,26 @@ class Engine:
         return comp_error, comp_mask
 
     # -- latent slot (compress.py:142-144; fpzip is replaced by a tagged container) -----
-    def pack_latent(self, latent, codec="raw") -> bytes:
+    def stage_latent(self, latent):
+        """Start the device->pinned-host copy of the latent (no sync); pass the result to pack_latent()
+        after any later sync of the stream so that the copy hides behind the decoder."""
+        t = self.torch
+        nb = latent.numel() * 4
+        pin = self._pinned("latent", nb)
+        pin[:nb].copy_(latent.reshape(-1).view(t.uint8), non_blocking=True)
+        return pin, nb
+
+    def pack_latent(self, latent, codec="raw", staged=None) -> bytes:
         meta = {"precision": self.precision, "model": self.model.arch.name,
                 "filters": self.model.arch.filters, "kernel": self.model.arch.kernel, "codec": codec}
         mj = json.dumps(meta).encode()
-        raw = latent.cpu().numpy().astype("<f4").tobytes()
+        if staged is not None:                      # float32 little-endian, already on the host
+            raw = memoryview(staged[0].numpy())[:staged[1]]
+        else:
+            raw = latent.cpu().numpy().astype("<f4").tobytes()
         if codec == "bz2":
             raw = bz2.compress(raw, 9)
-        return LATENT_MAGIC + struct.pack("<I", len(mj)) + mj + raw
+        return b"".join([LATENT_MAGIC, struct.pack("<I", len(mj)), mj, raw])
 
     def join_latents(self, blobs) -> bytes:
         """Concatenate the latent containers of consecutive chunk ranges (time shards) into one."""

@@ -51,6 +51,7 @@ SIGNATURES = {
     "lc_decode": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "lc_scan_workspace_bytes": (_sz, [_i64]),
     "lc_quantize": (_i, [_p, _i, _p, _i64, _f, _f, _f, _f, _p, _p, _p, _p, _p]),
+    "lc_quantize_checked": (_i, [_p, _i, _p, _i64, _f, _f, _f, _f, _d, _d, _p, _p, _p, _p, _p]),
     "lc_diff_i32": (_i, [_p, _i64, _p, _p]),
     "lc_diff_i8": (_i, [_p, _i64, _p, _p]),
     "lc_cumsum_i32": (_i, [_p, _i64, _p, _p, _p]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "lc_unsymbolize_i32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p]),
     "lc_pack_trits": (_i, [_p, _i64, _p, _p]),
     "lc_unpack_trits": (_i, [_p, _i64, _p, _p]),
+    "lc_huff_build_table": (_i, [_p, _i, _p, _p, _p, _p]),
     "lc_huff_max_bytes": (_sz, [_i64]),
     "lc_huff_workspace_bytes": (_sz, [_i64, _i]),
     "lc_huff_encode": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p]),

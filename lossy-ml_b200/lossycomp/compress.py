@@ -65,6 +65,7 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         mean, std = np.float32(inject["mean"]), np.float32(inject["std"])
         max_abs = float(inject.get("max_abs", max_abs))
     latent = eng.encode(x, mean, std, batch=batch)                                   # compress.py:66-86
+    staged = eng.stage_latent(latent)    # its D2H copy runs behind the decoder; the quantiser's sync covers it
     tm and tm.mark("encode")
     if "recon_std" in inject:
         recon = inject["recon_std"]
@@ -79,14 +80,20 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         thr = abs_err - g
     elif mode != "parity":
         raise ValueError("mode must be 'strict' or 'parity'")
+    # verify: None/True = bound check fused into the quantisation pass (strict mode's default);
+    # "full" = run the decoder's reconstruct kernel and an independent fp64 comparison; False = none
     verify = (mode == "strict") if verify is None else verify
     while True:
-        mask, q = eng.quantize(x, recon, mean, std, thr)                             # compress.py:114-135
         thr2 = thr * 2.0                                                             # compress.py:129
-        if not verify:
+        if verify == "full":
+            mask, q = eng.quantize(x, recon, mean, std, thr)                         # compress.py:114-135
+            xhat = eng.reconstruct(recon, mask, q, mean, std, thr2)
+            viol, max_err = eng.verify(x, xhat, abs_err)
+        elif verify:
+            mask, q, viol, max_err = eng.quantize(x, recon, mean, std, thr, check_abs_err=abs_err)
+        else:
+            mask, q = eng.quantize(x, recon, mean, std, thr)
             break
-        xhat = eng.reconstruct(recon, mask, q, mean, std, thr2)
-        viol, max_err = eng.verify(x, xhat, abs_err)
         info.update(violations=viol, max_err=max_err)
         if viol == 0 or mode != "strict":
             break
@@ -96,7 +103,7 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     n_out = int(q.numel())
     if latent_codec is None:      # compat codec: lossless host coder for the latent too (fpzip's role, compress.py:144)
         latent_codec = "bz2" if codec == "bz2" else "raw"
-    comp_data = eng.pack_latent(latent, latent_codec)                                # compress.py:142-144
+    comp_data = eng.pack_latent(latent, latent_codec, staged)                                # compress.py:142-144
     tm and tm.mark("latent_pack")
     lshape = (latent.shape[0],) + tuple(eng.model.arch.latent_shape()[1:])
     if codec == "bz2":

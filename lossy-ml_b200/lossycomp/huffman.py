@@ -133,12 +133,13 @@ class Table:
         return lut, np.array(nodes, dtype=np.int32).reshape(-1)
 
     # -- serialisation (explicit codes: the tree is not canonical) -----------
+    _REC = np.dtype([("s", "u1"), ("l", "u1"), ("c", "<u4")])
+
     def to_bytes(self) -> bytes:
-        syms = [int(v) for v in np.nonzero(self.used)[0]]
-        out = bytearray([len(syms) & 0xFF, len(syms) >> 8])
-        for s in syms:
-            out += bytes([s, int(self.len[s])]) + int(self.code[s]).to_bytes(4, "little")
-        return bytes(out)
+        syms = np.nonzero(self.used)[0]
+        rec = np.empty(syms.size, dtype=self._REC)
+        rec["s"], rec["l"], rec["c"] = syms, self.len[syms], self.code[syms]
+        return bytes([syms.size & 0xFF, syms.size >> 8]) + rec.tobytes()
 
     @staticmethod
     def from_bytes(b: bytes) -> Tuple["Table", int]:
@@ -154,6 +155,24 @@ class Table:
 
     def encoded_bits(self, hist) -> int:
         return int((np.asarray(hist, dtype=np.int64) * self.len.astype(np.int64)).sum())
+
+
+def build_table_native(hist) -> Table:
+    """build_table() through the library's host entry point lc_huff_build_table (what the codec calls:
+    three tables per compress() cost 0.4 ms in Python, microseconds in C); same result bit for bit."""
+    import ctypes as C
+
+    from . import _native as N
+    h = np.ascontiguousarray(hist, dtype=np.int64)
+    assert h.size == 256
+    t = Table({}, False)
+    used = np.zeros(256, dtype=np.uint8)
+    ref = C.c_int(0)
+    N.check(N.lib().lc_huff_build_table(h.ctypes.data, MAX_CODE_BITS, t.code.ctypes.data, t.len.ctypes.data,
+                                        used.ctypes.data, C.byref(ref)), "lc_huff_build_table")
+    t.used = used.astype(bool)
+    t.reference_tree = bool(ref.value)
+    return t
 
 
 def build_table(hist) -> Table:

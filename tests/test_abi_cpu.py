@@ -100,3 +100,32 @@ def test_chunk_index_map_matches_oracle_property(lib):
     # and the merge really is the inverse of chunk on the kept parts
     a = np.arange(33 * 100 * 97, dtype=np.float32).reshape(33, 100, 97, 1)
     assert np.array_equal(O.merge_data(O.chunk_data(a), a.shape), a)
+
+
+def test_native_table_builder_equals_reference_mirror():
+    """lc_huff_build_table (host C) against huffman.build_table (the Python mirror of the reference's tree,
+    itself pinned to the reference's code strings in test_oracle_golden): same codes, lengths and flags,
+    including heavy ties, single symbols, empty histograms and trees that need depth capping."""
+    from lossycomp import huffman as HF
+    rng = np.random.default_rng(3)
+    hists = [np.zeros(256, np.int64)]
+    one = np.zeros(256, np.int64); one[200] = 9; hists.append(one)
+    fib = [1, 1]
+    while len(fib) < 70:
+        fib.append(fib[-1] + fib[-2])
+    deep = np.zeros(256, np.int64); deep[:70] = fib; hists.append(deep)
+    for trial in range(400):
+        k = int(rng.integers(1, 257))
+        h = np.zeros(256, np.int64)
+        idx = rng.choice(256, k, replace=False)
+        h[idx] = [rng.integers(1, 4, k), rng.integers(1, 1 << 30, k), np.ones(k, np.int64),
+                  (2.0 ** rng.uniform(0, 40, k)).astype(np.int64) + 1][trial % 4]
+        hists.append(h)
+    for h in hists:
+        a, b = HF.build_table(h), HF.build_table_native(h)
+        assert np.array_equal(a.code, b.code) and np.array_equal(a.len, b.len)
+        assert np.array_equal(a.used, b.used) and a.reference_tree == b.reference_tree
+        assert a.to_bytes() == b.to_bytes()
+        back, _ = HF.Table.from_bytes(b.to_bytes())
+        assert back.codes == b.codes
+    assert not HF.build_table_native(deep).reference_tree and HF.build_table_native(deep).len.max() <= 32

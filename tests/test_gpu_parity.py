@@ -306,3 +306,34 @@ def test_host_io_paths_agree(torch):
     assert np.abs(x[..., 0].astype(np.float64) - fresh[..., 0]).max() <= 0.05
     with pytest.raises(AssertionError):
         decompress(b_page, out=np.empty(7, dtype=np.float32))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fused_bound_check_equals_reference_violation_set(eng, torch, name):
+    """lc_quantize_checked on the reference's reconstruction, in the reference's arithmetic (thr = abs_err):
+    same mask / codes as lc_quantize, and its in-pass violation count / maximum error equal those of the
+    reference's own decompress() output -- i.e. it reproduces the reference's 1/2-ulp violations exactly."""
+    g = golden_case(name)
+    x = dev(torch, g["x"])
+    recon = dev(torch, g["recon_std"][..., 0])
+    thr = float(g["abs_err"])
+    m0, q0 = eng.quantize(x, recon, g["mean"], g["std"], thr)
+    m1, q1, viol, mx = eng.quantize(x, recon, g["mean"], g["std"], thr, check_abs_err=thr)
+    assert torch.equal(m0, m1) and torch.equal(q0, q1)
+    assert viol == int(g["violations"])
+    ref_max = np.abs(g["x"][..., 0].astype(np.float64) - g["xhat"][..., 0].astype(np.float64)).max()
+    assert mx == ref_max
+    # and the independent two-kernel path agrees
+    xhat = eng.reconstruct(recon, m1, q1, g["mean"], g["std"], thr * 2.0)
+    assert eng.verify(x, xhat, thr) == (viol, mx)
+
+
+def test_verify_modes_give_identical_blobs(eng, torch):
+    from lossycomp.compress import compress_device
+    from oracle import lossycomp_oracle as O
+    x = dev(torch, O.synthetic_field(16, 100, 120, seed=5))
+    a, ia = compress_device(eng, x, 0.02, verify="full")
+    b, ib = compress_device(eng, x, 0.02)
+    c, _ = compress_device(eng, x, 0.02, verify=False)
+    assert pickle.dumps(a) == pickle.dumps(b) == pickle.dumps(c)
+    assert ia["violations"] == ib["violations"] == 0 and ia["max_err"] == ib["max_err"] <= 0.02

@@ -20,8 +20,7 @@ for i in range(3):
 ms, cnt = eng.profile_read()
 print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms))
 ''' % (ROOT, ROOT)
-for dbg, label in [(0, "full"), (16, "single issuer"), (1, "no MMA"), (8, "no copies"), (9, "no MMA no copies"),
-                   ]:
+for dbg, label in [(0, "full"), (32, "UP stores coalesced (wrong place)"), (64, "UP stores both columns"), (4, "no stores")]:
     env = dict(os.environ, LOSSYCOMP_TC_DEBUG=str(dbg))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
