@@ -60,7 +60,6 @@ struct SweepParams {
   int slab_slots, slab_start;    // the stage holds slots [row0 + 128*j + slab_start, +slab_slots) of every plane
   int stages;
   int nbuf, acc_stride, tmem_cols;   // TMEM accumulator ring
-  int skip_tile;                     // K3 with residual add: the skip tile of the plane rides in the stage (bulk copy)
   // MMA
   int N, nks, nvar;
   const uint4* wimg;
@@ -70,7 +69,7 @@ struct SweepParams {
   uint64_t a_desc[kMaxVar][kMaxKs], b_desc[kMaxVar][kMaxKs];   // descriptors for smem offsets relative to sA / sB
   const float* bias;
   int cout, relu, half, out_T;
-  int debug;   // bit0: no MMA issue, bit1: no epilogue TMEM loads, bit2: no stores, bit3: no bulk copies
+  int debug;   // ablation: bit0 no MMA issue, bit3 no bulk copies, bit4 single issuer warp
 };
 
 // 12 consecutive accumulator columns of this thread's TMEM lane
@@ -124,112 +123,107 @@ __device__ __forceinline__ RowInfo row_info(const SweepParams& p, int item, int 
   return r;
 }
 
-// y = acc + bias (+ skip) -> ReLU -> 16-bit -> out(n, t, h, w)
-struct VoxAddr {
-  long long o0, s0;     // vector index of (n, t=0, h, w, g=0) in the output / skip tensor
-  int o_t, s_t;         // vectors per time plane
+// Output / skip addressing of one tile row: vector pointers of (n, t = 0, h, w, group 0)
+struct VoxPtr {
+  uint4* o;
+  const uint4* s;          // nullptr when the layer has no residual input
+  long long o_t, s_t;      // vectors per time plane
+  long long o_g, s_g;      // vectors per group plane
 };
 
-__device__ __forceinline__ VoxAddr vox_addr(const SweepParams& p, int n, int h, int w) {
-  VoxAddr a;
-  a.o0 = gp_vec_index(p.out, n, 0, h, w, 0);
-  a.o_t = p.out.NP * p.out.G * p.out.S;
-  a.s0 = p.skip.base ? gp_vec_index(p.skip, n, 0, h, w, 0) : 0;
-  a.s_t = p.skip.NP * p.skip.G * p.skip.S;
+__device__ __forceinline__ VoxPtr vox_ptr(const SweepParams& p, int n, int h, int w) {
+  VoxPtr a;
+  a.o = reinterpret_cast<uint4*>(p.out.base) + gp_vec_index(p.out, n, 0, h, w, 0);
+  a.o_t = (long long)p.out.NP * p.out.G * p.out.S;
+  a.o_g = p.out.S;
+  a.s = p.skip.base ? reinterpret_cast<const uint4*>(p.skip.base) + gp_vec_index(p.skip, n, 0, h, w, 0) : nullptr;
+  a.s_t = (long long)p.skip.NP * p.skip.G * p.skip.S;
+  a.s_g = p.skip.S;
   return a;
 }
 
-// Channels [12*half, 12*half+12) of one voxel: y = acc + bias (+ skip) -> ReLU -> 16-bit -> out.
-// half 0 owns vector g0 and the low 8 bytes of g1, half 1 the high 8 bytes of g1 and vector g2.
-__device__ __forceinline__ void unpack4(const uint2 v, int half16, float f[4]) {
-  f[0] = h16_to_float((unsigned short)(v.x & 0xffff), half16);
-  f[1] = h16_to_float((unsigned short)(v.x >> 16), half16);
-  f[2] = h16_to_float((unsigned short)(v.y & 0xffff), half16);
-  f[3] = h16_to_float((unsigned short)(v.y >> 16), half16);
-}
-__device__ __forceinline__ uint2 pack4(const float f[4], int half16) {
-  return make_uint2(pack2(f[0], f[1], half16), pack2(f[2], f[3], half16));
-}
-
+// The 12 channels [12*half, 12*half+12) of a voxel as stored: half 0 owns vector g0 and the low 8 bytes of
+// g1, half 1 the high 8 bytes of g1 and vector g2.
 struct SkipRegs {
   uint4 a;
   uint2 b;
 };
 
-__device__ __forceinline__ SkipRegs load_skip(const SweepParams& p, const VoxAddr& va, int t, int half) {
+__device__ __forceinline__ SkipRegs load_skip(const uint4* sk, long long s_g, int half) {
   SkipRegs r;
-  const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base);
-  const long long si = va.s0 + (long long)t * va.s_t;
   if (half == 0) {
-    r.a = __ldg(sk + si);
-    r.b = __ldg(reinterpret_cast<const uint2*>(sk + si + p.skip.S));
+    r.a = __ldg(sk);
+    r.b = __ldg(reinterpret_cast<const uint2*>(sk + s_g));
   } else {
-    r.b = __ldg(reinterpret_cast<const uint2*>(sk + si + p.skip.S) + 1);
-    r.a = __ldg(sk + si + 2LL * p.skip.S);
+    r.b = __ldg(reinterpret_cast<const uint2*>(sk + s_g) + 1);
+    r.a = __ldg(sk + 2 * s_g);
   }
   return r;
 }
 
-// skip tile in shared memory: [group][128 rows][16 bytes]
-__device__ __forceinline__ SkipRegs load_skip_smem(const uint8_t* tile, int row, int half) {
-  SkipRegs r;
-  const uint4* g0 = reinterpret_cast<const uint4*>(tile) + row;
-  if (half == 0) {
-    r.a = g0[0];
-    r.b = *reinterpret_cast<const uint2*>(g0 + 128);
+template <int H16>
+__device__ __forceinline__ void unpack2_t(unsigned w, float& lo, float& hi) {
+  if (H16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
   } else {
-    r.b = *(reinterpret_cast<const uint2*>(g0 + 128) + 1);
-    r.a = g0[256];
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
+}
+
+// (ReLU +) saturate + round-to-nearest-even + pack of two floats: one F2FP
+template <int H16, int RELU>
+__device__ __forceinline__ unsigned pack2_t(float a, float b) {
+  unsigned r;
+  if (H16) {
+    if (RELU) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  } else {
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   }
   return r;
 }
 
-__device__ __forceinline__ void store_voxel(const SweepParams& p, const int h16, const float (&bias_r)[kHalf],
-                                            const VoxAddr& va, int t, int half, const float (&acc)[kHalf],
-                                            const SkipRegs* skp) {
+// y (bias already inside) (+ skip) -> ReLU -> 16-bit -> the voxel's 12 channels of this half at plane pointer o.
+// Channels beyond cout need no masking: their weight columns, bias and skip padding are zero, so y is +0.
+template <int H16, int RELU, bool SKIP>
+__device__ __forceinline__ void store12(uint4* o, long long o_g, int G, int half, const float (&acc)[kHalf],
+                                        const SkipRegs& sk) {
   float y[kHalf];
 #pragma unroll
-  for (int c = 0; c < kHalf; ++c) y[c] = acc[c] + bias_r[c];
-  // y[0..7]/y[8..11] for half 0 are (vector g0, low half of g1); for half 1 y[0..3]/y[4..11] are
-  // (high half of g1, vector g2)
-  if (skp) {
-    float f8[8], f4[4];
-    unpack8(skp->a, h16, f8);
-    unpack4(skp->b, h16, f4);
+  for (int c = 0; c < kHalf; ++c) y[c] = acc[c];
+  if (SKIP) {
+    float f[kHalf];   // the skip channels in the order of y
     if (half == 0) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] = __fadd_rn(y[k], f8[k]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) y[8 + k] = __fadd_rn(y[8 + k], f4[k]);
+      unpack2_t<H16>(sk.a.x, f[0], f[1]); unpack2_t<H16>(sk.a.y, f[2], f[3]);
+      unpack2_t<H16>(sk.a.z, f[4], f[5]); unpack2_t<H16>(sk.a.w, f[6], f[7]);
+      unpack2_t<H16>(sk.b.x, f[8], f[9]); unpack2_t<H16>(sk.b.y, f[10], f[11]);
     } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(y[k], f4[k]);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) y[4 + k] = __fadd_rn(y[4 + k], f8[k]);
+      unpack2_t<H16>(sk.b.x, f[0], f[1]); unpack2_t<H16>(sk.b.y, f[2], f[3]);
+      unpack2_t<H16>(sk.a.x, f[4], f[5]); unpack2_t<H16>(sk.a.y, f[6], f[7]);
+      unpack2_t<H16>(sk.a.z, f[8], f[9]); unpack2_t<H16>(sk.a.w, f[10], f[11]);
     }
-  }
-  // channels beyond cout are stored as zeros (only the last vector of the second half can contain them)
 #pragma unroll
-  for (int c = 0; c < kHalf; ++c)
-    if (half * kHalf + c >= p.cout) y[c] = 0.f;
-  uint4* o = reinterpret_cast<uint4*>(p.out.base);
-  const long long oi = va.o0 + (long long)t * va.o_t;
-  const int relu = p.relu;
+    for (int c = 0; c < kHalf; ++c) y[c] = __fadd_rn(y[c], f[c]);
+  }
   if (half == 0) {
-    o[oi] = pack8_act(&y[0], h16, relu);
-    if (p.out.G > 1)
-      *reinterpret_cast<uint2*>(o + oi + p.out.S) =
-          make_uint2(pack2_act(y[8], y[9], h16, relu), pack2_act(y[10], y[11], h16, relu));
+    o[0] = make_uint4(pack2_t<H16, RELU>(y[0], y[1]), pack2_t<H16, RELU>(y[2], y[3]),
+                      pack2_t<H16, RELU>(y[4], y[5]), pack2_t<H16, RELU>(y[6], y[7]));
+    if (G > 1)
+      *reinterpret_cast<uint2*>(o + o_g) = make_uint2(pack2_t<H16, RELU>(y[8], y[9]), pack2_t<H16, RELU>(y[10], y[11]));
   } else {
-    if (p.out.G > 1)
-      *(reinterpret_cast<uint2*>(o + oi + p.out.S) + 1) =
-          make_uint2(pack2_act(y[0], y[1], h16, relu), pack2_act(y[2], y[3], h16, relu));
-    if (p.out.G > 2) o[oi + 2LL * p.out.S] = pack8_act(&y[4], h16, relu);
+    if (G > 1)
+      *(reinterpret_cast<uint2*>(o + o_g) + 1) = make_uint2(pack2_t<H16, RELU>(y[0], y[1]), pack2_t<H16, RELU>(y[2], y[3]));
+    if (G > 2)
+      o[2 * o_g] = make_uint4(pack2_t<H16, RELU>(y[4], y[5]), pack2_t<H16, RELU>(y[6], y[7]),
+                              pack2_t<H16, RELU>(y[8], y[9]), pack2_t<H16, RELU>(y[10], y[11]));
   }
 }
 
-template <int MODE, int H16>
-__global__ void __launch_bounds__(kTcThreads, (MODE == MODE_K3 || MODE == MODE_K4 || MODE == MODE_UP) ? 2 : 1)
+template <int MODE, int H16, int RELU>
+__global__ void __launch_bounds__(kTcThreads, MODE == MODE_DOWN ? 1 : 2)
 sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull[kMaxBufs], tempty[kMaxBufs], wbar;
@@ -240,8 +234,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   // issuer's descriptor arithmetic stays in uniform registers
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int slab_bytes = p.slab_slots * 16;
-  const int skip_bytes = p.skip_tile ? p.skip.G * 128 * 16 : 0;
-  const int stage_bytes = p.in_NPG * slab_bytes + skip_bytes;
+  const int stage_bytes = p.in_NPG * slab_bytes;
   uint8_t* sB = smem;
   uint8_t* sA = smem + ((p.wimg_bytes + 127) & ~127);
   if (threadIdx.x == 0) {
@@ -276,13 +269,6 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
             umma::bulk_g2s(sA + stage * stage_bytes + g * slab_bytes,
                            p.in + slab0 + (long long)(t * p.in_NPG + g) * p.in_S, (uint32_t)slab_bytes,
                            &full[stage]);
-          if (p.skip_tile) {   // rows of this tile of skip plane t (consumed when output plane t is finalised)
-            const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride +
-                              p.skip.GL + p.row0 + tile * 128;
-            for (int g = 0; g < p.skip.G; ++g)
-              umma::bulk_g2s(sA + stage * stage_bytes + p.in_NPG * slab_bytes + g * 2048,
-                             sk + (long long)(t * p.skip.G + g) * p.skip.S, 2048u, &full[stage]);
-          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -332,28 +318,25 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   } else if (warp >= 2 && warp <= 9) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     // 8 warps: warp w reads TMEM lanes 32*(w&3)..+31 (hardware rule); warps 2-5 take output channels
-    // 0..11 of every dt block, warps 6-9 channels 12..23.
+    // 0..11 of every dt block, warps 6-9 channels 12..23.  The warps are issue-bound, so the loops below
+    // are written to cost few instructions per plane: accumulators rotate through unrolled steps instead
+    // of register moves, the bias is added where a plane's first block arrives (replacing a move), ReLU
+    // and the 16-bit rounding are one F2FP per channel pair, nothing is masked.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + half * kHalf;
-    const bool has_skip = p.skip.base != nullptr;
     float bias_r[kHalf];
 #pragma unroll
     for (int c = 0; c < kHalf; ++c) bias_r[c] = s_bias[half * kHalf + c];
-    int ebuf = 0, ephase = 0;
-    int estage = 0, efphase = 0;   // stage whose skip tile is read next, and the parity of its `full` barrier
+    int ebuf = 0, ephase = 0, estage = 0;
     auto wait_d = [&]() -> uint32_t {
-      const int buf = ebuf;
-      umma::mbar_wait(&tfull[buf], ephase);
+      umma::mbar_wait(&tfull[ebuf], ephase);
       umma::tcgen05_fence_after();
       // the MMAs that read this step's stage are complete: hand the stage back to the producer
-      // (K3 with a skip tile keeps it one step longer and releases it itself after reading the tile)
-      if (!p.skip_tile) {
-        if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
-        if (++estage == p.stages) { estage = 0; efphase ^= 1; }
-      }
-      return lane_addr + buf * p.acc_stride;
+      if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
+      if (++estage == p.stages) estage = 0;
+      return lane_addr + ebuf * p.acc_stride;
     };
     auto release_d = [&]() {
       umma::tcgen05_fence_before();
@@ -361,81 +344,131 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       if (lane == 0) umma::mbar_arrive(&tempty[ebuf]);
       if (++ebuf == p.nbuf) { ebuf = 0; ephase ^= 1; }
     };
+    const int G = p.out.G;
+    const int T = p.in_T;
     if (MODE == MODE_K4_OUT1 && half == 1) {
       // single output channel: the second half of the epilogue warps has nothing to do
     } else
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const RowInfo ri = row_info(p, item, row);
-      VoxAddr va;
-      VoxAddr vb;   // experiment (debug bit 64): the neighbouring column
-      if (MODE == MODE_UP) {
-        va = vox_addr(p, ri.n, 2 * ri.h + (ri.cls >> 1), (p.debug & 32) ? ri.w + p.rows_W * (ri.cls & 1) : 2 * ri.w + (ri.cls & 1));
-        vb = vox_addr(p, ri.n, 2 * ri.h + (ri.cls >> 1), 2 * ri.w + 1 - (ri.cls & 1));
-      }
-      else if (MODE != MODE_K4_OUT1) va = vox_addr(p, ri.n, ri.h, ri.w);
+      const bool valid = ri.valid;
+      VoxPtr vp;
+      if (MODE == MODE_UP) vp = vox_ptr(p, ri.n, 2 * ri.h + (ri.cls >> 1), 2 * ri.w + (ri.cls & 1));
+      else if (MODE != MODE_K4_OUT1) vp = vox_ptr(p, ri.n, ri.h, ri.w);
+      const SkipRegs no_skip = {};
       if (MODE == MODE_K3) {
-        // block dt -> output plane t_in - dt + 1
-        float aP[kHalf], aC[kHalf], aN[kHalf];
+        // block dt -> output plane t_in - dt + 1.  Roles at step t: P = plane t-1 (completes), C = plane t,
+        // N = plane t+1 (starts with this step's block 0 + bias).
+        auto run = [&](auto skip_tag) {
+          constexpr bool SKIP = decltype(skip_tag)::value;
+          float a0[kHalf], a1[kHalf], a2[kHalf];
 #pragma unroll
-        for (int c = 0; c < kHalf; ++c) { aP[c] = 0.f; aC[c] = 0.f; }
-        SkipRegs sk;
-        for (int t = 0; t < p.in_T; ++t) {
-          // the skip values of the plane finished in this step are fetched before waiting for the MMA
-          if (has_skip && !p.skip_tile && t >= 1 && ri.valid) sk = load_skip(p, va, t - 1, half);
-          const uint32_t ta = wait_d();
-          if (!(p.debug & 2)) {
-            float db[3][kHalf];
-            ld_blocks<3>(ta, db);
-            release_d();
+          for (int c = 0; c < kHalf; ++c) { a0[c] = 0.f; a1[c] = bias_r[c]; }
+          uint4* op = vp.o - vp.o_t;            // plane t-1 of the output / skip tensors, advanced every step
+          const uint4* sp = vp.s - vp.s_t;
+          auto step = [&](float (&aP)[kHalf], float (&aC)[kHalf], float (&aN)[kHalf], int t) {
+            SkipRegs sk = no_skip;
+            // the skip values of the plane finished in this step are fetched before waiting for the MMA
+            if (SKIP && t >= 1 && valid) sk = load_skip(sp, vp.s_g, half);
+            const uint32_t ta = wait_d();
+            if (SKIP) {
+              // blocks 1,2 first: plane t-1 completes and is stored, freeing registers before block 0 arrives
+              // (with the six skip registers the three-block form spills)
+              {
+                float db[2][kHalf];
+                ld_blocks<2>(ta + 24, db);
 #pragma unroll
-            for (int c = 0; c < kHalf; ++c) { aN[c] = db[0][c]; aC[c] += db[1][c]; aP[c] += db[2][c]; }
+                for (int c = 0; c < kHalf; ++c) { aC[c] += db[0][c]; aP[c] += db[1][c]; }
+              }
+              if (t >= 1 && valid) store12<H16, RELU, SKIP>(op, vp.o_g, G, half, aP, sk);
+              float d0[kHalf];
+              ld_cols12(ta, d0);
+              release_d();
+#pragma unroll
+              for (int c = 0; c < kHalf; ++c) aN[c] = d0[c] + bias_r[c];
+            } else {
+              float db[3][kHalf];
+              ld_blocks<3>(ta, db);
+              release_d();
+#pragma unroll
+              for (int c = 0; c < kHalf; ++c) {
+                aN[c] = db[0][c] + bias_r[c];
+                aC[c] += db[1][c];
+                aP[c] += db[2][c];
+              }
+              if (t >= 1 && valid) store12<H16, RELU, SKIP>(op, vp.o_g, G, half, aP, sk);
+            }
+            op += vp.o_t;
+            if (SKIP) sp += vp.s_t;
+          };
+          auto finish = [&](float (&aP)[kHalf]) {
+            if (!valid) return;
+            SkipRegs sk = no_skip;
+            if (SKIP) sk = load_skip(sp, vp.s_g, half);
+            store12<H16, RELU, SKIP>(op, vp.o_g, G, half, aP, sk);
+          };
+          int t = 0;
+          for (; t + 3 <= T; t += 3) { step(a0, a1, a2, t); step(a1, a2, a0, t + 1); step(a2, a0, a1, t + 2); }
+          if (T - t == 0) {
+            finish(a0);
+          } else if (T - t == 1) {
+            step(a0, a1, a2, t);
+            finish(a1);
           } else {
-            release_d();
+            step(a0, a1, a2, t);
+            step(a1, a2, a0, t + 1);
+            finish(a2);
           }
-          if (p.skip_tile && t >= 1) {
-            // skip tile of plane t-1 sits in the previous step's stage: read it, then release that stage
-            // acquire the bulk-copy (async proxy) writes of that stage ourselves: observing tfull alone
-            // does not order them before our generic-proxy reads
-            umma::mbar_wait(&full[estage], efphase);
-            sk = load_skip_smem(sA + estage * stage_bytes + p.in_NPG * slab_bytes, row, half);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
-            if (++estage == p.stages) { estage = 0; efphase ^= 1; }
-          }
-          if (t >= 1 && ri.valid && !(p.debug & 4)) store_voxel(p, H16, bias_r, va, t - 1, half, aP, has_skip ? &sk : nullptr);
-#pragma unroll
-          for (int c = 0; c < kHalf; ++c) { aP[c] = aC[c]; aC[c] = aN[c]; }
-        }
-        if (ri.valid) {
-          if (has_skip && !p.skip_tile) sk = load_skip(p, va, p.in_T - 1, half);
-        }
-        if (p.skip_tile) {
-          umma::mbar_wait(&full[estage], efphase);
-          sk = load_skip_smem(sA + estage * stage_bytes + p.in_NPG * slab_bytes, row, half);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
-          if (++estage == p.stages) { estage = 0; efphase ^= 1; }
-        }
-        if (ri.valid) store_voxel(p, H16, bias_r, va, p.in_T - 1, half, aP, has_skip ? &sk : nullptr);
+        };
+        if (vp.s != nullptr) run(std::true_type{}); else run(std::false_type{});
       } else if (MODE == MODE_K4) {
-        // k=4, pad 1/2: block dt -> output plane t_in - dt + 1  (planes t+1, t, t-1, t-2)
-        float a1[kHalf], a2[kHalf], a3[kHalf], a0[kHalf];
+        // k=4, pad 1/2: block dt -> output plane t_in - dt + 1.  Roles at step t: A3 = plane t-2 (completes),
+        // A2 = t-1, A1 = t, A0 = t+1 (starts).
+        float b0[kHalf], b1[kHalf], b2[kHalf], b3[kHalf];
 #pragma unroll
-        for (int c = 0; c < kHalf; ++c) { a1[c] = 0.f; a2[c] = 0.f; a3[c] = 0.f; }
-        for (int t = 0; t < p.in_T; ++t) {
+        for (int c = 0; c < kHalf; ++c) { b0[c] = 0.f; b1[c] = 0.f; b2[c] = bias_r[c]; }
+        uint4* op = vp.o - 2 * vp.o_t;          // plane t-2
+        auto step = [&](float (&A3)[kHalf], float (&A2)[kHalf], float (&A1)[kHalf], float (&A0)[kHalf], int t) {
+          // blocks 2,3 first: plane t-2 completes and is stored, which frees its registers for plane t+1
+          // (four accumulator sets plus four blocks in flight would not fit the 80-register budget)
           const uint32_t ta = wait_d();
-          float db[4][kHalf];
-          ld_blocks<4>(ta, db);
-          release_d();
+          {
+            float db[2][kHalf];
+            ld_blocks<2>(ta + 48, db);
 #pragma unroll
-          for (int c = 0; c < kHalf; ++c) { a0[c] = db[0][c]; a1[c] += db[1][c]; a2[c] += db[2][c]; a3[c] += db[3][c]; }
-          if (t >= 2 && ri.valid) store_voxel(p, H16, bias_r, va, t - 2, half, a3, nullptr);
+            for (int c = 0; c < kHalf; ++c) { A2[c] += db[0][c]; A3[c] += db[1][c]; }
+          }
+          if (t >= 2 && valid) store12<H16, RELU, false>(op, vp.o_g, G, half, A3, no_skip);
+          op += vp.o_t;
+          {
+            float db[2][kHalf];
+            ld_blocks<2>(ta, db);
+            release_d();
 #pragma unroll
-          for (int c = 0; c < kHalf; ++c) { a3[c] = a2[c]; a2[c] = a1[c]; a1[c] = a0[c]; }
+            for (int c = 0; c < kHalf; ++c) { A0[c] = db[0][c] + bias_r[c]; A1[c] += db[1][c]; }
+          }
+        };
+        auto finish = [&](float (&A3)[kHalf], float (&A2)[kHalf]) {
+          if (!valid) return;
+          if (T >= 2) store12<H16, RELU, false>(op, vp.o_g, G, half, A3, no_skip);
+          store12<H16, RELU, false>(op + vp.o_t, vp.o_g, G, half, A2, no_skip);
+        };
+        int t = 0;
+        for (; t + 4 <= T; t += 4) {
+          step(b0, b1, b2, b3, t); step(b1, b2, b3, b0, t + 1); step(b2, b3, b0, b1, t + 2); step(b3, b0, b1, b2, t + 3);
         }
-        if (ri.valid) {
-          store_voxel(p, H16, bias_r, va, p.in_T - 2, half, a3, nullptr);
-          store_voxel(p, H16, bias_r, va, p.in_T - 1, half, a2, nullptr);
+        const int r = T - t;
+        if (r == 0) {
+          finish(b0, b1);
+        } else if (r == 1) {
+          step(b0, b1, b2, b3, t);
+          finish(b1, b2);
+        } else if (r == 2) {
+          step(b0, b1, b2, b3, t); step(b1, b2, b3, b0, t + 1);
+          finish(b2, b3);
+        } else {
+          step(b0, b1, b2, b3, t); step(b1, b2, b3, b0, t + 1); step(b2, b3, b0, b1, t + 2);
+          finish(b3, b0);
         }
       } else if constexpr (MODE == MODE_K4_OUT1) {
         // cout = 1, taps dt and dw folded into N: column dt*4+dw of row r is the contribution of input
@@ -444,22 +477,22 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
         // (tiles overlap by 3 rows).  fp32 output is scattered straight into the merged (T,H,W) field,
         // keeping only what merge_data keeps of this chunk.
         __shared__ float xch[2][128][17];
-        float a0[1], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float a0, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int t0, h0, w0, kt, kh, kw;
         p.geom.origin(p.chunk_begin + ri.n, t0, h0, w0);
         p.geom.keep_from(p.chunk_begin + ri.n, kt, kh, kw);
-        const bool keep_hw = ri.valid && row >= 1 && row <= p.row_step && ri.h >= kh && ri.w >= kw;
+        const bool keep_hw = valid && row >= 1 && row <= p.row_step && ri.h >= kh && ri.w >= kw;
         float* dst = p.out_f32 + ((size_t)t0 * p.geom.H + (h0 + ri.h)) * p.geom.W + (w0 + ri.w);
         const size_t plane = (size_t)p.geom.H * p.geom.W;
         const int rm = max(row - 1, 0), rp1 = min(row + 1, 127), rp2 = min(row + 2, 127);
         auto emit = [&](int t, float acc) {
           if (keep_hw && t >= kt) {
             float y = acc + s_bias[0];
-            if (p.relu) y = fmaxf(y, 0.f);
+            if (RELU) y = fmaxf(y, 0.f);
             dst[(size_t)t * plane] = y;
           }
         };
-        for (int t = 0; t < p.in_T; ++t) {
+        for (int t = 0; t < T; ++t) {
           const uint32_t ta = wait_d() - half * kHalf;
           uint32_t v0[8], v1[8];
           umma::tmem_ld8(ta, v0);
@@ -474,67 +507,74 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 #pragma unroll
           for (int dt = 0; dt < 4; ++dt)
             s[dt] = ((x[rm][dt * 4 + 0] + x[row][dt * 4 + 1]) + x[rp1][dt * 4 + 2]) + x[rp2][dt * 4 + 3];
-          a0[0] = s[0];
+          a0 = s[0];
           a1 += s[1];
           a2 += s[2];
           a3 += s[3];
           if (t >= 2) emit(t - 2, a3);
-          a3 = a2; a2 = a1; a1 = a0[0];
+          a3 = a2; a2 = a1; a1 = a0;
         }
-        emit(p.in_T - 2, a3);
-        emit(p.in_T - 1, a2);
+        emit(T - 2, a3);
+        emit(T - 1, a2);
       } else if (MODE == MODE_DOWN) {
-        // t_in = 2*to + dt - 1.  odd t_in: block0 = dt 0 -> plane (t_in+1)/2 (starts it), block1 = dt 2 ->
-        // plane (t_in-1)/2.  even t_in: block0 = dt 1 -> plane t_in/2, block1 = dt 3 -> plane t_in/2 - 1 (done).
-        float aO[kHalf], aN[kHalf];
+        // t_in = 2*to + dt - 1.  Even t_in = 2m: block0 = dt 1 -> plane m, block1 = dt 3 -> plane m-1 (completes).
+        // Odd t_in = 2m+1: block0 = dt 0 -> plane m+1 (starts), block1 = dt 2 -> plane m.
+        // pair(X, Y): X holds plane m-1, Y plane m on entry; on exit Y holds plane m and X plane m+1.
+        float u[kHalf], v[kHalf];
 #pragma unroll
-        for (int c = 0; c < kHalf; ++c) { aO[c] = 0.f; aN[c] = 0.f; }
-        for (int t = 0; t < p.in_T; ++t) {
-          const uint32_t ta = wait_d();
-          float db[2][kHalf];
-          ld_blocks<2>(ta, db);
-          release_d();
-          if (t & 1) {
+        for (int c = 0; c < kHalf; ++c) { u[c] = 0.f; v[c] = bias_r[c]; }
+        auto pair = [&](float (&X)[kHalf], float (&Y)[kHalf], int t) {
+          {
+            const uint32_t ta = wait_d();
+            float db[2][kHalf];
+            ld_blocks<2>(ta, db);
+            release_d();
 #pragma unroll
-            for (int c = 0; c < kHalf; ++c) { aN[c] = db[0][c]; aO[c] += db[1][c]; }
-          } else {
-#pragma unroll
-            for (int c = 0; c < kHalf; ++c) { aN[c] += db[0][c]; aO[c] += db[1][c]; }
+            for (int c = 0; c < kHalf; ++c) { Y[c] += db[0][c]; X[c] += db[1][c]; }
             const int m = t >> 1;
-            if (m >= 1 && ri.valid) store_voxel(p, H16, bias_r, va, m - 1, half, aO, nullptr);
-#pragma unroll
-            for (int c = 0; c < kHalf; ++c) aO[c] = aN[c];
+            if (m >= 1 && valid) store12<H16, RELU, false>(vp.o + (long long)(m - 1) * vp.o_t, vp.o_g, G, half, X, no_skip);
           }
+          if (t + 1 < T) {
+            const uint32_t ta = wait_d();
+            float db[2][kHalf];
+            ld_blocks<2>(ta, db);
+            release_d();
+#pragma unroll
+            for (int c = 0; c < kHalf; ++c) { X[c] = db[0][c] + bias_r[c]; Y[c] += db[1][c]; }
+          }
+        };
+        int t = 0;
+        bool last_in_v = false;     // the last plane is in the Y array of the last pair() call
+        for (; t + 4 <= T; t += 4) { pair(u, v, t); pair(v, u, t + 2); }
+        if (t < T) {
+          pair(u, v, t);
+          last_in_v = true;
+          if (t + 2 < T) { pair(v, u, t + 2); last_in_v = false; }
         }
-        if (ri.valid) store_voxel(p, H16, bias_r, va, p.out_T - 1, half, aO, nullptr);
+        if (valid) {
+          if (last_in_v) store12<H16, RELU, false>(vp.o + (long long)(p.out_T - 1) * vp.o_t, vp.o_g, G, half, v, no_skip);
+          else store12<H16, RELU, false>(vp.o + (long long)(p.out_T - 1) * vp.o_t, vp.o_g, G, half, u, no_skip);
+        }
       } else if (MODE == MODE_UP) {
         // output plane 2*t_in + kt - 1; block kt.  Planes 2t-1 and 2t complete at step t.
         float cX[kHalf], cY[kHalf];
 #pragma unroll
-        for (int c = 0; c < kHalf; ++c) { cX[c] = 0.f; cY[c] = 0.f; }
-        for (int t = 0; t < p.in_T; ++t) {
+        for (int c = 0; c < kHalf; ++c) { cX[c] = 0.f; cY[c] = bias_r[c]; }
+        uint4* op = vp.o - vp.o_t;              // plane 2t-1
+        for (int t = 0; t < T; ++t) {
           const uint32_t ta = wait_d();
           float db[4][kHalf];
-          if (!(p.debug & 2)) {
-            ld_blocks<4>(ta, db);
-          } else {
-#pragma unroll
-            for (int c = 0; c < kHalf; ++c) { db[0][c] = 0.f; db[1][c] = 0.f; db[2][c] = 0.f; db[3][c] = 0.f; }
-          }
+          ld_blocks<4>(ta, db);
           release_d();
 #pragma unroll
           for (int c = 0; c < kHalf; ++c) { cX[c] += db[0][c]; cY[c] += db[1][c]; }
-          const bool st = ri.valid && !(p.debug & 4);
-          if (t >= 1 && st) store_voxel(p, H16, bias_r, va, 2 * t - 1, half, cX, nullptr);
-          if (st) store_voxel(p, H16, bias_r, va, 2 * t, half, cY, nullptr);
-          if (p.debug & 64) {
-            if (t >= 1 && st) store_voxel(p, H16, bias_r, vb, 2 * t - 1, half, cX, nullptr);
-            if (st) store_voxel(p, H16, bias_r, vb, 2 * t, half, cY, nullptr);
-          }
+          if (t >= 1 && valid) store12<H16, RELU, false>(op, vp.o_g, G, half, cX, no_skip);
+          if (valid) store12<H16, RELU, false>(op + vp.o_t, vp.o_g, G, half, cY, no_skip);
+          op += 2 * vp.o_t;
 #pragma unroll
-          for (int c = 0; c < kHalf; ++c) { cX[c] = db[2][c]; cY[c] = db[3][c]; }
+          for (int c = 0; c < kHalf; ++c) { cX[c] = db[2][c] + bias_r[c]; cY[c] = db[3][c] + bias_r[c]; }
         }
-        if (ri.valid) store_voxel(p, H16, bias_r, va, 2 * p.in_T - 1, half, cX, nullptr);
+        if (valid) store12<H16, RELU, false>(op, vp.o_g, G, half, cX, no_skip);
       }
     }
   }
@@ -782,23 +822,42 @@ __global__ void __launch_bounds__(256) gather_wfold_c2k4_kernel(const float* __r
   }
 }
 
-template <int MODE>
-int launch_mode(const lc_codec* h, const SweepParams& p, int grid, int smem, cudaStream_t s) {
+// Resident CTAs per SM: two (the epilogue warps of one CTA cover the MMA / barrier latency of the other; 80
+// registers, half the TMEM columns, 110 KB of stages each) except for the stride-2 mode, whose 74 KB weight
+// image plus two 31 KB parity-split stages need a whole SM.
+// LOSSYCOMP_TC_ONE_PER_SM=<comma list of mode numbers> forces one for more modes (experiments).
+int ctas_per_sm(int mode) {
+  static int one_mask = -1;
+  if (one_mask < 0) {
+    one_mask = 1 << MODE_DOWN;
+    if (const char* e = getenv("LOSSYCOMP_TC_ONE_PER_SM"))
+      for (const char* c = e; *c; ++c)
+        if (*c >= '1' && *c <= '5') one_mask |= 1 << (*c - '0');
+  }
+  return (one_mask >> mode) & 1 ? 1 : 2;
+}
+
+template <int MODE, int H16, int RELU>
+int launch_variant(const SweepParams& p, int grid, int smem, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE, H16, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  (void)h;
-  if (p.half) sweep_tc_kernel<MODE, 1><<<grid, kTcThreads, smem, s>>>(p);
-  else sweep_tc_kernel<MODE, 0><<<grid, kTcThreads, smem, s>>>(p);
+  sweep_tc_kernel<MODE, H16, RELU><<<grid, kTcThreads, smem, s>>>(p);
   return LC_OK;
+}
+
+template <int MODE>
+int launch_mode(const lc_codec* h, const SweepParams& p, int grid, int smem, cudaStream_t s) {
+  (void)h;
+  if (p.half) return p.relu ? launch_variant<MODE, 1, 1>(p, grid, smem, s) : launch_variant<MODE, 1, 0>(p, grid, smem, s);
+  return p.relu ? launch_variant<MODE, 0, 1>(p, grid, smem, s) : launch_variant<MODE, 0, 0>(p, grid, smem, s);
 }
 
 int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStream_t s) {
   const int smem = lp.smem_bytes;
-  const int per_sm = (lp.backend == MODE_K3 || lp.backend == MODE_K4 || lp.backend == MODE_UP) ? 2 : 1;
+  const int per_sm = ctas_per_sm(lp.backend);
   int grid = per_sm * h->num_sms;
   if (grid > p.n_items) grid = p.n_items;
   int rc = LC_OK;
@@ -1027,10 +1086,9 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
   // opt-in: with two issuer warps the smem skip tile showed a rare stale read of plane 0 (under investigation);
   // the prefetched global-load path is 3 % slower and bit-deterministic
-  const bool want_skip_tile = (mode == MODE_K3) && L.res_add && getenv("LOSSYCOMP_SKIP_TILE") != nullptr;
-  p.skip_tile = want_skip_tile ? 1 : 0;
-  const int stage_bytes = p.in_NPG * p.slab_slots * 16 + (want_skip_tile ? 3 * 2048 : 0);
-  const int budget = ((mode == MODE_K3 || mode == MODE_K4 || mode == MODE_UP) ? 110 : 200) * 1024;
+  const int stage_bytes = p.in_NPG * p.slab_slots * 16;
+  // dynamic shared memory per CTA; the single-channel mode also holds a 17.6 KB static exchange tile
+  const int budget = (ctas_per_sm(mode) == 2 ? (mode == MODE_K4_OUT1 ? 90 : 110) : 200) * 1024;
   const int fixed = ((p.wimg_bytes + 127) & ~127) + 256;
   int stages = (budget - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1040,7 +1098,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   }
   p.stages = stages;
   {
-    const bool two_per_sm = (mode == MODE_K3 || mode == MODE_K4 || mode == MODE_UP);
+    const bool two_per_sm = ctas_per_sm(mode) == 2;
     p.tmem_cols = two_per_sm ? 256 : 512;
     p.acc_stride = (p.N + 7) & ~7;
     p.nbuf = p.tmem_cols / p.acc_stride;
@@ -1156,7 +1214,6 @@ static int tc_run(lc_codec* h, int first, int count, const ActView& first_in, vo
       p.in_cs = cur.chunk_stride;
       p.out = out;
       if (L.res_add) p.skip = skip_v;
-      if (p.skip_tile && (!L.res_add || p.skip.PW != p.row_PW || p.skip.G != 3 || p.skip.NP != 1)) p.skip_tile = 0;
       p.n_items = n_chunks * p.tiles_per_chunk * p.n_classes;
       if (lp.backend == MODE_K4_OUT1) {
         p.out_f32 = recon_out;

@@ -27,6 +27,10 @@ LATENT_MAGIC = b"LCL1"
 HUFF_MAGIC = b"LCH1"
 SEG = 1024                      # symbols per independently decodable Huffman segment
 ESC = 255                       # escape symbol of the code stream
+# Revision of the autoencoder kernels' arithmetic (summation order, rounding points).  The error bound only
+# holds when the decoder reproduces the compressor's reconstruction bit for bit, so blobs record the
+# revision they were written with and a build with different arithmetic refuses them.
+NUMERICS_REV = 2
 # chunks per convolution launch: large batches amortise kernel prologues and tails (900 chunks x 19 tiles =
 # 57.8 waves of the 296 resident CTAs); the activation workspace is 19.4 MB per chunk
 DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "1024"))
@@ -497,7 +501,8 @@ class Engine:
 
     def pack_latent(self, latent, codec="raw", staged=None) -> bytes:
         meta = {"precision": self.precision, "model": self.model.arch.name,
-                "filters": self.model.arch.filters, "kernel": self.model.arch.kernel, "codec": codec}
+                "filters": self.model.arch.filters, "kernel": self.model.arch.kernel, "codec": codec,
+                "rev": NUMERICS_REV}
         mj = json.dumps(meta).encode()
         if staged is not None:                      # float32 little-endian, already on the host
             raw = memoryview(staged[0].numpy())[:staged[1]]
@@ -531,6 +536,9 @@ class Engine:
                                 "numerics must match the compressor's, SURVEY.md H2)")
         (lm,) = struct.unpack("<I", blob[4:8])
         meta = json.loads(blob[8:8 + lm])
+        if meta.get("rev", 1) != NUMERICS_REV:
+            raise N.NativeError(f"blob was written by kernel arithmetic revision {meta.get('rev', 1)}, this build is "
+                                f"revision {NUMERICS_REV}: its reconstruction would not be reproduced bit for bit")
         raw = blob[8 + lm:]
         if meta.get("codec") == "bz2":
             raw = bz2.decompress(raw)

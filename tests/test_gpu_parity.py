@@ -337,3 +337,25 @@ def test_verify_modes_give_identical_blobs(eng, torch):
     c, _ = compress_device(eng, x, 0.02, verify=False)
     assert pickle.dumps(a) == pickle.dumps(b) == pickle.dumps(c)
     assert ia["violations"] == ib["violations"] == 0 and ia["max_err"] == ib["max_err"] <= 0.02
+
+
+def test_blob_from_other_kernel_revision_is_refused(eng, torch):
+    """The decoder must reproduce the compressor's reconstruction bit for bit, so a blob written by kernels
+    with different arithmetic (recorded as 'rev' in the latent container) is an error, not a silent bound loss."""
+    import json
+    import struct
+    from lossycomp import _native as N
+    from lossycomp.compress import compress_device
+    from lossycomp.decompress import decompress_device
+    from oracle import lossycomp_oracle as O
+    x = dev(torch, O.synthetic_field(16, 48, 64, seed=2))
+    slots, _ = compress_device(eng, x, 0.05)
+    blob = slots[0]
+    (lm,) = struct.unpack("<I", blob[4:8])
+    meta = json.loads(blob[8:8 + lm])
+    assert "rev" in meta
+    meta["rev"] += 1
+    mj = json.dumps(meta).encode()
+    slots[0] = blob[:4] + struct.pack("<I", len(mj)) + mj + blob[8 + lm:]
+    with pytest.raises(N.NativeError, match="revision"):
+        decompress_device(eng, slots)

@@ -20,8 +20,11 @@ for i in range(3):
 ms, cnt = eng.profile_read()
 print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms))
 ''' % (ROOT, ROOT)
-for dbg, label in [(0, "full"), (32, "UP stores coalesced (wrong place)"), (64, "UP stores both columns"), (4, "no stores")]:
-    env = dict(os.environ, LOSSYCOMP_TC_DEBUG=str(dbg))
+for dbg, label in [(0, "full"), (16, "single issuer"), (1, "no MMA"), (8, "no copies"), (9, "no MMA no copies"),
+                   (103, "K4_OUT1 at 1 CTA/SM"), (105, "UP at 1 CTA/SM")]:
+    env = dict(os.environ, LOSSYCOMP_TC_DEBUG=str(dbg if dbg < 100 else 0))
+    if dbg >= 100:      # 10m: force mode m to one CTA per SM
+        env["LOSSYCOMP_TC_ONE_PER_SM"] = str(dbg - 100)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
     print(f"debug={dbg:2d} {label:28s}", line[0] if line else out.stderr[-300:])
