@@ -223,7 +223,7 @@ __device__ __forceinline__ void store12(uint4* o, long long o_g, int G, int half
 }
 
 template <int MODE, int H16, int RELU>
-__global__ void __launch_bounds__(kTcThreads, MODE == MODE_DOWN ? 1 : 2)
+__global__ void __launch_bounds__(kTcThreads, (MODE == MODE_DOWN || MODE == MODE_UP) ? 1 : 2)
 sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull[kMaxBufs], tempty[kMaxBufs], wbar;
@@ -287,31 +287,37 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       const uint32_t idesc = umma::make_idesc(128, p.N, H16 ? 0 : 1);
       const uint64_t sA_add = (uint64_t)(umma::smem_u32(sA) >> 4), sB_add = (uint64_t)(umma::smem_u32(sB) >> 4);
       int stage = 0, phase = 0, buf = 0, bphase = 0, step = 0;
+      // MODE_UP runs two accumulator sub-steps per input plane (output-column parity 0 / 1, weight variants
+      // 2*ph and 2*ph + 1) on the same stage; every other mode one
+      constexpr int kSub = (MODE == MODE_UP) ? 2 : 1;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int var = 0;
-        if (MODE == MODE_UP) var = ((item % per_chunk) / p.tiles_per_chunk);
-        for (int t = 0; t < p.in_T; ++t, ++step) {
+        if (MODE == MODE_UP) var = 2 * ((item % per_chunk) / p.tiles_per_chunk);
+        for (int t = 0; t < p.in_T; ++t) {
           if (MODE == MODE_DOWN) var = t & 1;
-          const bool mine = (n_issuers == 1) ? (me == 0) : ((step & 1) == me);
-          if (mine) {
-            umma::mbar_wait(&tempty[buf], bphase ^ 1);
-            umma::mbar_wait(&full[stage], phase);
-            umma::tcgen05_fence_after();
-            const uint64_t a_add = sA_add + (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
-            const uint32_t d_addr = tmem + buf * p.acc_stride;
-            const int nks = (p.debug & 1) ? 0 : p.nks;
+#pragma unroll
+          for (int sub = 0; sub < kSub; ++sub, ++step) {
+            const bool mine = (n_issuers == 1) ? (me == 0) : ((step & 1) == me);
+            if (mine) {
+              umma::mbar_wait(&tempty[buf], bphase ^ 1);
+              umma::mbar_wait(&full[stage], phase);
+              umma::tcgen05_fence_after();
+              const uint64_t a_add = sA_add + (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
+              const uint32_t d_addr = tmem + buf * p.acc_stride;
+              const int nks = (p.debug & 1) ? 0 : p.nks;
 #pragma unroll 2
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t a = p.a_desc[var][ks] + a_add, b = p.b_desc[var][ks] + sB_add;
-              if (umma::elect_one()) umma::mma_f16(d_addr, a, b, idesc, ks > 0);
+              for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t a = p.a_desc[var + sub][ks] + a_add, b = p.b_desc[var + sub][ks] + sB_add;
+                if (umma::elect_one()) umma::mma_f16(d_addr, a, b, idesc, ks > 0);
+              }
+              __syncwarp();
+              // one commit per accumulator: it signals the epilogue, which releases the smem stage
+              if (umma::elect_one()) umma::commit(&tfull[buf]);
+              __syncwarp();
             }
-            __syncwarp();
-            // one commit per plane: it signals the epilogue, which releases the smem stage
-            if (umma::elect_one()) umma::commit(&tfull[buf]);
-            __syncwarp();
+            if (++buf == p.nbuf) { buf = 0; bphase ^= 1; }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          if (++buf == p.nbuf) { buf = 0; bphase ^= 1; }
         }
       }
     }
@@ -330,12 +336,14 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 #pragma unroll
     for (int c = 0; c < kHalf; ++c) bias_r[c] = s_bias[half * kHalf + c];
     int ebuf = 0, ephase = 0, estage = 0;
-    auto wait_d = [&]() -> uint32_t {
+    auto wait_d = [&](bool last_of_stage = true) -> uint32_t {
       umma::mbar_wait(&tfull[ebuf], ephase);
       umma::tcgen05_fence_after();
       // the MMAs that read this step's stage are complete: hand the stage back to the producer
-      if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
-      if (++estage == p.stages) estage = 0;
+      if (last_of_stage) {
+        if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
+        if (++estage == p.stages) estage = 0;
+      }
       return lane_addr + ebuf * p.acc_stride;
     };
     auto release_d = [&]() {
@@ -353,8 +361,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       const RowInfo ri = row_info(p, item, row);
       const bool valid = ri.valid;
       VoxPtr vp;
-      if (MODE == MODE_UP) vp = vox_ptr(p, ri.n, 2 * ri.h + (ri.cls >> 1), 2 * ri.w + (ri.cls & 1));
-      else if (MODE != MODE_K4_OUT1) vp = vox_ptr(p, ri.n, ri.h, ri.w);
+      if (MODE != MODE_K4_OUT1 && MODE != MODE_UP) vp = vox_ptr(p, ri.n, ri.h, ri.w);
       const SkipRegs no_skip = {};
       if (MODE == MODE_K3) {
         // block dt -> output plane t_in - dt + 1.  Roles at step t: P = plane t-1 (completes), C = plane t,
@@ -556,25 +563,87 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
           else store12<H16, RELU, false>(vp.o + (long long)(p.out_T - 1) * vp.o_t, vp.o_g, G, half, u, no_skip);
         }
       } else if (MODE == MODE_UP) {
-        // output plane 2*t_in + kt - 1; block kt.  Planes 2t-1 and 2t complete at step t.
-        float cX[kHalf], cY[kHalf];
+        // Row r is input position (h, w); this item's class is the output-line parity ph, and both output-column
+        // parities pw are computed here (two accumulators per plane), so that a warp can write runs of
+        // consecutive output columns: a thread writing every other 16-byte vector leaves half-filled 32-byte
+        // sectors behind, which cost the old one-parity-per-CTA form 1.0 of its 1.3 ms.
+        // Block kt of sub-step (t, pw) belongs to output plane 2t + kt - 1: planes 2t-1 and 2t complete at step t.
+        // Lane L stores what lane 16k + L/2 computed for pw = L & 1 (k = 0, 1): 32 consecutive columns per store.
+        const int odd = lane & 1;
+        uint4* ob[2];
+        bool vs[2];
 #pragma unroll
-        for (int c = 0; c < kHalf; ++c) { cX[c] = 0.f; cY[c] = bias_r[c]; }
-        uint4* op = vp.o - vp.o_t;              // plane 2t-1
-        for (int t = 0; t < T; ++t) {
-          const uint32_t ta = wait_d();
-          float db[4][kHalf];
-          ld_blocks<4>(ta, db);
-          release_d();
-#pragma unroll
-          for (int c = 0; c < kHalf; ++c) { cX[c] += db[0][c]; cY[c] += db[1][c]; }
-          if (t >= 1 && valid) store12<H16, RELU, false>(op, vp.o_g, G, half, cX, no_skip);
-          if (valid) store12<H16, RELU, false>(op + vp.o_t, vp.o_g, G, half, cY, no_skip);
-          op += 2 * vp.o_t;
-#pragma unroll
-          for (int c = 0; c < kHalf; ++c) { cX[c] = db[2][c] + bias_r[c]; cY[c] = db[3][c] + bias_r[c]; }
+        for (int k = 0; k < 2; ++k) {
+          const RowInfo rs = row_info(p, item, q * 32 + 16 * k + (lane >> 1));
+          vs[k] = rs.valid;
+          const VoxPtr v = vox_ptr(p, rs.n, 2 * rs.h + rs.cls, 2 * rs.w + odd);
+          ob[k] = v.o - v.o_t;                  // plane 2t-1
+          vp = v;
         }
-        if (valid) store12<H16, RELU, false>(op, vp.o_g, G, half, cX, no_skip);
+        float cX[2][kHalf], cY[2][kHalf];
+#pragma unroll
+        for (int c = 0; c < kHalf; ++c) { cX[0][c] = cX[1][c] = 0.f; cY[0][c] = cY[1][c] = bias_r[c]; }
+        auto pack6 = [&](const float (&y)[kHalf], unsigned (&o)[6]) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) o[i] = pack2_t<H16, RELU>(y[2 * i], y[2 * i + 1]);
+        };
+        // the six packed registers of 12 channels: half 0 = vector g0 + low 8 bytes of g1, half 1 = high 8 bytes
+        // of g1 + vector g2
+        auto store6 = [&](uint4* o, const unsigned (&v)[6]) {
+          if (half == 0) {
+            o[0] = make_uint4(v[0], v[1], v[2], v[3]);
+            if (G > 1) *reinterpret_cast<uint2*>(o + vp.o_g) = make_uint2(v[4], v[5]);
+          } else {
+            if (G > 1) *(reinterpret_cast<uint2*>(o + vp.o_g) + 1) = make_uint2(v[0], v[1]);
+            if (G > 2) o[2 * vp.o_g] = make_uint4(v[2], v[3], v[4], v[5]);
+          }
+        };
+        auto store_transposed = [&](const unsigned (&P0)[6], const unsigned (&P1)[6], long long plane_off, bool on) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int src = 16 * k + (lane >> 1);
+            unsigned v[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const unsigned x0 = __shfl_sync(0xffffffffu, P0[i], src);
+              const unsigned x1 = __shfl_sync(0xffffffffu, P1[i], src);
+              v[i] = odd ? x1 : x0;
+            }
+            if (on && vs[k]) store6(ob[k] + plane_off, v);
+          }
+        };
+        for (int t = 0; t < T; ++t) {
+          unsigned PX[2][6], PY[2][6];
+#pragma unroll
+          for (int pw = 0; pw < 2; ++pw) {
+            const uint32_t ta = wait_d(pw == 1);
+            {
+              float db[2][kHalf];
+              ld_blocks<2>(ta, db);
+#pragma unroll
+              for (int c = 0; c < kHalf; ++c) { db[0][c] += cX[pw][c]; db[1][c] += cY[pw][c]; }
+              pack6(db[0], PX[pw]);
+              pack6(db[1], PY[pw]);
+            }
+            {
+              float db[2][kHalf];
+              ld_blocks<2>(ta + 48, db);
+              release_d();
+#pragma unroll
+              for (int c = 0; c < kHalf; ++c) { cX[pw][c] = db[0][c] + bias_r[c]; cY[pw][c] = db[1][c] + bias_r[c]; }
+            }
+          }
+          store_transposed(PX[0], PX[1], 0, t >= 1);
+          store_transposed(PY[0], PY[1], vp.o_t, true);
+          ob[0] += 2 * vp.o_t;
+          ob[1] += 2 * vp.o_t;
+        }
+        {
+          unsigned PX[2][6];
+          pack6(cX[0], PX[0]);
+          pack6(cX[1], PX[1]);
+          store_transposed(PX[0], PX[1], 0, true);
+        }
       }
     }
   }
@@ -824,12 +893,13 @@ __global__ void __launch_bounds__(256) gather_wfold_c2k4_kernel(const float* __r
 
 // Resident CTAs per SM: two (the epilogue warps of one CTA cover the MMA / barrier latency of the other; 80
 // registers, half the TMEM columns, 110 KB of stages each) except for the stride-2 mode, whose 74 KB weight
-// image plus two 31 KB parity-split stages need a whole SM.
+// image plus two 31 KB parity-split stages need a whole SM, and the transposed mode, whose epilogue keeps
+// the accumulators of both output-column parities in registers.
 // LOSSYCOMP_TC_ONE_PER_SM=<comma list of mode numbers> forces one for more modes (experiments).
 int ctas_per_sm(int mode) {
   static int one_mask = -1;
   if (one_mask < 0) {
-    one_mask = 1 << MODE_DOWN;
+    one_mask = (1 << MODE_DOWN) | (1 << MODE_UP);
     if (const char* e = getenv("LOSSYCOMP_TC_ONE_PER_SM"))
       for (const char* c = e; *c; ++c)
         if (*c >= '1' && *c <= '5') one_mask |= 1 << (*c - '0');
@@ -978,12 +1048,12 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     }
     p.N = 48;
   } else if (mode == MODE_UP) {
-    // plain input at input resolution; one variant per output parity class (ph, pw):
+    // plain input at input resolution; one weight variant per output parity class cls = 2*ph + pw:
     // p=0: (k=1, i=j), (k=3, i=j-1);  p=1: (k=2, i=j), (k=0, i=j+1)
     p.row_PW = tin.PW; p.row0 = tin.PW; p.row_off_h = 1; p.row_off_w = 1;
     p.rows_H = L.in_h; p.rows_W = L.in_w;
     p.tiles_per_chunk = (L.in_h * tin.PW + 127) / 128;
-    p.n_classes = 4;
+    p.n_classes = 2;                      // output-line parity; both column parities run in the same CTA
     p.slab_start = -(tin.PW + 1);
     p.slab_slots = 128 + 2 * (tin.PW + 1);
     groups.resize(4);
