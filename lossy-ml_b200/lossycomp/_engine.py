@@ -40,6 +40,25 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_PyBytes_New = C.pythonapi.PyBytes_FromStringAndSize
+_PyBytes_New.restype = C.py_object
+_PyBytes_New.argtypes = [C.c_void_p, C.c_ssize_t]
+_PyBytes_Data = C.pythonapi.PyBytes_AsString
+_PyBytes_Data.restype = C.c_void_p
+_PyBytes_Data.argtypes = [C.py_object]
+
+
+def _new_bytes(n: int):
+    """An uninitialised bytes object of n bytes plus a writable uint8 view of it.  The C API allows filling a
+    bytes object created with a NULL source before anything else sees it; the containers are built that way so
+    that multi-megabyte payloads are written once, by the device->host copy itself."""
+    obj = _PyBytes_New(None, n)
+    if n == 0:
+        return obj, np.zeros(0, dtype=np.uint8)
+    view = np.ctypeslib.as_array((C.c_ubyte * n).from_address(_PyBytes_Data(obj)))
+    return obj, view
+
+
 class Engine:
     """One codec instance per (device, model, precision); replaces the per-call Keras build +
     load_weights of compress.py:41-57 / decompress.py:33-48 by a one-time weight upload."""
@@ -408,8 +427,9 @@ class Engine:
             self._small["pin_" + name] = b
         return b
 
-    def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str):
-        """Enqueue the Huffman packing of `sym` and the device->pinned-host copies; no sync."""
+    def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str, extra: dict, tail_len: int = 0):
+        """Enqueue the Huffman packing of `sym` (no sync) and allocate the finished 'LCH1' container as one
+        uninitialised bytes object: everything but the segment lengths, the payload and the tail is known now."""
         t = self.torch
         n = sym.numel()
         nseg = (n + SEG - 1) // SEG
@@ -425,23 +445,38 @@ class Engine:
                 "lc_huff_encode")
         self.launches += 1
         nbytes = (bits + 7) // 8
-        h_out = self._pinned("pay_" + tag, nbytes)
         h_seg = self._pinned("seg_" + tag, 8 * (nseg + 1))
-        h_out[:nbytes].copy_(out[:nbytes], non_blocking=True)
         h_seg[:8 * (nseg + 1)].copy_(segb[:nseg + 1].view(t.uint8), non_blocking=True)
-        return dict(n=n, nseg=nseg, bits=bits, nbytes=nbytes, h_out=h_out, h_seg=h_seg, table=table, keep=(out, segb, d_tab))
+        meta = dict(extra, n=int(n), seg=SEG, bits=int(bits), ref_tree=bool(table.reference_tree))
+        mj = json.dumps(meta).encode()
+        tb = table.to_bytes()
+        head = b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), nseg), mj, tb])
+        pay_off = len(head) + 2 * nseg
+        blob, view = _new_bytes(pay_off + nbytes + tail_len)
+        view[:len(head)] = np.frombuffer(head, dtype=np.uint8)
+        return dict(nseg=nseg, bits=bits, nbytes=nbytes, h_seg=h_seg, head_len=len(head), pay_off=pay_off, blob=blob,
+                    view=view, out=out, keep=(segb, d_tab))
 
-    def _finish_pack(self, job, extra: dict, tail: bytes = b"") -> bytes:
-        """After the sync: assemble the 'LCH1' container with a single copy of the payload."""
+    def _collect_pack(self, job):
+        """Copy the packed payload from the device straight into its place in the container (blocking)."""
+        n = job["nbytes"]
+        if n:
+            dst = self.torch.from_numpy(job["view"][job["pay_off"]:job["pay_off"] + n])
+            dst.copy_(job["out"][:n])
+
+    def _finish_pack(self, job, tail: bytes = b"") -> bytes:
+        """After the stream sync: fill in the segment lengths and the tail; returns the container."""
         nseg, bits = job["nseg"], job["bits"]
         offs = np.frombuffer(job["h_seg"].numpy(), dtype=np.int64, count=nseg + 1)
         assert int(offs[nseg]) == bits
-        lens = np.diff(offs[:nseg + 1]).astype(np.uint16) if nseg else np.zeros(0, np.uint16)   # <= 1024*32 bits
-        meta = dict(extra, n=int(job["n"]), seg=SEG, bits=int(bits), ref_tree=bool(job["table"].reference_tree))
-        mj = json.dumps(meta).encode()
-        tb = job["table"].to_bytes()
-        return b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), lens.size), mj, tb, lens.tobytes(),
-                         memoryview(job["h_out"].numpy())[:job["nbytes"]], tail])
+        if nseg:
+            lens = np.diff(offs[:nseg + 1]).astype("<u2")                                           # <= 1024*32 bits
+            job["view"][job["head_len"]:job["pay_off"]] = lens.view(np.uint8)
+        if tail:
+            job["view"][job["pay_off"] + job["nbytes"]:] = np.frombuffer(tail, dtype=np.uint8)
+        blob = job["blob"]
+        job.clear()
+        return blob
 
     def pack_streams(self, mask, q):
         """Entropy-code the mask and the code stream together -> (comp_error, comp_mask).
@@ -476,17 +511,20 @@ class Engine:
         N.check(self.lib.lc_symbolize_i32(_ptr(q), n_q, diff, bias, ESC, _ptr(sym_q), _ptr(esc), _ptr(nesc),
                                           _ptr(ws), self._stream()), "lc_symbolize_i32")
         self.launches += 1
-        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m")
-        job_q = self._launch_pack(sym_q, tabs_q[pick], tabs_q[pick].encoded_bits(hists_q[pick]), "q")
+        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", {"kind": "mask5", "n_mask": int(n_m)})
+        job_q = self._launch_pack(sym_q, tabs_q[pick], tabs_q[pick].encoded_bits(hists_q[pick]), "q",
+                                  {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne}, tail_len=4 * ne)
         h_esc = None
         if ne:
             h_esc = self._pinned("esc", 4 * ne)
             h_esc[:4 * ne].copy_(esc[:ne].view(t.uint8), non_blocking=True)
+        # the payloads land directly inside the returned bytes objects: no staging copy, no join
+        self._collect_pack(job_m)
+        self._collect_pack(job_q)
         self.torch.cuda.current_stream(self.dev).synchronize()                    # sync 2
         escb = bytes(memoryview(h_esc.numpy())[:4 * ne]) if ne else b""
-        comp_mask = self._finish_pack(job_m, {"kind": "mask5", "n_mask": int(n_m)})
-        comp_error = self._finish_pack(job_q, {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne},
-                                       tail=escb)
+        comp_mask = self._finish_pack(job_m)
+        comp_error = self._finish_pack(job_q, tail=escb)
         return comp_error, comp_mask
 
     # -- latent slot (compress.py:142-144; fpzip is replaced by a tagged container) -----

@@ -15,7 +15,11 @@ for i in range(3):
     slots, info = compress_device(eng, x, 0.1, timing=True)
 print({k: round(v, 2) for k, v in info["timing_ms"].items()}, "total", round(sum(info["timing_ms"].values()), 2))
 import cProfile, pstats
+for i in range(3):
+    compress_device(eng, x, 0.1)
 pr = cProfile.Profile(); pr.enable()
-slots, info = compress_device(eng, x, 0.1)
+for i in range(5):
+    slots, info = compress_device(eng, x, 0.1)
 torch.cuda.synchronize(); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+print("per-call ms = listed seconds * 200")
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
