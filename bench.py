@@ -35,7 +35,7 @@ ABS_ERR = 0.1
 FIELD = (24, 720, 1440)          # configs[1] of BASELINE.json
 CPU_SAMPLE = (24, 336, 720)      # bounded sample of the same field for the CPU legs (~10-20 s)
 # DRAM bytes per chunk per launch of the dominant kernel, from the ncu --set full capture under profiles/
-NCU_DRAM_BYTES_PER_CHUNK = {"sweep_tc_kernel<K3>": 4.13e6}   # mean of its 4 layers: 3.05 MB (plain), 5.2 MB (with skip)
+NCU_DRAM_BYTES_PER_CHUNK = {"sweep_tc_kernel<K3>": 4.16e6}   # mean of its 4 layers: 3.08 MB (plain), 5.24 MB (with skip)
 
 
 def parse():

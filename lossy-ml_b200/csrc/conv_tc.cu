@@ -60,6 +60,10 @@ struct SweepParams {
   int slab_slots, slab_start;    // the stage holds slots [row0 + 128*j + slab_start, +slab_slots) of every plane
   int stages;
   int nbuf, acc_stride, tmem_cols;   // TMEM accumulator ring
+  // MODE_K3 residual add done by the tensor core: the skip tile of plane t rides in stage t as skip.G extra K groups
+  // multiplied by identity weights in the centre time block (skip_slots vectors per group, the first skip_pad of
+  // them alignment padding); 0 = the epilogue adds the skip from global memory
+  int skip_mma, skip_slots, skip_pad;
   // MMA
   int N, nks, nvar;
   const uint4* wimg;
@@ -234,7 +238,8 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
   // issuer's descriptor arithmetic stays in uniform registers
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int slab_bytes = p.slab_slots * 16;
-  const int stage_bytes = p.in_NPG * slab_bytes;
+  const int skip_bytes = p.skip_mma ? p.skip.G * p.skip_slots * 16 : 0;
+  const int stage_bytes = p.in_NPG * slab_bytes + skip_bytes;
   uint8_t* sB = smem;
   uint8_t* sA = smem + ((p.wimg_bytes + 127) & ~127);
   if (threadIdx.x == 0) {
@@ -269,6 +274,13 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
             umma::bulk_g2s(sA + stage * stage_bytes + g * slab_bytes,
                            p.in + slab0 + (long long)(t * p.in_NPG + g) * p.in_S, (uint32_t)slab_bytes,
                            &full[stage]);
+          if (p.skip_mma) {   // rows of this tile of skip plane t (same row numbering as the input planes)
+            const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride +
+                              p.skip.GL + p.row0 + tile * 128 - p.skip_pad;
+            for (int g = 0; g < p.skip.G; ++g)
+              umma::bulk_g2s(sA + stage * stage_bytes + p.in_NPG * slab_bytes + g * p.skip_slots * 16,
+                             sk + (long long)(t * p.skip.G + g) * p.skip.S, (uint32_t)(p.skip_slots * 16), &full[stage]);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -427,7 +439,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
             finish(a2);
           }
         };
-        if (vp.s != nullptr) run(std::true_type{}); else run(std::false_type{});
+        if (vp.s != nullptr && !p.skip_mma) run(std::true_type{}); else run(std::false_type{});
       } else if (MODE == MODE_K4) {
         // k=4, pad 1/2: block dt -> output plane t_in - dt + 1.  Roles at step t: A3 = plane t-2 (completes),
         // A2 = t-1, A1 = t, A0 = t+1 (starts).
@@ -856,16 +868,19 @@ __global__ void gather_wfold_kernel(const float* __restrict__ x, ChunkGeom g, in
 }
 
 // fast path of gather_wfold_kernel for the shipped models' input (C = 2, k = 4, one group): one thread per
-// voxel, four 8-byte loads (neighbours overlap in L1), one 16-byte store
+// run of four voxels along w -- seven 8-byte loads and seven IEEE divisions feed four 16-byte stores (one
+// thread per voxel standardised every input four times and was bound by the divisions)
 __global__ void __launch_bounds__(256) gather_wfold_c2k4_kernel(const float* __restrict__ x, ChunkGeom g, float mean,
                                                                 float stdv, int chunk_begin, int n_chunks, ActView out,
                                                                 int pad_lo) {
-  const long long total = (long long)n_chunks * CT * CH * CW;
+  constexpr int kRun = 4;
+  static_assert(CW % kRun == 0, "chunk width must be a multiple of the run length");
+  const long long total = (long long)n_chunks * CT * CH * (CW / kRun);
   uint4* o = reinterpret_cast<uint4*>(out.base);
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
        v += (long long)gridDim.x * blockDim.x) {
-    const int lw = (int)(v % CW);
-    const int r1 = (int)(v / CW);
+    const int lw0 = (int)(v % (CW / kRun)) * kRun;
+    const int r1 = (int)(v / (CW / kRun));
     const int lh = r1 % CH;
     const int r2 = r1 / CH;
     const int lt = r2 % CT;
@@ -873,21 +888,26 @@ __global__ void __launch_bounds__(256) gather_wfold_c2k4_kernel(const float* __r
     int t0, h0, w0;
     g.origin(chunk_begin + chunk, t0, h0, w0);
     const float2* line = reinterpret_cast<const float2*>(x) + ((size_t)(t0 + lt) * g.H + (h0 + lh)) * g.W + w0;
-    float f[8];
+    float2 in[kRun + 3];
 #pragma unroll
-    for (int dw = 0; dw < 4; ++dw) {
-      const int w = lw + dw - pad_lo;
+    for (int j = 0; j < kRun + 3; ++j) {
+      const int w = lw0 + j - pad_lo;
       float2 val = make_float2(0.f, 0.f);
       if (w >= 0 && w < CW) {
         val = __ldg(line + w);
         val.x = __fdiv_rn(__fsub_rn(val.x, mean), stdv);
       }
-      f[2 * dw] = val.x;
-      f[2 * dw + 1] = val.y;
+      in[j] = val;
     }
     const long long idx = (long long)chunk * out.chunk_stride + (long long)lt * out.S + out.GL +
-                          (lh + pad_lo) * out.PW + lw;
-    o[idx] = pack8(f, out.half);
+                          (lh + pad_lo) * out.PW + lw0;
+#pragma unroll
+    for (int r = 0; r < kRun; ++r) {
+      float f[8];
+#pragma unroll
+      for (int dw = 0; dw < 4; ++dw) { f[2 * dw] = in[r + dw].x; f[2 * dw + 1] = in[r + dw].y; }
+      o[idx + r] = pack8(f, out.half);
+    }
   }
 }
 
@@ -968,7 +988,7 @@ struct KGroup {
 
 // Build the per-layer SweepParams template: geometry, K-step tables and the weight image.
 static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan& tin, const TensorPlan& tout,
-                       const std::vector<float>& w16, int half) {
+                       const TensorPlan* tskip, const std::vector<float>& w16, int half) {
   DevLayer& L = h->layers[i];
   LayerPlan& lp = P->layer[i];
   SweepParams& p = lp.sp;
@@ -998,6 +1018,17 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     block_kt.resize(1);
     for (int dt = 0; dt < k; ++dt) block_kt[0].push_back(dt);
     p.N = 80;
+    // Residual add on the tensor core: three more K groups (the 27 tap groups leave half a K step unused anyway:
+    // 30 groups = 15 MMAs instead of 14) read the skip tile with identity weights, which removes the skip loads,
+    // 12 conversions and 12 adds per voxel from the issue-bound epilogue.  Needs the skip tensor in the input's
+    // row numbering.
+    if (L.res_add && tskip && tskip->fmt == FMT_GP16 && tskip->layout == LAYOUT_PLAIN && tskip->PW == tin.PW &&
+        tskip->G == G && !getenv("LOSSYCOMP_NO_SKIP_MMA")) {
+      p.skip_mma = 1;
+      p.skip_pad = (tskip->GL + p.row0) % 8;
+      p.skip_slots = (128 + p.skip_pad + 7) & ~7;
+      for (int g = 0; g < G; ++g) groups[0].push_back({0, -1 - g, 0, -1, -1, g * 8});
+    }
   } else if (mode == MODE_K4_OUT1) {
     // plain input; taps dh only (dt and dw are folded into N = 4x4); tiles advance by 125 rows
     p.row_PW = tin.PW; p.row0 = tin.PW; p.row_off_h = 1; p.row_off_w = 1;
@@ -1080,7 +1111,10 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     p.slab_start -= pad;
     p.slab_slots = (p.slab_slots + pad + 7) & ~7;
     for (auto& gv : groups)
-      for (auto& kg : gv) kg.a_addr = (uint32_t)((kg.plane * p.slab_slots + kg.off_slots + pad) * 16);
+      for (auto& kg : gv) {
+        if (kg.plane >= 0) kg.a_addr = (uint32_t)((kg.plane * p.slab_slots + kg.off_slots + pad) * 16);
+        else kg.a_addr = (uint32_t)((p.in_NPG * p.slab_slots + (-1 - kg.plane) * p.skip_slots + p.skip_pad) * 16);
+      }
   }
   {   // every bulk copy must stay inside its own plane (guards included)
     const int first = tin.GL + p.row0 - p.row_shift + p.slab_start;
@@ -1091,10 +1125,18 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     }
     for (auto& gv : groups)
       for (auto& kg : gv)
-        if (kg.off_slots < 0 || (int)(kg.a_addr / 16) - kg.plane * p.slab_slots + 128 > p.slab_slots) {
+        if (kg.plane >= 0 && (kg.off_slots < 0 || (int)(kg.a_addr / 16) - kg.plane * p.slab_slots + 128 > p.slab_slots)) {
           lc_set_error("layer %d: operand view leaves its slab", i);
           return LC_EINVAL;
         }
+  }
+  if (p.skip_mma) {
+    const int first = tskip->GL + p.row0 - p.skip_pad;
+    const int last = first + (p.tiles_per_chunk - 1) * 128 + p.skip_slots;
+    if (first < 0 || last > tskip->S) {
+      lc_set_error("layer %d: skip tiles [%d, %d) leave the skip plane of %d vectors", i, first, last, tskip->S);
+      return LC_EINVAL;
+    }
   }
   p.nvar = (int)groups.size();
   const int ngroups = (int)groups[0].size();
@@ -1134,6 +1176,11 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
         if (mode == MODE_K4_OUT1) { kw_fold = co; co = 0; }      // column = dt*4 + dw, single output channel
         if (blk >= (int)block_kt[var].size() || co >= cout) continue;
         const int kt = block_kt[var][blk];
+        if (kg.plane < 0) {   // skip group: identity into the centre time block (output plane = input plane)
+          if (kt == L.pad_lo && co >= kg.ci0 && co < kg.ci0 + 8)
+            img[var * var_elems + ((size_t)gi * p.N + n) * 8 + (co - kg.ci0)] = to_h16_host(1.0f, half);
+          continue;
+        }
         for (int k8 = 0; k8 < 8; ++k8) {
           int kh = kg.tap_h, kw = kg.tap_w, ci = kg.ci0 + k8;
           if (mode == MODE_K4) {   // pseudo-channel -> (dw, ci)
@@ -1156,7 +1203,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
   // opt-in: with two issuer warps the smem skip tile showed a rare stale read of plane 0 (under investigation);
   // the prefetched global-load path is 3 % slower and bit-deterministic
-  const int stage_bytes = p.in_NPG * p.slab_slots * 16;
+  const int stage_bytes = p.in_NPG * p.slab_slots * 16 + (p.skip_mma ? G * p.skip_slots * 16 : 0);
   // dynamic shared memory per CTA; the single-channel mode also holds a 17.6 KB static exchange tile
   const int budget = (ctas_per_sm(mode) == 2 ? (mode == MODE_K4_OUT1 ? 90 : 110) : 200) * 1024;
   const int fixed = ((p.wimg_bytes + 127) & ~127) + 256;
@@ -1220,6 +1267,7 @@ int tc_prepare(lc_codec* h) {
   }
   P->block_vecs = (off + 63) & ~63LL;
 
+  int skip_src = -1;      // layer whose output the next residual add reads
   for (int i = 0; i < nl; ++i) {
     DevLayer& L = h->layers[i];
     LayerPlan& lp = P->layer[i];
@@ -1232,9 +1280,11 @@ int tc_prepare(lc_codec* h) {
     lp.backend = 0;
     if (mode[i]) {
       const TensorPlan& tin = (i == 0) ? P->in_enc : P->out[i - 1];
-      int rc = build_sweep(h, P, i, mode[i], tin, P->out[i], w16, half);
+      int rc = build_sweep(h, P, i, mode[i], tin, P->out[i], (L.res_add && skip_src >= 0) ? &P->out[skip_src] : nullptr,
+                           w16, half);
       if (rc != LC_OK) return rc;
     }
+    if (L.res_save) skip_src = i;
   }
   return LC_OK;
 }

@@ -159,9 +159,9 @@ unsymbolize_kernel(const uint8_t* __restrict__ sym, long long n, int bias, int e
 }
 
 // ---------------------------------------------------------------- Huffman pack
-// one tile = 256 threads x 16 consecutive symbols = 4 independently decodable segments of kSeg symbols
+// one tile = kThreads threads x 16 consecutive symbols = kThreads/64 independently decodable segments of kSeg symbols
 constexpr int kSegItems = 16;
-constexpr int kTileSyms = kThreads * kSegItems;   // 4096
+constexpr int kTileSyms = kThreads * kSegItems;
 constexpr int kSeg = 1024;                        // symbols per segment (64 threads)
 constexpr int kSegPerTile = kTileSyms / kSeg;
 
@@ -172,8 +172,10 @@ huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t*
                    unsigned long long* ws) {
   __shared__ uint32_t s_code[256];
   __shared__ uint8_t s_len[256];
-  s_code[threadIdx.x] = code[threadIdx.x];
-  s_len[threadIdx.x] = len[threadIdx.x];
+  if (threadIdx.x < 256) {
+    s_code[threadIdx.x] = code[threadIdx.x];
+    s_len[threadIdx.x] = len[threadIdx.x];
+  }
   const int tile = take_ticket(ws);   // contains a __syncthreads
   const long long i0 = (long long)tile * kTileSyms + (long long)threadIdx.x * kSegItems;
   uint8_t s[kSegItems];

@@ -120,13 +120,19 @@ quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ re
       if (worst > 0.0) atomicMax(count + 2, (unsigned long long)__double_as_longlong(worst));
     }
   }
+  // compaction through shared memory: the tile's outliers are gathered in C order and written out as one
+  // coalesced run (per-thread 4-byte stores would touch every 32-byte sector several times, each a partial write)
+  __shared__ int32_t s_q[kTile];
   int total;
   const int texcl = block_exclusive<int>(cnt, total);
-  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
-  long long o = (long long)base + texcl;
+  {
+    int o = texcl;
 #pragma unroll
-  for (int k = 0; k < kItems; ++k)
-    if (m[k] != 0) qout[o++] = q[k];
+    for (int k = 0; k < kItems; ++k)
+      if (m[k] != 0) s_q[o++] = q[k];
+  }
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);   // contains a __syncthreads
+  for (int i = threadIdx.x; i < total; i += kThreads) qout[base + i] = s_q[i];
   if ((long long)(tile + 1) * kTile >= n && threadIdx.x == 0) *count = base + (unsigned long long)total;
 }
 
