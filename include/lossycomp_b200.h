@@ -169,6 +169,16 @@ int lc_unsymbolize_i32(const uint8_t* d_sym, int64_t n, int diff, int bias, int 
 int lc_pack_trits(const int8_t* d_mask, int64_t n, uint8_t* d_sym, void* stream);
 int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* stream);
 
+/* Zero-run tokens for sparse masks (large abs_error): a Huffman code cannot spend less than one bit per symbol,
+ * so runs of zero bytes are folded into the alphabet: tokens 0..242 are literal bytes (0 = one zero byte),
+ * 243+k = 2^(k+1) zero bytes (k = 0..4).  Runs do not cross 32-byte segments and are decomposed largest power of
+ * two first.  lc_rle_tokens writes the tokens (at most n), their count and their 256-bin histogram;
+ * lc_rle_expand is the inverse (d_sym: n bytes).  d_ws: lc_rle_workspace_bytes(n). */
+size_t lc_rle_workspace_bytes(int64_t n);
+int lc_rle_tokens(const uint8_t* d_sym, int64_t n, uint8_t* d_tok, unsigned long long* d_n_tok, uint32_t* d_hist,
+                  void* d_ws, void* stream);
+int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, uint8_t* d_sym, int64_t n, void* d_ws, void* stream);
+
 /* Huffman bit packing from a host-built table: code[s] (right-aligned, MSB of the code is
  * emitted first) and len[s] (0..32).  The stream is cut into segments of `seg` (= 1024) symbols; each
  * segment starts at the bit offset d_seg_bits[i] (uint64, exclusive scan written by the call),

@@ -103,6 +103,113 @@ __global__ void unpack_trits_kernel(const uint8_t* __restrict__ in, long long n,
   }
 }
 
+// ---------------------------------------------------------------- zero-run tokens
+// A Huffman code spends at least one bit per symbol, so a mask whose 5-trit bytes are almost all zero (large
+// abs_error) cannot go below n/40 bytes however small its entropy is.  Runs of zero bytes are therefore folded
+// into the alphabet itself: bytes 0..242 are literals (0 = a single zero byte) and 243+k stands for 2^(k+1) zero
+// bytes (k = 0..4).  Runs are confined to the 32 bytes one thread owns and are decomposed greedily, largest power
+// of two first, so tokenising is thread-local bit arithmetic; the token stream stays a byte stream for the same
+// Huffman packer.  Whether a mask is coded plain or tokenised is decided from the two histograms.
+constexpr int kRleSeg = 32;                        // bytes per thread = longest run
+constexpr int kRleTile = kThreads * kRleSeg;       // 8192 bytes per block
+constexpr int kRleFirst = 243;                     // first run symbol (2 zero bytes)
+
+__global__ void __launch_bounds__(kThreads)
+rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, uint8_t* __restrict__ tok,
+                  unsigned long long* __restrict__ n_tok, uint32_t* __restrict__ hist, unsigned long long* ws) {
+  __shared__ uint8_t s_tok[kRleTile];
+  __shared__ uint32_t s_hist[256];
+  if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+  const int tile = take_ticket(ws);   // contains a __syncthreads
+  const long long i0 = (long long)tile * kRleTile + (long long)threadIdx.x * kRleSeg;
+  uint8_t b[kRleSeg];
+  int len = 0;                         // valid bytes of this thread's segment
+  if (i0 + kRleSeg <= n && (reinterpret_cast<uintptr_t>(sym) & 15) == 0) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(sym + i0), v1 = *reinterpret_cast<const uint4*>(sym + i0 + 16);
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int k = 0; k < kRleSeg; ++k) b[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
+    len = kRleSeg;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kRleSeg; ++k) b[k] = (i0 + k < n) ? sym[i0 + k] : 1;   // padding is "non-zero": never in a run
+    len = (i0 < n) ? (int)((n - i0 < kRleSeg) ? (n - i0) : kRleSeg) : 0;
+  }
+  unsigned nz = 0;                     // bit k: byte k is not part of a zero run
+#pragma unroll
+  for (int k = 0; k < kRleSeg; ++k) nz |= (unsigned)(b[k] != 0 || k >= len) << k;
+  // token starts: every literal, and inside a zero run [s, s+R) the offsets j with j = R with its low bits cleared
+  unsigned start = 0;
+  uint8_t val[kRleSeg];
+#pragma unroll
+  for (int k = 0; k < kRleSeg; ++k) {
+    val[k] = b[k];
+    if (k < len) {
+      if ((nz >> k) & 1u) {
+        start |= 1u << k;
+      } else {
+        const unsigned below = nz & ((1u << k) - 1u);
+        const int s0 = below ? (32 - __clz(below)) : 0;
+        const unsigned above = (k == 31) ? 0u : (nz >> (k + 1)) << (k + 1);
+        const int e = above ? (__ffs(above) - 1) : kRleSeg;
+        const int j = k - s0, R = e - s0;
+        const int hb = 31 - __clz((unsigned)(R ^ j));       // R > j, so R ^ j != 0
+        if ((j & ((2 << hb) - 1)) == 0) {
+          start |= 1u << k;
+          val[k] = hb ? (uint8_t)(kRleFirst - 1 + hb) : (uint8_t)0;
+        }
+      }
+    }
+  }
+  const int cnt = __popc(start);
+  int total;
+  const int texcl = block_exclusive<int>(cnt, total);
+  {
+    int o = texcl;
+#pragma unroll
+    for (int k = 0; k < kRleSeg; ++k)
+      if ((start >> k) & 1u) {
+        s_tok[o++] = val[k];
+        atomicAdd(&s_hist[val[k]], 1u);
+      }
+  }
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);   // contains a __syncthreads
+  for (int i = threadIdx.x; i < total; i += kThreads) tok[base + i] = s_tok[i];
+  if (threadIdx.x < 256 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+  if ((long long)(tile + 1) * kRleTile >= n && threadIdx.x == 0) *n_tok = base + (unsigned long long)total;
+}
+
+// tokens -> bytes: exclusive scan of the token lengths gives every literal its position; the output was zero-filled
+constexpr int kExpItems = 16;
+__global__ void __launch_bounds__(kThreads)
+rle_expand_kernel(const uint8_t* __restrict__ tok, long long n_tok, uint8_t* __restrict__ out, long long n_out,
+                  unsigned long long* ws) {
+  const int tile = take_ticket(ws);
+  const long long i0 = (long long)tile * (kThreads * kExpItems) + (long long)threadIdx.x * kExpItems;
+  uint8_t t[kExpItems];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < kExpItems; ++k) {
+    t[k] = (i0 + k < n_tok) ? tok[i0 + k] : 0;
+    if (i0 + k < n_tok) sum += (t[k] < kRleFirst) ? 1 : (2 << (t[k] - kRleFirst));
+  }
+  int total;
+  const int texcl = block_exclusive<int>(sum, total);
+  const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
+  long long pos = (long long)base + texcl;
+#pragma unroll
+  for (int k = 0; k < kExpItems; ++k) {
+    if (i0 + k < n_tok) {
+      if (t[k] < kRleFirst) {
+        if (t[k] != 0 && pos < n_out) out[pos] = t[k];
+        pos += 1;
+      } else {
+        pos += 2 << (t[k] - kRleFirst);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- int32 codes <-> byte symbols
 constexpr int kItems = 8;
 constexpr int kTile = kThreads * kItems;
@@ -330,6 +437,42 @@ extern "C" int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, 
   if (n <= 0) return LC_OK;
   LC_REQUIRE(d_mask && d_sym, "null argument");
   unpack_trits_kernel<<<grid_for((n + 4) / 5, 256), 256, 0, as_stream(stream)>>>(d_sym, n, d_mask);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" size_t lc_rle_workspace_bytes(int64_t n) {
+  const long long nt = ((n < 1 ? 1 : n) + kRleTile - 1) / kRleTile;
+  const long long ne = ((n < 1 ? 1 : n) + kThreads * kExpItems - 1) / (kThreads * kExpItems);
+  return ws_bytes(nt > ne ? nt : ne);
+}
+
+extern "C" int lc_rle_tokens(const uint8_t* d_sym, int64_t n, uint8_t* d_tok, unsigned long long* d_n_tok,
+                             uint32_t* d_hist, void* d_ws, void* stream) {
+  LC_REQUIRE(d_sym && d_tok && d_n_tok && d_hist && d_ws, "null argument");
+  LC_REQUIRE(n > 0, "empty input");
+  cudaStream_t s = as_stream(stream);
+  const long long nt = (n + kRleTile - 1) / kRleTile;
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  LC_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint32_t), s));
+  LC_CUDA(cudaMemsetAsync(d_n_tok, 0, sizeof(unsigned long long), s));
+  rle_tokens_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, d_tok, d_n_tok, d_hist,
+                                                      reinterpret_cast<unsigned long long*>(d_ws));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, uint8_t* d_sym, int64_t n, void* d_ws,
+                             void* stream) {
+  LC_REQUIRE(d_sym && d_ws && n > 0, "bad argument");
+  cudaStream_t s = as_stream(stream);
+  LC_CUDA(cudaMemsetAsync(d_sym, 0, (size_t)n, s));
+  if (n_tok <= 0) return LC_OK;
+  LC_REQUIRE(d_tok, "null argument");
+  const long long nt = (n_tok + kThreads * kExpItems - 1) / (kThreads * kExpItems);
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  rle_expand_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_tok, n_tok, d_sym, n,
+                                                      reinterpret_cast<unsigned long long*>(d_ws));
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

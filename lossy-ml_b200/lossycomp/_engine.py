@@ -361,6 +361,12 @@ class Engine:
             return t.cat([self.unpack_mask(p) for p in parts])
         sym, meta = self.unpack_stream(blob)
         n = meta["n_mask"]
+        if meta.get("rle"):                  # zero-run tokens -> 5-trit bytes
+            tok, ns = sym, int(meta["n_sym"])
+            sym = t.empty(ns, dtype=t.uint8, device=self.dev)
+            ws = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(max(ns, tok.numel())))
+            N.check(self.lib.lc_rle_expand(_ptr(tok), tok.numel(), _ptr(sym), ns, _ptr(ws), self._stream()), "lc_rle_expand")
+            self.launches += 1
         mask = t.empty(n, dtype=t.int8, device=self.dev)
         N.check(self.lib.lc_unpack_trits(_ptr(sym), n, _ptr(mask), self._stream()), "lc_unpack_trits")
         self.launches += 1
@@ -488,16 +494,29 @@ class Engine:
         # ---- pass 1 (async): symbols of the mask, histograms of everything
         sym_m = t.empty((n_m + 4) // 5, dtype=t.uint8, device=self.dev)
         N.check(self.lib.lc_pack_trits(_ptr(mask), n_m, _ptr(sym_m), self._stream()), "lc_pack_trits")
-        h3 = t.empty(768, dtype=t.int32, device=self.dev)
+        # histograms: [0:256] mask bytes, [256:768] the two code candidates, [768:1024] zero-run tokens of the mask,
+        # [1024:1026] their count (uint64)
+        h3 = t.empty(1026, dtype=t.int32, device=self.dev)
         N.check(self.lib.lc_hist_u8(_ptr(sym_m), sym_m.numel(), _ptr(h3), self._stream()), "lc_hist_u8")
         cand = ((0, 0), (1, 127))
         N.check(self.lib.lc_hist_codes(_ptr(q), n_q, ESC, cand[0][1], cand[1][1],
                                        C.c_void_p(h3.data_ptr() + 1024), self._stream()), "lc_hist_codes")
-        self.launches += 3
-        hh = h3.cpu().numpy().astype(np.int64) & 0xFFFFFFFF                       # sync 1
-        hist_m, hists_q = hh[:256], (hh[256:512], hh[512:])
-        # ---- host: tables
+        tok_m = t.empty(sym_m.numel(), dtype=t.uint8, device=self.dev)
+        ws_r = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(sym_m.numel()))
+        N.check(self.lib.lc_rle_tokens(_ptr(sym_m), sym_m.numel(), _ptr(tok_m), C.c_void_p(h3.data_ptr() + 4096),
+                                       C.c_void_p(h3.data_ptr() + 3072), _ptr(ws_r), self._stream()), "lc_rle_tokens")
+        self.launches += 4
+        hh = h3.cpu().numpy()                                                     # sync 1
+        n_tok = int(hh[1024:1026].view(np.int64)[0])
+        hh = hh[:1024].astype(np.int64) & 0xFFFFFFFF
+        hist_m, hists_q, hist_t = hh[:256], (hh[256:512], hh[512:768]), hh[768:1024]
+        # ---- host: tables; the mask goes out as zero-run tokens when that is shorter (sparse masks)
         tab_m = HF.build_table_native(hist_m)
+        tab_t = HF.build_table_native(hist_t)
+        mask_extra = {"kind": "mask5", "n_mask": int(n_m)}
+        if tab_t.encoded_bits(hist_t) + 16 * (n_tok // SEG) < tab_m.encoded_bits(hist_m) + 16 * (sym_m.numel() // SEG):
+            sym_m, tab_m, hist_m = tok_m[:n_tok], tab_t, hist_t
+            mask_extra.update(rle=1, n_sym=int((n_m + 4) // 5))
         tabs_q = [HF.build_table_native(h) for h in hists_q]
         costs = [tb.encoded_bits(h) + 32 * int(h[ESC]) for tb, h in zip(tabs_q, hists_q)]
         pick = 0 if costs[0] <= costs[1] else 1
@@ -511,7 +530,7 @@ class Engine:
         N.check(self.lib.lc_symbolize_i32(_ptr(q), n_q, diff, bias, ESC, _ptr(sym_q), _ptr(esc), _ptr(nesc),
                                           _ptr(ws), self._stream()), "lc_symbolize_i32")
         self.launches += 1
-        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", {"kind": "mask5", "n_mask": int(n_m)})
+        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", mask_extra)
         job_q = self._launch_pack(sym_q, tabs_q[pick], tabs_q[pick].encoded_bits(hists_q[pick]), "q",
                                   {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne}, tail_len=4 * ne)
         h_esc = None

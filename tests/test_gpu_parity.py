@@ -359,3 +359,99 @@ def test_blob_from_other_kernel_revision_is_refused(eng, torch):
     slots[0] = blob[:4] + struct.pack("<I", len(mj)) + mj + blob[8 + lm:]
     with pytest.raises(N.NativeError, match="revision"):
         decompress_device(eng, slots)
+
+
+def test_full_size_field_properties(torch):
+    """BASELINE.json configs[1] at full size (24 x 720 x 1440, 900 chunks, the shape bench.py times), through
+    size-independent properties: every element within the bound, compress() deterministic (identical blobs from
+    two calls), decoder idempotent and batch-split invariant, blob self-describing (9 slots, counts consistent),
+    and the decoded mask / code streams reproduce the compressor's exactly."""
+    from lossycomp import _native as N
+    from lossycomp._engine import Engine
+    from lossycomp.compress import compress_device
+    from lossycomp.decompress import decompress_device
+    eng = Engine.get(None, "fp16", 0)
+    T, H, W = 24, 720, 1440
+    x = torch.empty((T, H, W, 2), dtype=torch.float32, device="cuda")
+    N.check(eng.lib.lc_synth_field(x.data_ptr(), T, H, W, 0, 0, 1234, None), "lc_synth_field")
+    abs_err = 0.1
+    slots, info = compress_device(eng, x, abs_err, return_parts=True)
+    slots2, _ = compress_device(eng, x, abs_err)
+    assert pickle.dumps(slots) == pickle.dumps(slots2)
+    assert len(slots) == 9 and slots[1][0] == 900 and tuple(slots[2]) == (T, H, W, 2)
+    assert slots[3][0] == info["q"].numel() == int((info["mask"] > 0).sum().item())
+    assert torch.equal(eng.unpack_mask(slots[7]), info["mask"]) and torch.equal(eng.unpack_codes(slots[6]), info["q"])
+    xhat = decompress_device(eng, slots)
+    viol, mx = eng.verify(x, xhat, abs_err)
+    assert viol == 0 and mx <= abs_err
+    assert torch.equal(xhat, decompress_device(eng, slots))                 # idempotent
+    assert torch.equal(xhat, decompress_device(eng, slots, batch=77))       # ragged batch split of the 900 chunks
+    cf = T * H * W * 4 / len(pickle.dumps(slots))
+    assert cf > 8.0
+
+
+def _rle_tokens_reference(b):
+    """NumPy/Python restatement of lc_rle_tokens: 32-byte segments, zero runs -> largest power of two first."""
+    out = []
+    for s0 in range(0, len(b), 32):
+        seg = b[s0:s0 + 32]
+        i = 0
+        while i < len(seg):
+            if seg[i] != 0:
+                out.append(int(seg[i])); i += 1
+                continue
+            r = 1
+            while i + r < len(seg) and seg[i + r] == 0:
+                r += 1
+            for k in range(5, -1, -1):
+                if r & (1 << k):
+                    out.append(0 if k == 0 else 242 + k)
+            i += r
+    return np.array(out, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("n,density", [(1, 0.0), (31, 0.5), (32, 0.0), (33, 0.02), (8192, 0.001), (8193, 0.3),
+                                       (100003, 0.01), (100003, 0.9), (250000, 0.0)])
+def test_zero_run_tokens_match_reference_and_invert(eng, torch, n, density):
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    b = np.where(rng.random(n) < density, rng.integers(1, 243, n), 0).astype(np.uint8)
+    d_b = dev(torch, b)
+    tok = torch.empty(n, dtype=torch.uint8, device="cuda")
+    meta = torch.zeros(258, dtype=torch.int32, device="cuda")           # [0:256] histogram, [256:258] count
+    ws = torch.empty(eng.lib.lc_rle_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    from lossycomp import _native as N
+    N.check(eng.lib.lc_rle_tokens(d_b.data_ptr(), n, tok.data_ptr(), C.c_void_p(meta.data_ptr() + 1024),
+                                  meta.data_ptr(), ws.data_ptr(), None), "lc_rle_tokens")
+    m = meta.cpu().numpy()
+    n_tok = int(m[256:258].view(np.int64)[0])
+    ref = _rle_tokens_reference(b)
+    got = tok[:n_tok].cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(m[:256].astype(np.int64), np.bincount(ref, minlength=256))
+    back = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+    N.check(eng.lib.lc_rle_expand(tok.data_ptr(), n_tok, back.data_ptr(), n, ws.data_ptr(), None), "lc_rle_expand")
+    np.testing.assert_array_equal(back.cpu().numpy(), b)
+
+
+def test_sparse_mask_uses_zero_run_tokens_and_roundtrips(eng, torch):
+    """At a large abs_error almost every 5-trit byte is zero: the container must switch to zero-run tokens (a
+    plain Huffman stream cannot go below one bit per byte) and decode to the identical mask."""
+    import json
+    import struct
+    rng = np.random.default_rng(5)
+    n = 1_000_003
+    mask = np.where(rng.random(n) < 0.0005, rng.integers(1, 3, n), 0).astype(np.int8)
+    q = np.ones(int((mask > 0).sum()), dtype=np.int32)
+    comp_error, comp_mask = eng.pack_streams(dev(torch, mask), dev(torch, q))
+    lm = struct.unpack("<I", comp_mask[4:8])[0]
+    meta = json.loads(comp_mask[16:16 + lm])
+    assert meta.get("rle") == 1
+    assert len(comp_mask) < n // 40 // 4            # far below the one-bit-per-byte floor of the plain stream
+    assert np.array_equal(eng.unpack_mask(comp_mask).cpu().numpy(), mask)
+    assert np.array_equal(eng.unpack_codes(comp_error).cpu().numpy(), q)
+    dense = np.where(rng.random(n) < 0.3, rng.integers(1, 3, n), 0).astype(np.int8)
+    qd = rng.integers(1, 9, int((dense > 0).sum())).astype(np.int32)
+    ce, cm = eng.pack_streams(dev(torch, dense), dev(torch, qd))
+    assert "rle" not in json.loads(cm[16:16 + struct.unpack("<I", cm[4:8])[0]])
+    assert np.array_equal(eng.unpack_mask(cm).cpu().numpy(), dense)
