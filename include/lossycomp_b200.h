@@ -132,6 +132,14 @@ int lc_quantize_checked(const float* d_x, int C, const float* d_recon, int64_t n
                         float thr, float thr2, double thr2_dec, double abs_err, int8_t* d_mask, int32_t* d_q,
                         unsigned long long* d_out3, void* d_ws, void* stream);
 
+/* Latent quantisation (the reference stores the bottleneck tensor losslessly through fpzip, compress.py:142-144;
+ * here it is rounded to IEEE half precision, which the decoder then consumes on both sides, so the error bound
+ * is unaffected -- the residual stage absorbs the rounding).  lc_latent_quantize overwrites d_latent with the
+ * dequantised values and writes the low / high byte planes of the half-precision codes; lc_latent_dequantize
+ * rebuilds the fp32 latent from the planes. */
+int lc_latent_quantize(float* d_latent, int64_t n, uint8_t* d_lo, uint8_t* d_hi, void* stream);
+int lc_latent_dequantize(const uint8_t* d_lo, const uint8_t* d_hi, int64_t n, float* d_latent, void* stream);
+
 /* compress.py:147-151,159-163 -- first difference [v0, v1-v0, ...] (int8 wraps like NumPy). */
 int lc_diff_i32(const int32_t* d_in, int64_t n, int32_t* d_out, void* stream);
 int lc_diff_i8(const int8_t* d_in, int64_t n, int8_t* d_out, void* stream);
@@ -169,15 +177,18 @@ int lc_unsymbolize_i32(const uint8_t* d_sym, int64_t n, int diff, int bias, int 
 int lc_pack_trits(const int8_t* d_mask, int64_t n, uint8_t* d_sym, void* stream);
 int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* stream);
 
-/* Zero-run tokens for sparse masks (large abs_error): a Huffman code cannot spend less than one bit per symbol,
- * so runs of zero bytes are folded into the alphabet: tokens 0..242 are literal bytes (0 = one zero byte),
- * 243+k = 2^(k+1) zero bytes (k = 0..4).  Runs do not cross 32-byte segments and are decomposed largest power of
- * two first.  lc_rle_tokens writes the tokens (at most n), their count and their 256-bin histogram;
- * lc_rle_expand is the inverse (d_sym: n bytes).  d_ws: lc_rle_workspace_bytes(n). */
+/* Run tokens for sparse streams (large abs_error): a Huffman code cannot spend less than one bit per symbol,
+ * so runs of the dominant byte `run_sym` are folded into the alphabet: a run of 2^(k+1) of them (k = 0..4) becomes
+ * the token run_first + k, every other byte (a single run_sym included) stays a literal.  Runs do not cross
+ * 32-byte segments and are decomposed largest power of two first.  The stream must not contain the bytes
+ * run_first .. run_first+4 (the caller checks its histogram).  Mask bytes: run_sym 0, run_first 243; code symbols:
+ * run_sym 1, run_first 250.  lc_rle_tokens writes the tokens (at most n), their count and their 256-bin
+ * histogram; lc_rle_expand is the inverse (d_sym: n bytes).  d_ws: lc_rle_workspace_bytes(n). */
 size_t lc_rle_workspace_bytes(int64_t n);
-int lc_rle_tokens(const uint8_t* d_sym, int64_t n, uint8_t* d_tok, unsigned long long* d_n_tok, uint32_t* d_hist,
+int lc_rle_tokens(const uint8_t* d_sym, int64_t n, int run_sym, int run_first, uint8_t* d_tok,
+                  unsigned long long* d_n_tok, uint32_t* d_hist, void* d_ws, void* stream);
+int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, int run_sym, int run_first, uint8_t* d_sym, int64_t n,
                   void* d_ws, void* stream);
-int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, uint8_t* d_sym, int64_t n, void* d_ws, void* stream);
 
 /* Huffman bit packing from a host-built table: code[s] (right-aligned, MSB of the code is
  * emitted first) and len[s] (0..32).  The stream is cut into segments of `seg` (= 1024) symbols; each

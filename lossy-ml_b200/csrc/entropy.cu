@@ -109,14 +109,16 @@ __global__ void unpack_trits_kernel(const uint8_t* __restrict__ in, long long n,
 // into the alphabet itself: bytes 0..242 are literals (0 = a single zero byte) and 243+k stands for 2^(k+1) zero
 // bytes (k = 0..4).  Runs are confined to the 32 bytes one thread owns and are decomposed greedily, largest power
 // of two first, so tokenising is thread-local bit arithmetic; the token stream stays a byte stream for the same
-// Huffman packer.  Whether a mask is coded plain or tokenised is decided from the two histograms.
+// Huffman packer.  Whether a mask is coded plain or tokenised is decided from the two histograms.  The same
+// kernels serve the code stream at large abs_error (nearly every code is 1): run symbol and first run token are
+// parameters (the five run tokens must be unused by the stream, which the caller checks on its histogram).
 constexpr int kRleSeg = 32;                        // bytes per thread = longest run
 constexpr int kRleTile = kThreads * kRleSeg;       // 8192 bytes per block
-constexpr int kRleFirst = 243;                     // first run symbol (2 zero bytes)
 
 __global__ void __launch_bounds__(kThreads)
-rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, uint8_t* __restrict__ tok,
-                  unsigned long long* __restrict__ n_tok, uint32_t* __restrict__ hist, unsigned long long* ws) {
+rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, int run_sym, int run_first,
+                  uint8_t* __restrict__ tok, unsigned long long* __restrict__ n_tok, uint32_t* __restrict__ hist,
+                  unsigned long long* ws) {
   __shared__ uint8_t s_tok[kRleTile];
   __shared__ uint32_t s_hist[256];
   if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
@@ -132,12 +134,12 @@ rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, uint8_t* __restr
     len = kRleSeg;
   } else {
 #pragma unroll
-    for (int k = 0; k < kRleSeg; ++k) b[k] = (i0 + k < n) ? sym[i0 + k] : 1;   // padding is "non-zero": never in a run
+    for (int k = 0; k < kRleSeg; ++k) b[k] = (i0 + k < n) ? sym[i0 + k] : 0;
     len = (i0 < n) ? (int)((n - i0 < kRleSeg) ? (n - i0) : kRleSeg) : 0;
   }
-  unsigned nz = 0;                     // bit k: byte k is not part of a zero run
+  unsigned nz = 0;                     // bit k: byte k is not part of a run (padding beyond len never is)
 #pragma unroll
-  for (int k = 0; k < kRleSeg; ++k) nz |= (unsigned)(b[k] != 0 || k >= len) << k;
+  for (int k = 0; k < kRleSeg; ++k) nz |= (unsigned)(b[k] != run_sym || k >= len) << k;
   // token starts: every literal, and inside a zero run [s, s+R) the offsets j with j = R with its low bits cleared
   unsigned start = 0;
   uint8_t val[kRleSeg];
@@ -156,7 +158,7 @@ rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, uint8_t* __restr
         const int hb = 31 - __clz((unsigned)(R ^ j));       // R > j, so R ^ j != 0
         if ((j & ((2 << hb) - 1)) == 0) {
           start |= 1u << k;
-          val[k] = hb ? (uint8_t)(kRleFirst - 1 + hb) : (uint8_t)0;
+          val[k] = hb ? (uint8_t)(run_first - 1 + hb) : (uint8_t)run_sym;
         }
       }
     }
@@ -179,11 +181,12 @@ rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, uint8_t* __restr
   if ((long long)(tile + 1) * kRleTile >= n && threadIdx.x == 0) *n_tok = base + (unsigned long long)total;
 }
 
-// tokens -> bytes: exclusive scan of the token lengths gives every literal its position; the output was zero-filled
+// tokens -> bytes: exclusive scan of the token lengths gives every literal its position; the output was filled
+// with the run symbol
 constexpr int kExpItems = 16;
 __global__ void __launch_bounds__(kThreads)
-rle_expand_kernel(const uint8_t* __restrict__ tok, long long n_tok, uint8_t* __restrict__ out, long long n_out,
-                  unsigned long long* ws) {
+rle_expand_kernel(const uint8_t* __restrict__ tok, long long n_tok, int run_sym, int run_first,
+                  uint8_t* __restrict__ out, long long n_out, unsigned long long* ws) {
   const int tile = take_ticket(ws);
   const long long i0 = (long long)tile * (kThreads * kExpItems) + (long long)threadIdx.x * kExpItems;
   uint8_t t[kExpItems];
@@ -191,7 +194,8 @@ rle_expand_kernel(const uint8_t* __restrict__ tok, long long n_tok, uint8_t* __r
 #pragma unroll
   for (int k = 0; k < kExpItems; ++k) {
     t[k] = (i0 + k < n_tok) ? tok[i0 + k] : 0;
-    if (i0 + k < n_tok) sum += (t[k] < kRleFirst) ? 1 : (2 << (t[k] - kRleFirst));
+    const int r = (int)t[k] - run_first;                   // 0..4: a run of 2 << r
+    if (i0 + k < n_tok) sum += (r < 0 || r > 4) ? 1 : (2 << r);
   }
   int total;
   const int texcl = block_exclusive<int>(sum, total);
@@ -200,11 +204,12 @@ rle_expand_kernel(const uint8_t* __restrict__ tok, long long n_tok, uint8_t* __r
 #pragma unroll
   for (int k = 0; k < kExpItems; ++k) {
     if (i0 + k < n_tok) {
-      if (t[k] < kRleFirst) {
-        if (t[k] != 0 && pos < n_out) out[pos] = t[k];
+      const int r = (int)t[k] - run_first;
+      if (r < 0 || r > 4) {
+        if (t[k] != run_sym && pos < n_out) out[pos] = t[k];
         pos += 1;
       } else {
-        pos += 2 << (t[k] - kRleFirst);
+        pos += 2 << r;
       }
     }
   }
@@ -447,31 +452,34 @@ extern "C" size_t lc_rle_workspace_bytes(int64_t n) {
   return ws_bytes(nt > ne ? nt : ne);
 }
 
-extern "C" int lc_rle_tokens(const uint8_t* d_sym, int64_t n, uint8_t* d_tok, unsigned long long* d_n_tok,
-                             uint32_t* d_hist, void* d_ws, void* stream) {
+extern "C" int lc_rle_tokens(const uint8_t* d_sym, int64_t n, int run_sym, int run_first, uint8_t* d_tok,
+                             unsigned long long* d_n_tok, uint32_t* d_hist, void* d_ws, void* stream) {
   LC_REQUIRE(d_sym && d_tok && d_n_tok && d_hist && d_ws, "null argument");
   LC_REQUIRE(n > 0, "empty input");
+  LC_REQUIRE(run_sym >= 0 && run_sym < 256 && run_first >= 0 && run_first + 4 < 256 &&
+                 (run_sym < run_first || run_sym > run_first + 4), "bad run symbols");
   cudaStream_t s = as_stream(stream);
   const long long nt = (n + kRleTile - 1) / kRleTile;
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
   LC_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint32_t), s));
   LC_CUDA(cudaMemsetAsync(d_n_tok, 0, sizeof(unsigned long long), s));
-  rle_tokens_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, d_tok, d_n_tok, d_hist,
+  rle_tokens_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, run_sym, run_first, d_tok, d_n_tok, d_hist,
                                                       reinterpret_cast<unsigned long long*>(d_ws));
   LC_LAUNCH_CHECK();
   return LC_OK;
 }
 
-extern "C" int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, uint8_t* d_sym, int64_t n, void* d_ws,
-                             void* stream) {
+extern "C" int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, int run_sym, int run_first, uint8_t* d_sym,
+                             int64_t n, void* d_ws, void* stream) {
   LC_REQUIRE(d_sym && d_ws && n > 0, "bad argument");
+  LC_REQUIRE(run_sym >= 0 && run_sym < 256 && run_first >= 0 && run_first + 4 < 256, "bad run symbols");
   cudaStream_t s = as_stream(stream);
-  LC_CUDA(cudaMemsetAsync(d_sym, 0, (size_t)n, s));
+  LC_CUDA(cudaMemsetAsync(d_sym, run_sym, (size_t)n, s));
   if (n_tok <= 0) return LC_OK;
   LC_REQUIRE(d_tok, "null argument");
   const long long nt = (n_tok + kThreads * kExpItems - 1) / (kThreads * kExpItems);
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
-  rle_expand_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_tok, n_tok, d_sym, n,
+  rle_expand_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_tok, n_tok, run_sym, run_first, d_sym, n,
                                                       reinterpret_cast<unsigned long long*>(d_ws));
   LC_LAUNCH_CHECK();
   return LC_OK;

@@ -4,6 +4,7 @@
 // Bit-exactness with NumPy: every float op is an explicit round-to-nearest intrinsic so nvcc
 // cannot contract a*b+c into an FMA; the divide is IEEE (__fdiv_rn), the
 // rounding is half-to-even (__float2int_rn == np.round().astype(int32) for in-range values).
+#include <cuda_fp16.h>
 #include "scan.cuh"
 
 using namespace lcscan;
@@ -178,6 +179,38 @@ reconstruct_kernel(const float* __restrict__ recon, const int8_t* __restrict__ m
   }
 }
 
+// Latent quantisation: the bottleneck tensor is stored as IEEE half precision (round to nearest even, saturating),
+// split into its low and high byte planes (only the high one -- sign, exponent, two mantissa bits -- is
+// compressible).  The fp32 latent is overwritten with the dequantised values, which is what the decoder consumes in
+// compress() and decompress() alike, so the reconstruction both sides see is identical.
+__global__ void latent_quantize_kernel(float* __restrict__ lat, long long n, uint8_t* __restrict__ lo,
+                                       uint8_t* __restrict__ hi) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // The half-precision code is produced in a 32-bit register (cvt.rn.f16x2 with a zero upper half) and its bytes
+    // are taken with 32-bit integer ops: ptxas 12.9 turns `st.u8` of a 16-bit register written by cvt.rn.f16.f32
+    // into a numeric half->u8 conversion (F2I.U8.F16), which zeroed the low byte plane.
+    const float v = fminf(fmaxf(lat[i], -65504.f), 65504.f);                // NaN propagates
+    unsigned w;
+    float back;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(0.f), "f"(v));
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, l; }" : "=f"(back) : "r"(w));
+    lo[i] = (uint8_t)(w & 0xffu);
+    hi[i] = (uint8_t)((w >> 8) & 0xffu);
+    lat[i] = back;
+  }
+}
+
+__global__ void latent_dequantize_kernel(const uint8_t* __restrict__ lo, const uint8_t* __restrict__ hi, long long n,
+                                         float* __restrict__ lat) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    const unsigned short u = (unsigned short)((unsigned)lo[i] | ((unsigned)hi[i] << 8));
+    float back;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(back) : "h"(u));
+    lat[i] = back;
+  }
+}
+
 template <typename T>
 __global__ void diff_kernel(const T* __restrict__ in, long long n, T* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -263,6 +296,27 @@ extern "C" int lc_reconstruct(const float* d_recon, const int8_t* d_mask, const 
                                                        d_out, reinterpret_cast<unsigned long long*>(d_ws),
                                                        aligned16(d_recon), aligned8(d_mask),
                                                        aligned16(d_out));
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_latent_quantize(float* d_latent, int64_t n, uint8_t* d_lo, uint8_t* d_hi, void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_latent && d_lo && d_hi, "null argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  latent_quantize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_latent, n, d_lo, d_hi);
+  LC_LAUNCH_CHECK();
+  return LC_OK;
+}
+
+extern "C" int lc_latent_dequantize(const uint8_t* d_lo, const uint8_t* d_hi, int64_t n, float* d_latent,
+                                    void* stream) {
+  if (n <= 0) return LC_OK;
+  LC_REQUIRE(d_latent && d_lo && d_hi, "null argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  latent_dequantize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_lo, d_hi, n, d_latent);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

@@ -27,6 +27,8 @@ LATENT_MAGIC = b"LCL1"
 HUFF_MAGIC = b"LCH1"
 SEG = 1024                      # symbols per independently decodable Huffman segment
 ESC = 255                       # escape symbol of the code stream
+MASK_RUN = (0, 243)             # run tokens of the mask stream: runs of byte 0, tokens 243..247
+CODE_RUN = (1, 250)             # run tokens of the code stream: runs of code 1 (undifferenced), tokens 250..254
 # Revision of the autoencoder kernels' arithmetic (summation order, rounding points).  The error bound only
 # holds when the decoder reproduces the compressor's reconstruction bit for bit, so blobs record the
 # revision they were written with and a build with different arithmetic refuses them.
@@ -365,7 +367,9 @@ class Engine:
             tok, ns = sym, int(meta["n_sym"])
             sym = t.empty(ns, dtype=t.uint8, device=self.dev)
             ws = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(max(ns, tok.numel())))
-            N.check(self.lib.lc_rle_expand(_ptr(tok), tok.numel(), _ptr(sym), ns, _ptr(ws), self._stream()), "lc_rle_expand")
+            N.check(self.lib.lc_rle_expand(_ptr(tok), tok.numel(), int(meta.get("run_sym", 0)),
+                                           int(meta.get("run_first", 243)), _ptr(sym), ns, _ptr(ws), self._stream()),
+                    "lc_rle_expand")
             self.launches += 1
         mask = t.empty(n, dtype=t.int8, device=self.dev)
         N.check(self.lib.lc_unpack_trits(_ptr(sym), n, _ptr(mask), self._stream()), "lc_unpack_trits")
@@ -414,6 +418,13 @@ class Engine:
         body, escb = (blob[:len(blob) - 4 * ne], blob[len(blob) - 4 * ne:]) if ne else (blob, b"")
         sym, meta = self.unpack_stream(body)
         n = meta["n"]
+        if meta.get("rle"):                  # run tokens -> code symbols
+            tok, n = sym, int(meta["n_sym"])
+            sym = t.empty(n, dtype=t.uint8, device=self.dev)
+            ws = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(max(n, tok.numel())))
+            N.check(self.lib.lc_rle_expand(_ptr(tok), tok.numel(), int(meta["run_sym"]), int(meta["run_first"]), _ptr(sym),
+                                           n, _ptr(ws), self._stream()), "lc_rle_expand")
+            self.launches += 1
         q = t.empty(n, dtype=t.int32, device=self.dev)
         if n == 0:
             return q
@@ -503,8 +514,9 @@ class Engine:
                                        C.c_void_p(h3.data_ptr() + 1024), self._stream()), "lc_hist_codes")
         tok_m = t.empty(sym_m.numel(), dtype=t.uint8, device=self.dev)
         ws_r = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(sym_m.numel()))
-        N.check(self.lib.lc_rle_tokens(_ptr(sym_m), sym_m.numel(), _ptr(tok_m), C.c_void_p(h3.data_ptr() + 4096),
-                                       C.c_void_p(h3.data_ptr() + 3072), _ptr(ws_r), self._stream()), "lc_rle_tokens")
+        N.check(self.lib.lc_rle_tokens(_ptr(sym_m), sym_m.numel(), *MASK_RUN, _ptr(tok_m),
+                                       C.c_void_p(h3.data_ptr() + 4096), C.c_void_p(h3.data_ptr() + 3072), _ptr(ws_r),
+                                       self._stream()), "lc_rle_tokens")
         self.launches += 4
         hh = h3.cpu().numpy()                                                     # sync 1
         n_tok = int(hh[1024:1026].view(np.int64)[0])
@@ -516,7 +528,7 @@ class Engine:
         mask_extra = {"kind": "mask5", "n_mask": int(n_m)}
         if tab_t.encoded_bits(hist_t) + 16 * (n_tok // SEG) < tab_m.encoded_bits(hist_m) + 16 * (sym_m.numel() // SEG):
             sym_m, tab_m, hist_m = tok_m[:n_tok], tab_t, hist_t
-            mask_extra.update(rle=1, n_sym=int((n_m + 4) // 5))
+            mask_extra.update(rle=1, n_sym=int((n_m + 4) // 5), run_sym=MASK_RUN[0], run_first=MASK_RUN[1])
         tabs_q = [HF.build_table_native(h) for h in hists_q]
         costs = [tb.encoded_bits(h) + 32 * int(h[ESC]) for tb, h in zip(tabs_q, hists_q)]
         pick = 0 if costs[0] <= costs[1] else 1
@@ -531,8 +543,25 @@ class Engine:
                                           _ptr(ws), self._stream()), "lc_symbolize_i32")
         self.launches += 1
         job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", mask_extra)
-        job_q = self._launch_pack(sym_q, tabs_q[pick], tabs_q[pick].encoded_bits(hists_q[pick]), "q",
-                                  {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne}, tail_len=4 * ne)
+        tab_q, hist_q = tabs_q[pick], hists_q[pick]
+        code_extra = {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne}
+        # Large abs_error: nearly every code is 1 and the one-bit floor of the Huffman code dominates the slot.
+        # Fold runs of 1 into run tokens (one more host sync, taken only in this regime) when that is shorter.
+        if pick == 0 and hist_q[CODE_RUN[0]] > 0.55 * n_q and not hist_q[CODE_RUN[1]:CODE_RUN[1] + 5].any():
+            tok_q = t.empty(n_q, dtype=t.uint8, device=self.dev)
+            ht = t.empty(258, dtype=t.int32, device=self.dev)
+            ws_q = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(n_q))
+            N.check(self.lib.lc_rle_tokens(_ptr(sym_q), n_q, *CODE_RUN, _ptr(tok_q), C.c_void_p(ht.data_ptr() + 1024),
+                                           _ptr(ht), _ptr(ws_q), self._stream()), "lc_rle_tokens")
+            self.launches += 1
+            hv = ht.cpu().numpy()                                                 # sync (sparse regime only)
+            n_tok = int(hv[256:258].view(np.int64)[0])
+            hist_t = hv[:256].astype(np.int64) & 0xFFFFFFFF
+            tab_t = HF.build_table_native(hist_t)
+            if tab_t.encoded_bits(hist_t) + 16 * (n_tok // SEG) < tab_q.encoded_bits(hist_q) + 16 * (n_q // SEG):
+                sym_q, tab_q, hist_q = tok_q[:n_tok], tab_t, hist_t
+                code_extra.update(rle=1, n_sym=int(n_q), run_sym=CODE_RUN[0], run_first=CODE_RUN[1])
+        job_q = self._launch_pack(sym_q, tab_q, tab_q.encoded_bits(hist_q), "q", code_extra, tail_len=4 * ne)
         h_esc = None
         if ne:
             h_esc = self._pinned("esc", 4 * ne)
@@ -556,11 +585,12 @@ class Engine:
         pin[:nb].copy_(latent.reshape(-1).view(t.uint8), non_blocking=True)
         return pin, nb
 
+    def _latent_meta(self, codec, **extra):
+        return dict({"precision": self.precision, "model": self.model.arch.name, "filters": self.model.arch.filters,
+                     "kernel": self.model.arch.kernel, "codec": codec, "rev": NUMERICS_REV}, **extra)
+
     def pack_latent(self, latent, codec="raw", staged=None) -> bytes:
-        meta = {"precision": self.precision, "model": self.model.arch.name,
-                "filters": self.model.arch.filters, "kernel": self.model.arch.kernel, "codec": codec,
-                "rev": NUMERICS_REV}
-        mj = json.dumps(meta).encode()
+        mj = json.dumps(self._latent_meta(codec)).encode()
         if staged is not None:                      # float32 little-endian, already on the host
             raw = memoryview(staged[0].numpy())[:staged[1]]
         else:
@@ -569,21 +599,84 @@ class Engine:
             raw = bz2.compress(raw, 9)
         return b"".join([LATENT_MAGIC, struct.pack("<I", len(mj)), mj, raw])
 
+    # -- latent quantisation: half-precision codes, high byte plane Huffman-coded ('f16' codec) ---------------
+    def quantize_latent(self, latent):
+        """Round the latent to half precision IN PLACE (the decoder must consume the rounded values) and return
+        (low byte plane, high byte plane, event recorded after the kernel)."""
+        t = self.torch
+        n = latent.numel()
+        lo = t.empty(n, dtype=t.uint8, device=self.dev)
+        hi = t.empty(n, dtype=t.uint8, device=self.dev)
+        N.check(self.lib.lc_latent_quantize(_ptr(latent), n, _ptr(lo), _ptr(hi), self._stream()), "lc_latent_quantize")
+        self.launches += 1
+        ev = t.cuda.Event()
+        ev.record(t.cuda.current_stream(self.dev))
+        return lo, hi, ev
+
+    def _f16_container(self, n, lo_bytes, hi_container) -> bytes:
+        mj = json.dumps(self._latent_meta("f16", n=int(n))).encode()
+        return b"".join([LATENT_MAGIC, struct.pack("<I", len(mj)), mj, lo_bytes, hi_container])
+
+    def pack_latent_f16(self, lo, hi, ev) -> bytes:
+        """Entropy-code the planes of quantize_latent() on a side stream.  Call it after the decoder has been
+        enqueued: only the side stream is synchronised, so the two host syncs of the Huffman stage hide behind
+        the decoder's kernels."""
+        t = self.torch
+        side = self._small.get("side_stream")
+        if side is None:
+            side = self._small["side_stream"] = t.cuda.Stream(device=self.dev)
+        side.wait_event(ev)
+        lo.record_stream(side)
+        hi.record_stream(side)
+        n = hi.numel()
+        with t.cuda.stream(side):
+            h = t.empty(256, dtype=t.int32, device=self.dev)
+            N.check(self.lib.lc_hist_u8(_ptr(hi), n, _ptr(h), self._stream()), "lc_hist_u8")
+            self.launches += 1
+            h_lo = self._pinned("lat_lo", n)
+            h_lo[:n].copy_(lo, non_blocking=True)
+            hist = h.cpu().numpy().astype(np.int64) & 0xFFFFFFFF                  # syncs the side stream only
+            table = HF.build_table_native(hist)
+            job = self._launch_pack(hi, table, table.encoded_bits(hist), "lat", {"kind": "latent_hi"})
+            self._collect_pack(job)
+            side.synchronize()
+            hi_container = self._finish_pack(job)
+        return self._f16_container(n, memoryview(h_lo.numpy())[:n], hi_container)
+
+    def _split_f16(self, blob, meta, lm):
+        n = int(meta["n"])
+        off = 8 + lm
+        return n, blob[off:off + n], blob[off + n:]
+
     def join_latents(self, blobs) -> bytes:
         """Concatenate the latent containers of consecutive chunk ranges (time shards) into one."""
-        metas, raws = [], []
+        t = self.torch
+        metas, bodies = [], []
         for b in blobs:
             assert b[:4] == LATENT_MAGIC
             (lm,) = struct.unpack("<I", b[4:8])
-            meta = json.loads(b[8:8 + lm])
-            raw = b[8 + lm:]
-            if meta.get("codec") == "bz2":
-                raw = bz2.decompress(raw)
-            metas.append(meta)
-            raws.append(raw)
-        meta = dict(metas[0], codec="raw")
-        assert all(m["precision"] == meta["precision"] and m["model"] == meta["model"] for m in metas)
-        mj = json.dumps(meta).encode()
+            metas.append((json.loads(b[8:8 + lm]), lm))
+            bodies.append(b)
+        first = metas[0][0]
+        assert all(m["precision"] == first["precision"] and m["model"] == first["model"] and
+                   m.get("rev", 1) == first.get("rev", 1) for m, _ in metas)
+        if all(m.get("codec") == "f16" for m, _ in metas):
+            los, his = [], []
+            for (m, lm), b in zip(metas, bodies):
+                n, lo, hic = self._split_f16(b, m, lm)
+                los.append(lo)
+                his.append(self.unpack_stream(hic)[0])
+            hi = t.cat(his)
+            return self._f16_container(hi.numel(), b"".join(los), self.pack_stream(hi, {"kind": "latent_hi"}))
+        raws = []
+        for (m, lm), b in zip(metas, bodies):
+            if m.get("codec") == "f16":
+                n = int(m["n"])
+                raws.append(self.unpack_latent(b, (1, n))[0].cpu().numpy().astype("<f4").tobytes())
+            else:
+                raw = b[8 + lm:]
+                raws.append(bz2.decompress(raw) if m.get("codec") == "bz2" else raw)
+        mj = json.dumps(dict(first, codec="raw")).encode()
         return LATENT_MAGIC + struct.pack("<I", len(mj)) + mj + b"".join(raws)
 
     def unpack_latent(self, blob: bytes, shape):
@@ -596,6 +689,16 @@ class Engine:
         if meta.get("rev", 1) != NUMERICS_REV:
             raise N.NativeError(f"blob was written by kernel arithmetic revision {meta.get('rev', 1)}, this build is "
                                 f"revision {NUMERICS_REV}: its reconstruction would not be reproduced bit for bit")
+        if meta.get("codec") == "f16":
+            t = self.torch
+            n, lo_b, hic = self._split_f16(blob, meta, lm)
+            assert n == int(np.prod(shape))
+            lo = t.from_numpy(np.frombuffer(lo_b, dtype=np.uint8).copy()).to(self.dev, non_blocking=True)
+            hi = self.unpack_stream(hic)[0]
+            lat = t.empty((shape[0], n // shape[0]), dtype=t.float32, device=self.dev)
+            N.check(self.lib.lc_latent_dequantize(_ptr(lo), _ptr(hi), n, _ptr(lat), self._stream()), "lc_latent_dequantize")
+            self.launches += 1
+            return lat, meta
         raw = blob[8 + lm:]
         if meta.get("codec") == "bz2":
             raw = bz2.decompress(raw)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "lc_scan_workspace_bytes": (_sz, [_i64]),
     "lc_quantize": (_i, [_p, _i, _p, _i64, _f, _f, _f, _f, _p, _p, _p, _p, _p]),
     "lc_quantize_checked": (_i, [_p, _i, _p, _i64, _f, _f, _f, _f, _d, _d, _p, _p, _p, _p, _p]),
+    "lc_latent_quantize": (_i, [_p, _i64, _p, _p, _p]),
+    "lc_latent_dequantize": (_i, [_p, _p, _i64, _p, _p]),
     "lc_diff_i32": (_i, [_p, _i64, _p, _p]),
     "lc_diff_i8": (_i, [_p, _i64, _p, _p]),
     "lc_cumsum_i32": (_i, [_p, _i64, _p, _p, _p]),
@@ -65,8 +67,8 @@ SIGNATURES = {
     "lc_pack_trits": (_i, [_p, _i64, _p, _p]),
     "lc_unpack_trits": (_i, [_p, _i64, _p, _p]),
     "lc_rle_workspace_bytes": (_sz, [_i64]),
-    "lc_rle_tokens": (_i, [_p, _i64, _p, _p, _p, _p, _p]),
-    "lc_rle_expand": (_i, [_p, _i64, _p, _i64, _p, _p]),
+    "lc_rle_tokens": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
+    "lc_rle_expand": (_i, [_p, _i64, _i, _i, _p, _i64, _p, _p]),
     "lc_huff_build_table": (_i, [_p, _i, _p, _p, _p, _p]),
     "lc_huff_max_bytes": (_sz, [_i64]),
     "lc_huff_workspace_bytes": (_sz, [_i64, _i]),

@@ -64,13 +64,23 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     if "mean" in inject:                 # parity tests / global statistics of a time-sharded field
         mean, std = np.float32(inject["mean"]), np.float32(inject["std"])
         max_abs = float(inject.get("max_abs", max_abs))
+    if latent_codec is None:
+        # "f16": latent quantised to half precision + Huffman (16-bit engines); compat codec: lossless host coder
+        # for the latent too (fpzip's role, compress.py:144); fp32 engine: raw fp32
+        latent_codec = "bz2" if codec == "bz2" else ("f16" if eng.precision != "fp32" else "raw")
     latent = eng.encode(x, mean, std, batch=batch)                                   # compress.py:66-86
-    staged = eng.stage_latent(latent)    # its D2H copy runs behind the decoder; the quantiser's sync covers it
+    if latent_codec == "f16":
+        planes = eng.quantize_latent(latent)     # in place: the decoder below consumes the rounded latent
+    else:
+        staged = eng.stage_latent(latent)        # its D2H copy runs behind the decoder; the quantiser's sync covers it
     tm and tm.mark("encode")
     if "recon_std" in inject:
         recon = inject["recon_std"]
     else:
         recon = eng.decode(latent, T, H, W, batch=batch)                             # compress.py:99-111
+    comp_data = None
+    if latent_codec == "f16":
+        comp_data = eng.pack_latent_f16(*planes)                                     # side stream, behind the decoder
     tm and tm.mark("decode")
     thr = abs_err
     info = {"mode": mode, "codec": codec}
@@ -101,9 +111,8 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         assert thr > 0.5 * abs_err, "cannot meet the bound in float32"
     tm and tm.mark("quantize+verify")
     n_out = int(q.numel())
-    if latent_codec is None:      # compat codec: lossless host coder for the latent too (fpzip's role, compress.py:144)
-        latent_codec = "bz2" if codec == "bz2" else "raw"
-    comp_data = eng.pack_latent(latent, latent_codec, staged)                                # compress.py:142-144
+    if comp_data is None:
+        comp_data = eng.pack_latent(latent, latent_codec, staged)                    # compress.py:142-144
     tm and tm.mark("latent_pack")
     lshape = (latent.shape[0],) + tuple(eng.model.arch.latent_shape()[1:])
     if codec == "bz2":

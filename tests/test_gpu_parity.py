@@ -421,7 +421,7 @@ def test_zero_run_tokens_match_reference_and_invert(eng, torch, n, density):
     meta = torch.zeros(258, dtype=torch.int32, device="cuda")           # [0:256] histogram, [256:258] count
     ws = torch.empty(eng.lib.lc_rle_workspace_bytes(n), dtype=torch.uint8, device="cuda")
     from lossycomp import _native as N
-    N.check(eng.lib.lc_rle_tokens(d_b.data_ptr(), n, tok.data_ptr(), C.c_void_p(meta.data_ptr() + 1024),
+    N.check(eng.lib.lc_rle_tokens(d_b.data_ptr(), n, 0, 243, tok.data_ptr(), C.c_void_p(meta.data_ptr() + 1024),
                                   meta.data_ptr(), ws.data_ptr(), None), "lc_rle_tokens")
     m = meta.cpu().numpy()
     n_tok = int(m[256:258].view(np.int64)[0])
@@ -430,8 +430,16 @@ def test_zero_run_tokens_match_reference_and_invert(eng, torch, n, density):
     np.testing.assert_array_equal(got, ref)
     np.testing.assert_array_equal(m[:256].astype(np.int64), np.bincount(ref, minlength=256))
     back = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
-    N.check(eng.lib.lc_rle_expand(tok.data_ptr(), n_tok, back.data_ptr(), n, ws.data_ptr(), None), "lc_rle_expand")
+    N.check(eng.lib.lc_rle_expand(tok.data_ptr(), n_tok, 0, 243, back.data_ptr(), n, ws.data_ptr(), None), "lc_rle_expand")
     np.testing.assert_array_equal(back.cpu().numpy(), b)
+    # the code-stream parameters: runs of symbol 1, tokens 250..254 (same kernels)
+    c = np.where(b == 0, 1, np.where(b == 1, 2, np.minimum(b, 200))).astype(np.uint8)
+    N.check(eng.lib.lc_rle_tokens(dev(torch, c).data_ptr(), n, 1, 250, tok.data_ptr(), C.c_void_p(meta.data_ptr() + 1024),
+                                  meta.data_ptr(), ws.data_ptr(), None), "lc_rle_tokens")
+    n_tok2 = int(meta.cpu().numpy()[256:258].view(np.int64)[0])
+    assert n_tok2 == n_tok
+    N.check(eng.lib.lc_rle_expand(tok.data_ptr(), n_tok2, 1, 250, back.data_ptr(), n, ws.data_ptr(), None), "lc_rle_expand")
+    np.testing.assert_array_equal(back.cpu().numpy(), c)
 
 
 def test_sparse_mask_uses_zero_run_tokens_and_roundtrips(eng, torch):
@@ -450,8 +458,53 @@ def test_sparse_mask_uses_zero_run_tokens_and_roundtrips(eng, torch):
     assert len(comp_mask) < n // 40 // 4            # far below the one-bit-per-byte floor of the plain stream
     assert np.array_equal(eng.unpack_mask(comp_mask).cpu().numpy(), mask)
     assert np.array_equal(eng.unpack_codes(comp_error).cpu().numpy(), q)
+    # codes that are almost all 1 (with a few larger ones and an escape) also switch to run tokens
+    q2 = np.ones(300_000, dtype=np.int32)
+    q2[rng.integers(0, q2.size, 900)] = rng.integers(2, 6, 900)
+    q2[12345] = 100000
+    m2 = np.zeros(n, dtype=np.int8); m2[:q2.size] = 1
+    ce2, cm2 = eng.pack_streams(dev(torch, m2), dev(torch, q2))
+    meta2 = json.loads(ce2[16:16 + struct.unpack("<I", ce2[4:8])[0]])
+    assert meta2.get("rle") == 1 and len(ce2) < q2.size // 8 // 3
+    assert np.array_equal(eng.unpack_codes(ce2).cpu().numpy(), q2)
+    assert np.array_equal(eng.unpack_mask(cm2).cpu().numpy(), m2)
     dense = np.where(rng.random(n) < 0.3, rng.integers(1, 3, n), 0).astype(np.int8)
     qd = rng.integers(1, 9, int((dense > 0).sum())).astype(np.int32)
     ce, cm = eng.pack_streams(dev(torch, dense), dev(torch, qd))
     assert "rle" not in json.loads(cm[16:16 + struct.unpack("<I", cm[4:8])[0]])
     assert np.array_equal(eng.unpack_mask(cm).cpu().numpy(), dense)
+
+
+def test_latent_f16_codec_roundtrip_and_join(torch):
+    """Default codec of the 16-bit engines: the latent is rounded to half precision in place (so compressor and
+    decompressor decode the same values), stored as a raw low byte plane + a Huffman-coded high byte plane; shard
+    containers join into one."""
+    import json
+    import struct
+    from lossycomp._engine import Engine
+    from lossycomp.compress import compress_device
+    from lossycomp.decompress import decompress_device
+    from oracle import lossycomp_oracle as O
+    e16 = Engine.get(None, "fp16", 0)
+    x = dev(torch, O.synthetic_field(32, 100, 150, seed=3))
+    slots, info = compress_device(e16, x, 0.05, return_parts=True)
+    blob = slots[0]
+    meta = json.loads(blob[8:8 + struct.unpack("<I", blob[4:8])[0]])
+    assert meta["codec"] == "f16" and meta["n"] == info["latent"].numel()
+    assert len(blob) < 0.45 * 4 * info["latent"].numel()                 # < half of fp32 (2 bytes, high plane coded)
+    lat, _ = e16.unpack_latent(blob, slots[1])
+    assert torch.equal(lat, info["latent"])                              # exactly the values the compressor decoded
+    assert torch.equal(lat, lat.half().float())                          # i.e. half-precision numbers
+    xhat = decompress_device(e16, slots)
+    assert e16.verify(x, xhat, 0.05)[0] == 0
+    # raw codec on request; join of two shard containers == container of the concatenation
+    raw_slots, _ = compress_device(e16, x, 0.05, latent_codec="raw")
+    assert len(raw_slots[0]) > 4 * info["latent"].numel()
+    half = lat.shape[0] // 2
+    parts = []
+    for part in (lat[:half], lat[half:]):
+        p = part.contiguous().clone()
+        parts.append(e16.pack_latent_f16(*e16.quantize_latent(p)))
+    joined = e16.join_latents(parts)
+    back, _ = e16.unpack_latent(joined, slots[1])
+    assert torch.equal(back, lat)
