@@ -207,6 +207,10 @@ size_t lc_huff_workspace_bytes(int64_t n, int seg);
 int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d_code, const uint8_t* d_len,
                    int seg, uint8_t* d_out, unsigned long long* d_seg_bits,
                    unsigned long long* d_total_bits, void* d_ws, void* stream);
+/* Host only: the decode-side arrays lc_huff_decode consumes, from a table as lc_huff_build_table (or a blob header)
+ * gives it.  lut: 2^lut_bits entries; tree: up to 1022 int32; *n_tree = entries written. */
+int lc_huff_build_decode(const uint32_t* code, const uint8_t* len, const uint8_t* used, int lut_bits, uint16_t* lut,
+                         int32_t* tree, int* n_tree);
 /* Decode: d_lut is a 2^lut_bits table of (len << 8 | sym) for codes no longer than lut_bits;
  * longer codes walk d_tree (node = {child0, child1}, leaves are ~sym). */
 int lc_huff_decode(const uint8_t* d_bits, int64_t n, int seg, const unsigned long long* d_seg_bits,

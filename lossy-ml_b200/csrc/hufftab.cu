@@ -86,3 +86,53 @@ extern "C" int lc_huff_build_table(const int64_t* hist, int max_bits, uint32_t* 
   LC_REQUIRE(false, "could not cap the code length");
   return LC_OK;
 }
+
+// Decode-side arrays of a prefix code (what lc_huff_decode consumes): a 2^lut_bits direct table of (len << 8 | sym)
+// for codes no longer than lut_bits, and a binary tree (node = {child0, child1}, leaves are ~sym, 0 = absent) that
+// holds every code.  A one-symbol alphabet (empty code) is the tree {~sym, ~sym}.  Returns the number of int32
+// entries written to `tree` (<= 2 * 511) through n_tree.
+extern "C" int lc_huff_build_decode(const uint32_t* code, const uint8_t* len, const uint8_t* used, int lut_bits,
+                                    uint16_t* lut, int32_t* tree, int* n_tree) {
+  LC_REQUIRE(code && len && used && lut && tree && n_tree, "null argument");
+  LC_REQUIRE(lut_bits >= 1 && lut_bits <= 16, "lut_bits must be in 1..16");
+  for (int i = 0; i < (1 << lut_bits); ++i) lut[i] = 0;
+  int n_used = 0, only = 0;
+  for (int s = 0; s < kMaxSyms; ++s)
+    if (used[s]) { ++n_used; only = s; }
+  if (n_used <= 1) {
+    tree[0] = ~only;
+    tree[1] = ~only;
+    *n_tree = 2;
+    return LC_OK;
+  }
+  int nodes = 1;
+  tree[0] = 0;
+  tree[1] = 0;
+  for (int s = 0; s < kMaxSyms; ++s) {
+    if (!used[s]) continue;
+    const int L = len[s];
+    LC_REQUIRE(L >= 1 && L <= 32, "code length out of range");
+    const uint32_t c = code[s];
+    if (L <= lut_bits) {
+      const uint32_t base = c << (lut_bits - L);
+      for (uint32_t k = 0; k < (1u << (lut_bits - L)); ++k) lut[base + k] = (uint16_t)((L << 8) | s);
+    }
+    int node = 0;
+    for (int i = 0; i < L; ++i) {
+      const int bit = (int)((c >> (L - 1 - i)) & 1u);
+      if (i == L - 1) {
+        tree[2 * node + bit] = ~s;
+      } else {
+        if (tree[2 * node + bit] <= 0) {
+          LC_REQUIRE(nodes < 2 * kMaxSyms, "not a prefix code");
+          tree[2 * nodes] = 0;
+          tree[2 * nodes + 1] = 0;
+          tree[2 * node + bit] = nodes++;
+        }
+        node = tree[2 * node + bit];
+      }
+    }
+  }
+  *n_tree = 2 * nodes;
+  return LC_OK;
+}

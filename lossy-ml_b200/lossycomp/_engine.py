@@ -303,21 +303,55 @@ class Engine:
             np.zeros(0, np.uint16)
         return payload, lens, got_bits
 
-    def huff_unpack(self, payload: bytes, n: int, seg_lens: np.ndarray, table: HF.Table):
+    def _stage_ring(self, nbytes):
+        """A pinned staging buffer that is safe to overwrite: a ring of four, each guarded by the event recorded
+        after its last host->device copy."""
+        t = self.torch
+        ring = self._small.setdefault("stage_ring", [])
+        i = self._small["stage_next"] = (self._small.get("stage_next", -1) + 1) % 4
+        while len(ring) <= i:
+            ring.append([None, None])
+        buf, ev = ring[i]
+        if ev is not None:
+            ev.synchronize()
+        if buf is None or buf.numel() < nbytes:
+            buf = t.empty(max(int(nbytes * 1.25), 1 << 16), dtype=t.uint8, pin_memory=True)
+        ring[i] = [buf, None]
+        return buf, ring[i]
+
+    def huff_unpack(self, payload, n: int, seg_lens: np.ndarray, table: HF.Table):
+        """Huffman bits (bytes-like) -> n uint8 symbols on the device.  Payload, segment offsets and the decode
+        tables travel in ONE pinned staging buffer and one asynchronous copy."""
         t = self.torch
         sym = t.empty(n, dtype=t.uint8, device=self.dev)
         if n == 0:
             return sym
-        bits = t.zeros(((len(payload) + 3) // 4) * 4 + 16, dtype=t.uint8, device=self.dev)
-        if payload:
-            bits[:len(payload)] = t.frombuffer(bytearray(payload), dtype=t.uint8).to(self.dev)
-        offs = np.concatenate(([0], np.cumsum(seg_lens.astype(np.int64))[:-1])).astype(np.int64)
-        segb = t.from_numpy(offs).to(self.dev)
-        lut, tree = table.decode_arrays()
-        d_lut = t.from_numpy(lut.view(np.int16).copy()).to(self.dev)
-        d_tree = t.from_numpy(tree.copy()).to(self.dev)
-        N.check(self.lib.lc_huff_decode(_ptr(bits), n, SEG, _ptr(segb), _ptr(d_lut), HF.LUT_BITS,
-                                        _ptr(d_tree), _ptr(sym), self._stream()), "lc_huff_decode")
+        npay = len(payload)
+        pay_cap = ((npay + 3) // 4) * 4 + 16                      # the decoder reads whole words past the end
+        offs = np.zeros(max(seg_lens.size, 1), dtype=np.int64)
+        if seg_lens.size > 1:
+            np.cumsum(seg_lens[:-1], dtype=np.int64, out=offs[1:])
+        lut, tree = table.decode_arrays_native()
+        o_seg = (pay_cap + 7) & ~7
+        o_lut = o_seg + 8 * offs.size
+        o_tree = (o_lut + 2 * lut.size + 3) & ~3
+        total = o_tree + 4 * tree.size
+        host, slot = self._stage_ring(total)
+        hv = host.numpy()
+        if npay:
+            hv[:npay] = np.frombuffer(payload, dtype=np.uint8)
+        hv[npay:pay_cap] = 0
+        hv[o_seg:o_lut] = offs.view(np.uint8)
+        hv[o_lut:o_lut + 2 * lut.size] = lut.view(np.uint8)
+        hv[o_tree:total] = tree.view(np.uint8)
+        dbuf = t.empty(total, dtype=t.uint8, device=self.dev)
+        dbuf.copy_(host[:total], non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record(t.cuda.current_stream(self.dev))
+        slot[1] = ev
+        base = dbuf.data_ptr()
+        N.check(self.lib.lc_huff_decode(C.c_void_p(base), n, SEG, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
+                                        HF.LUT_BITS, C.c_void_p(base + o_tree), _ptr(sym), self._stream()), "lc_huff_decode")
         self.launches += 1
         return sym
 
@@ -335,15 +369,15 @@ class Engine:
         return b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), lens.size), mj, tb,
                          lens.tobytes(), payload])
 
-    def unpack_stream(self, blob: bytes):
-        assert blob[:4] == HUFF_MAGIC
-        lm, ltb, nl = struct.unpack("<III", blob[4:16])
+    def unpack_stream(self, blob):
+        mv = memoryview(blob)
+        assert bytes(mv[:4]) == HUFF_MAGIC
+        lm, ltb, nl = struct.unpack("<III", mv[4:16])
         p = 16
-        meta = json.loads(blob[p:p + lm]); p += lm
-        table, _ = HF.Table.from_bytes(blob[p:p + ltb]); p += ltb
-        lens = np.frombuffer(blob, dtype=np.uint16, count=nl, offset=p); p += 2 * nl
-        payload = blob[p:]
-        sym = self.huff_unpack(payload, meta["n"], lens, table)
+        meta = json.loads(bytes(mv[p:p + lm])); p += lm
+        table, _ = HF.Table.from_bytes(mv[p:p + ltb]); p += ltb
+        lens = np.frombuffer(mv, dtype=np.uint16, count=nl, offset=p); p += 2 * nl
+        sym = self.huff_unpack(mv[p:], meta["n"], lens, table)      # a view: the payload is copied once, into pinned memory
         return sym, meta
 
     def pack_mask(self, mask) -> bytes:
@@ -415,7 +449,8 @@ class Engine:
         lm = struct.unpack("<I", blob[4:8])[0]
         meta = json.loads(blob[16:16 + lm])
         ne = meta["n_esc"]
-        body, escb = (blob[:len(blob) - 4 * ne], blob[len(blob) - 4 * ne:]) if ne else (blob, b"")
+        mv = memoryview(blob)
+        body, escb = (mv[:len(mv) - 4 * ne], mv[len(mv) - 4 * ne:]) if ne else (mv, b"")
         sym, meta = self.unpack_stream(body)
         n = meta["n"]
         if meta.get("rle"):                  # run tokens -> code symbols

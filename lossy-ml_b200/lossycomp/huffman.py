@@ -132,6 +132,19 @@ class Table:
                     node = nodes[node][bi]
         return lut, np.array(nodes, dtype=np.int32).reshape(-1)
 
+    def decode_arrays_native(self, lut_bits: int = LUT_BITS):
+        """decode_arrays() through the library's host entry point lc_huff_build_decode (same arrays)."""
+        import ctypes as C
+
+        from . import _native as N
+        lut = np.empty(1 << lut_bits, dtype=np.uint16)
+        tree = np.empty(1022, dtype=np.int32)
+        used = self.used.astype(np.uint8)
+        n = C.c_int(0)
+        N.check(N.lib().lc_huff_build_decode(self.code.ctypes.data, self.len.ctypes.data, used.ctypes.data, lut_bits,
+                                             lut.ctypes.data, tree.ctypes.data, C.byref(n)), "lc_huff_build_decode")
+        return lut, tree[:n.value]
+
     # -- serialisation (explicit codes: the tree is not canonical) -----------
     _REC = np.dtype([("s", "u1"), ("l", "u1"), ("c", "<u4")])
 
@@ -142,16 +155,10 @@ class Table:
         return bytes([syms.size & 0xFF, syms.size >> 8]) + rec.tobytes()
 
     @staticmethod
-    def from_bytes(b: bytes) -> Tuple["Table", int]:
+    def from_bytes(b) -> Tuple["Table", int]:
         n = b[0] | (b[1] << 8)
-        codes = {}
-        p = 2
-        for _ in range(n):
-            s, L = b[p], b[p + 1]
-            c = int.from_bytes(b[p + 2:p + 6], "little")
-            codes[s] = format(c, "b").zfill(L) if L else ""
-            p += 6
-        return Table(codes, False), p
+        rec = np.frombuffer(b, dtype=Table._REC, count=n, offset=2)
+        return Table(arrays=(rec["s"].astype(np.int64), rec["c"], rec["l"])), 2 + 6 * n
 
     def encoded_bits(self, hist) -> int:
         return int((np.asarray(hist, dtype=np.int64) * self.len.astype(np.int64)).sum())
