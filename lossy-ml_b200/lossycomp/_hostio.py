@@ -31,11 +31,27 @@ def _bounds(n, parts):
     return [(a, min(a + step, n)) for a in range(0, n, step)]
 
 
-def d2h(eng, t_dev, shape, out=None):
+def prefault(shape):
+    """Allocate the result array and start touching its pages in the thread pool (one write per 4 KB page).  Called
+    before the device work of decompress() so that the first-touch page faults of the 100 MB result are taken while
+    the GPU decodes; pass the returned (array, futures) to d2h()."""
+    host = np.empty(shape, dtype=np.float32)
+    flat = host.reshape(-1)
+    jobs = [_threads().submit(_touch, flat[a:b]) for a, b in _bounds(flat.size, _SLICES)]
+    return host, jobs
+
+
+def _touch(part):
+    part[::1024] = 0.0
+
+
+def d2h(eng, t_dev, shape, out=None, wait=()):
     """Device float32 tensor -> numpy float32 array of `shape` (`out` if given, else freshly allocated)."""
     torch = eng.torch
     n = t_dev.numel()
     src = t_dev.reshape(-1)
+    for j in wait:
+        j.result()
     if out is not None:
         assert out.dtype == np.float32 and out.size == n and out.flags.c_contiguous, \
             "out must be a C-contiguous float32 array of the field's size"

@@ -74,11 +74,14 @@ def decompress(compressed_data, verbose=False, *, precision=None, model=None, de
         except Exception:
             precision = None
     eng = Engine.get(model, precision, device)
-    dev_out = decompress_device(eng, slots)
     T, H, W = (int(v) for v in slots[2][:3])
+    pending = ()
+    if out is None:            # fresh result: its page faults are taken by the thread pool while the GPU decodes
+        out, pending = _hostio.prefault((T, H, W, 1))
+    dev_out = decompress_device(eng, slots)
     if verbose:
         print("Done.")
-    return _hostio.d2h(eng, dev_out, (T, H, W, 1), out=out)                          # decompress.py:104-108
+    return _hostio.d2h(eng, dev_out, (T, H, W, 1), out=out, wait=pending)            # decompress.py:104-108
 
 
 def _peek_precision(comp_data: bytes):
