@@ -191,7 +191,7 @@ int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, int run_sym, int run_firs
                   void* d_ws, void* stream);
 
 /* Huffman bit packing from a host-built table: code[s] (right-aligned, MSB of the code is
- * emitted first) and len[s] (0..32).  The stream is cut into segments of `seg` (= 1024) symbols; each
+ * emitted first) and len[s] (0..32).  The stream is cut into segments of `seg` symbols (a power of two, 64..4096); each
  * segment starts at the bit offset d_seg_bits[i] (uint64, exclusive scan written by the call),
  * bits are big-endian within bytes exactly like the '0101..' strings of huffman.py.
  * d_total_bits receives the stream length in bits.  d_out must be zero-initialised and hold

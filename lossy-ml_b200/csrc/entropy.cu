@@ -271,17 +271,17 @@ unsymbolize_kernel(const uint8_t* __restrict__ sym, long long n, int bias, int e
 }
 
 // ---------------------------------------------------------------- Huffman pack
-// one tile = kThreads threads x 16 consecutive symbols = kThreads/64 independently decodable segments of kSeg symbols
+// one tile = kThreads threads x 16 consecutive symbols, cut into independently decodable segments of `seg`
+// symbols (a power of two between 64 and the tile: 1024 for the large streams, 256 for the small latent plane
+// whose decoding sits on decompress()'s critical path -- one thread decodes one segment)
 constexpr int kSegItems = 16;
 constexpr int kTileSyms = kThreads * kSegItems;
-constexpr int kSeg = 1024;                        // symbols per segment (64 threads)
-constexpr int kSegPerTile = kTileSyms / kSeg;
 
 __global__ void __launch_bounds__(kThreads)
 huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t* __restrict__ code,
                    const uint8_t* __restrict__ len, uint32_t* __restrict__ out,
                    unsigned long long* __restrict__ seg_bits, unsigned long long* __restrict__ total_bits,
-                   unsigned long long* ws) {
+                   unsigned long long* ws, int seg_threads) {
   __shared__ uint32_t s_code[256];
   __shared__ uint8_t s_len[256];
   if (threadIdx.x < 256) {
@@ -306,8 +306,8 @@ huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t*
   int total;
   const int texcl = block_exclusive<int>(bits, total);
   const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);
-  if ((threadIdx.x & (kSeg / kSegItems - 1)) == 0 && i0 < n)
-    seg_bits[(long long)tile * kSegPerTile + threadIdx.x / (kSeg / kSegItems)] = base + (unsigned long long)texcl;
+  if ((threadIdx.x & (seg_threads - 1)) == 0 && i0 < n)
+    seg_bits[(long long)tile * (kThreads / seg_threads) + threadIdx.x / seg_threads] = base + (unsigned long long)texcl;
   if (threadIdx.x == 0 && (long long)(tile + 1) * kTileSyms >= n) *total_bits = base + (unsigned long long)total;
   // emit: big-endian bit order within the byte stream == big-endian within 32-bit words that are
   // byte-swapped on store.  Accumulate into a 64-bit window and flush 32 bits at a time.
@@ -527,7 +527,7 @@ extern "C" int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d
                               int seg, uint8_t* d_out, unsigned long long* d_seg_bits,
                               unsigned long long* d_total_bits, void* d_ws, void* stream) {
   LC_REQUIRE(d_total_bits && d_ws, "null argument");
-  LC_REQUIRE(seg == kSeg, "segment length must be 1024 symbols");
+  LC_REQUIRE(seg >= 64 && seg <= kTileSyms && (seg & (seg - 1)) == 0, "segment length must be a power of two in 64..4096");
   cudaStream_t s = as_stream(stream);
   LC_CUDA(cudaMemsetAsync(d_total_bits, 0, sizeof(unsigned long long), s));
   if (n <= 0) return LC_OK;
@@ -538,7 +538,7 @@ extern "C" int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d
   huff_encode_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, d_code, d_len,
                                                        reinterpret_cast<uint32_t*>(d_out), d_seg_bits,
                                                        d_total_bits,
-                                                       reinterpret_cast<unsigned long long*>(d_ws));
+                                                       reinterpret_cast<unsigned long long*>(d_ws), seg / kSegItems);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

@@ -26,6 +26,7 @@ DEFAULT_PRECISION = "fp16"
 LATENT_MAGIC = b"LCL1"
 HUFF_MAGIC = b"LCH1"
 SEG = 1024                      # symbols per independently decodable Huffman segment
+LATENT_SEG = 256                # ... of the small latent plane, decoded on decompress()'s critical path
 ESC = 255                       # escape symbol of the code stream
 MASK_RUN = (0, 243)             # run tokens of the mask stream: runs of byte 0, tokens 243..247
 CODE_RUN = (1, 250)             # run tokens of the code stream: runs of code 1 (undifferenced), tokens 250..254
@@ -132,6 +133,13 @@ class Engine:
     # -- buffers ---------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def side_stream(self):
+        """Second stream of this engine (latent packing behind the decoder, entropy decoding beside it)."""
+        side = self._small.get("side_stream")
+        if side is None:
+            side = self._small["side_stream"] = self.torch.cuda.Stream(device=self.dev)
+        return side
 
     def _ae_ws(self, n_chunks):
         if self._ws is None or self._ws_chunks < n_chunks:
@@ -319,7 +327,7 @@ class Engine:
         ring[i] = [buf, None]
         return buf, ring[i]
 
-    def huff_unpack(self, payload, n: int, seg_lens: np.ndarray, table: HF.Table):
+    def huff_unpack(self, payload, n: int, seg_lens: np.ndarray, table: HF.Table, seg: int = SEG):
         """Huffman bits (bytes-like) -> n uint8 symbols on the device.  Payload, segment offsets and the decode
         tables travel in ONE pinned staging buffer and one asynchronous copy."""
         t = self.torch
@@ -350,7 +358,7 @@ class Engine:
         ev.record(t.cuda.current_stream(self.dev))
         slot[1] = ev
         base = dbuf.data_ptr()
-        N.check(self.lib.lc_huff_decode(C.c_void_p(base), n, SEG, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
+        N.check(self.lib.lc_huff_decode(C.c_void_p(base), n, seg, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
                                         HF.LUT_BITS, C.c_void_p(base + o_tree), _ptr(sym), self._stream()), "lc_huff_decode")
         self.launches += 1
         return sym
@@ -377,7 +385,7 @@ class Engine:
         meta = json.loads(bytes(mv[p:p + lm])); p += lm
         table, _ = HF.Table.from_bytes(mv[p:p + ltb]); p += ltb
         lens = np.frombuffer(mv, dtype=np.uint16, count=nl, offset=p); p += 2 * nl
-        sym = self.huff_unpack(mv[p:], meta["n"], lens, table)      # a view: the payload is copied once, into pinned memory
+        sym = self.huff_unpack(mv[p:], meta["n"], lens, table, int(meta.get("seg", SEG)))   # payload copied once, into pinned memory
         return sym, meta
 
     def pack_mask(self, mask) -> bytes:
@@ -479,27 +487,27 @@ class Engine:
             self._small["pin_" + name] = b
         return b
 
-    def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str, extra: dict, tail_len: int = 0):
+    def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str, extra: dict, tail_len: int = 0, seg: int = SEG):
         """Enqueue the Huffman packing of `sym` (no sync) and allocate the finished 'LCH1' container as one
         uninitialised bytes object: everything but the segment lengths, the payload and the tail is known now."""
         t = self.torch
         n = sym.numel()
-        nseg = (n + SEG - 1) // SEG
+        nseg = (n + seg - 1) // seg
         cap = ((bits + 31) // 32) * 4 + 16
         out = t.zeros(cap, dtype=t.uint8, device=self.dev)
         segb = t.empty(max(nseg, 1) + 1, dtype=t.int64, device=self.dev)
         tab = np.concatenate((table.code.view(np.uint8), table.len))            # 1024 + 256 bytes, one H2D
         d_tab = t.from_numpy(tab.copy()).to(self.dev, non_blocking=True)
-        ws = self._buf("scan_" + tag, self.lib.lc_huff_workspace_bytes(n, SEG))
+        ws = self._buf("scan_" + tag, self.lib.lc_huff_workspace_bytes(n, seg))
         N.check(self.lib.lc_huff_encode(_ptr(sym), n, C.c_void_p(d_tab.data_ptr()),
-                                        C.c_void_p(d_tab.data_ptr() + 1024), SEG, _ptr(out), _ptr(segb),
+                                        C.c_void_p(d_tab.data_ptr() + 1024), seg, _ptr(out), _ptr(segb),
                                         C.c_void_p(segb.data_ptr() + 8 * max(nseg, 1)), _ptr(ws), self._stream()),
                 "lc_huff_encode")
         self.launches += 1
         nbytes = (bits + 7) // 8
         h_seg = self._pinned("seg_" + tag, 8 * (nseg + 1))
         h_seg[:8 * (nseg + 1)].copy_(segb[:nseg + 1].view(t.uint8), non_blocking=True)
-        meta = dict(extra, n=int(n), seg=SEG, bits=int(bits), ref_tree=bool(table.reference_tree))
+        meta = dict(extra, n=int(n), seg=seg, bits=int(bits), ref_tree=bool(table.reference_tree))
         mj = json.dumps(meta).encode()
         tb = table.to_bytes()
         head = b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), nseg), mj, tb])
@@ -581,8 +589,9 @@ class Engine:
         tab_q, hist_q = tabs_q[pick], hists_q[pick]
         code_extra = {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne}
         # Large abs_error: nearly every code is 1 and the one-bit floor of the Huffman code dominates the slot.
-        # Fold runs of 1 into run tokens (one more host sync, taken only in this regime) when that is shorter.
-        if pick == 0 and hist_q[CODE_RUN[0]] > 0.55 * n_q and not hist_q[CODE_RUN[1]:CODE_RUN[1] + 5].any():
+        # Fold runs of 1 into run tokens (one more host sync, taken only when three codes in four are 1: below that
+        # the tokens gain ~2 % of the slot at best) when that is shorter.
+        if pick == 0 and hist_q[CODE_RUN[0]] > 0.75 * n_q and not hist_q[CODE_RUN[1]:CODE_RUN[1] + 5].any():
             tok_q = t.empty(n_q, dtype=t.uint8, device=self.dev)
             ht = t.empty(258, dtype=t.int32, device=self.dev)
             ws_q = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(n_q))
@@ -657,9 +666,7 @@ class Engine:
         enqueued: only the side stream is synchronised, so the two host syncs of the Huffman stage hide behind
         the decoder's kernels."""
         t = self.torch
-        side = self._small.get("side_stream")
-        if side is None:
-            side = self._small["side_stream"] = t.cuda.Stream(device=self.dev)
+        side = self.side_stream()
         side.wait_event(ev)
         lo.record_stream(side)
         hi.record_stream(side)
@@ -672,7 +679,7 @@ class Engine:
             h_lo[:n].copy_(lo, non_blocking=True)
             hist = h.cpu().numpy().astype(np.int64) & 0xFFFFFFFF                  # syncs the side stream only
             table = HF.build_table_native(hist)
-            job = self._launch_pack(hi, table, table.encoded_bits(hist), "lat", {"kind": "latent_hi"})
+            job = self._launch_pack(hi, table, table.encoded_bits(hist), "lat", {"kind": "latent_hi"}, seg=LATENT_SEG)
             self._collect_pack(job)
             side.synchronize()
             hi_container = self._finish_pack(job)
