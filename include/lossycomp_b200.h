@@ -182,11 +182,11 @@ int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* strea
  * the token run_first + k, every other byte (a single run_sym included) stays a literal.  Runs do not cross
  * 32-byte segments and are decomposed largest power of two first.  The stream must not contain the bytes
  * run_first .. run_first+4 (the caller checks its histogram).  Mask bytes: run_sym 0, run_first 243; code symbols:
- * run_sym 1, run_first 250.  lc_rle_tokens writes the tokens (at most n), their count and their 256-bin
- * histogram; lc_rle_expand is the inverse (d_sym: n bytes).  d_ws: lc_rle_workspace_bytes(n). */
+ * run_sym 1, run_first 250.  lc_rle_tokens writes the tokens (at most n), their count, their 256-bin histogram
+ * and, when d_hist_in is not NULL, the histogram of the input bytes (same pass); lc_rle_expand is the inverse (d_sym: n bytes).  d_ws: lc_rle_workspace_bytes(n). */
 size_t lc_rle_workspace_bytes(int64_t n);
 int lc_rle_tokens(const uint8_t* d_sym, int64_t n, int run_sym, int run_first, uint8_t* d_tok,
-                  unsigned long long* d_n_tok, uint32_t* d_hist, void* d_ws, void* stream);
+                  unsigned long long* d_n_tok, uint32_t* d_hist, uint32_t* d_hist_in, void* d_ws, void* stream);
 int lc_rle_expand(const uint8_t* d_tok, int64_t n_tok, int run_sym, int run_first, uint8_t* d_sym, int64_t n,
                   void* d_ws, void* stream);
 

@@ -118,10 +118,10 @@ constexpr int kRleTile = kThreads * kRleSeg;       // 8192 bytes per block
 __global__ void __launch_bounds__(kThreads)
 rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, int run_sym, int run_first,
                   uint8_t* __restrict__ tok, unsigned long long* __restrict__ n_tok, uint32_t* __restrict__ hist,
-                  unsigned long long* ws) {
+                  uint32_t* __restrict__ hist_in, unsigned long long* ws) {
   __shared__ uint8_t s_tok[kRleTile];
-  __shared__ uint32_t s_hist[256];
-  if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+  __shared__ uint32_t s_hist[256], s_hin[256];
+  if (threadIdx.x < 256) { s_hist[threadIdx.x] = 0; s_hin[threadIdx.x] = 0; }
   const int tile = take_ticket(ws);   // contains a __syncthreads
   const long long i0 = (long long)tile * kRleTile + (long long)threadIdx.x * kRleSeg;
   uint8_t b[kRleSeg];
@@ -163,6 +163,17 @@ rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, int run_sym, int
       }
     }
   }
+  if (hist_in) {
+    // histogram of the input bytes in the same pass (the plain-coding candidate's table needs it): the run symbol
+    // is counted per warp, the rest per byte
+    int runs = __popc(~nz);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) runs += __shfl_xor_sync(0xffffffffu, runs, o);
+    if ((threadIdx.x & 31) == 0 && runs) atomicAdd(&s_hin[run_sym], (unsigned)runs);
+#pragma unroll
+    for (int k = 0; k < kRleSeg; ++k)
+      if (k < len && b[k] != run_sym) atomicAdd(&s_hin[b[k]], 1u);
+  }
   const int cnt = __popc(start);
   int total;
   const int texcl = block_exclusive<int>(cnt, total);
@@ -178,6 +189,7 @@ rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, int run_sym, int
   const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);   // contains a __syncthreads
   for (int i = threadIdx.x; i < total; i += kThreads) tok[base + i] = s_tok[i];
   if (threadIdx.x < 256 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (hist_in && threadIdx.x < 256 && s_hin[threadIdx.x]) atomicAdd(&hist_in[threadIdx.x], s_hin[threadIdx.x]);
   if ((long long)(tile + 1) * kRleTile >= n && threadIdx.x == 0) *n_tok = base + (unsigned long long)total;
 }
 
@@ -453,7 +465,8 @@ extern "C" size_t lc_rle_workspace_bytes(int64_t n) {
 }
 
 extern "C" int lc_rle_tokens(const uint8_t* d_sym, int64_t n, int run_sym, int run_first, uint8_t* d_tok,
-                             unsigned long long* d_n_tok, uint32_t* d_hist, void* d_ws, void* stream) {
+                             unsigned long long* d_n_tok, uint32_t* d_hist, uint32_t* d_hist_in, void* d_ws,
+                             void* stream) {
   LC_REQUIRE(d_sym && d_tok && d_n_tok && d_hist && d_ws, "null argument");
   LC_REQUIRE(n > 0, "empty input");
   LC_REQUIRE(run_sym >= 0 && run_sym < 256 && run_first >= 0 && run_first + 4 < 256 &&
@@ -463,7 +476,8 @@ extern "C" int lc_rle_tokens(const uint8_t* d_sym, int64_t n, int run_sym, int r
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
   LC_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint32_t), s));
   LC_CUDA(cudaMemsetAsync(d_n_tok, 0, sizeof(unsigned long long), s));
-  rle_tokens_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, run_sym, run_first, d_tok, d_n_tok, d_hist,
+  if (d_hist_in) LC_CUDA(cudaMemsetAsync(d_hist_in, 0, 256 * sizeof(uint32_t), s));
+  rle_tokens_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_sym, n, run_sym, run_first, d_tok, d_n_tok, d_hist, d_hist_in,
                                                       reinterpret_cast<unsigned long long*>(d_ws));
   LC_LAUNCH_CHECK();
   return LC_OK;

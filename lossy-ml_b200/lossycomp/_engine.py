@@ -551,16 +551,15 @@ class Engine:
         # histograms: [0:256] mask bytes, [256:768] the two code candidates, [768:1024] zero-run tokens of the mask,
         # [1024:1026] their count (uint64)
         h3 = t.empty(1026, dtype=t.int32, device=self.dev)
-        N.check(self.lib.lc_hist_u8(_ptr(sym_m), sym_m.numel(), _ptr(h3), self._stream()), "lc_hist_u8")
         cand = ((0, 0), (1, 127))
         N.check(self.lib.lc_hist_codes(_ptr(q), n_q, ESC, cand[0][1], cand[1][1],
                                        C.c_void_p(h3.data_ptr() + 1024), self._stream()), "lc_hist_codes")
         tok_m = t.empty(sym_m.numel(), dtype=t.uint8, device=self.dev)
         ws_r = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(sym_m.numel()))
         N.check(self.lib.lc_rle_tokens(_ptr(sym_m), sym_m.numel(), *MASK_RUN, _ptr(tok_m),
-                                       C.c_void_p(h3.data_ptr() + 4096), C.c_void_p(h3.data_ptr() + 3072), _ptr(ws_r),
-                                       self._stream()), "lc_rle_tokens")
-        self.launches += 4
+                                       C.c_void_p(h3.data_ptr() + 4096), C.c_void_p(h3.data_ptr() + 3072), _ptr(h3),
+                                       _ptr(ws_r), self._stream()), "lc_rle_tokens")     # also fills h3[0:256]
+        self.launches += 3
         hh = h3.cpu().numpy()                                                     # sync 1
         n_tok = int(hh[1024:1026].view(np.int64)[0])
         hh = hh[:1024].astype(np.int64) & 0xFFFFFFFF
@@ -596,7 +595,7 @@ class Engine:
             ht = t.empty(258, dtype=t.int32, device=self.dev)
             ws_q = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(n_q))
             N.check(self.lib.lc_rle_tokens(_ptr(sym_q), n_q, *CODE_RUN, _ptr(tok_q), C.c_void_p(ht.data_ptr() + 1024),
-                                           _ptr(ht), _ptr(ws_q), self._stream()), "lc_rle_tokens")
+                                           _ptr(ht), None, _ptr(ws_q), self._stream()), "lc_rle_tokens")
             self.launches += 1
             hv = ht.cpu().numpy()                                                 # sync (sparse regime only)
             n_tok = int(hv[256:258].view(np.int64)[0])

@@ -67,7 +67,7 @@ SIGNATURES = {
     "lc_pack_trits": (_i, [_p, _i64, _p, _p]),
     "lc_unpack_trits": (_i, [_p, _i64, _p, _p]),
     "lc_rle_workspace_bytes": (_sz, [_i64]),
-    "lc_rle_tokens": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
+    "lc_rle_tokens": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p, _p]),
     "lc_rle_expand": (_i, [_p, _i64, _i, _i, _p, _i64, _p, _p]),
     "lc_huff_build_table": (_i, [_p, _i, _p, _p, _p, _p]),
     "lc_huff_build_decode": (_i, [_p, _p, _p, _i, _p, _p, _p]),

@@ -421,8 +421,10 @@ def test_zero_run_tokens_match_reference_and_invert(eng, torch, n, density):
     meta = torch.zeros(258, dtype=torch.int32, device="cuda")           # [0:256] histogram, [256:258] count
     ws = torch.empty(eng.lib.lc_rle_workspace_bytes(n), dtype=torch.uint8, device="cuda")
     from lossycomp import _native as N
+    hin = torch.zeros(256, dtype=torch.int32, device="cuda")
     N.check(eng.lib.lc_rle_tokens(d_b.data_ptr(), n, 0, 243, tok.data_ptr(), C.c_void_p(meta.data_ptr() + 1024),
-                                  meta.data_ptr(), ws.data_ptr(), None), "lc_rle_tokens")
+                                  meta.data_ptr(), hin.data_ptr(), ws.data_ptr(), None), "lc_rle_tokens")
+    np.testing.assert_array_equal(hin.cpu().numpy().astype(np.int64), np.bincount(b, minlength=256))
     m = meta.cpu().numpy()
     n_tok = int(m[256:258].view(np.int64)[0])
     ref = _rle_tokens_reference(b)
@@ -435,7 +437,7 @@ def test_zero_run_tokens_match_reference_and_invert(eng, torch, n, density):
     # the code-stream parameters: runs of symbol 1, tokens 250..254 (same kernels)
     c = np.where(b == 0, 1, np.where(b == 1, 2, np.minimum(b, 200))).astype(np.uint8)
     N.check(eng.lib.lc_rle_tokens(dev(torch, c).data_ptr(), n, 1, 250, tok.data_ptr(), C.c_void_p(meta.data_ptr() + 1024),
-                                  meta.data_ptr(), ws.data_ptr(), None), "lc_rle_tokens")
+                                  meta.data_ptr(), None, ws.data_ptr(), None), "lc_rle_tokens")
     n_tok2 = int(meta.cpu().numpy()[256:258].view(np.int64)[0])
     assert n_tok2 == n_tok
     N.check(eng.lib.lc_rle_expand(tok.data_ptr(), n_tok2, 1, 250, back.data_ptr(), n, ws.data_ptr(), None), "lc_rle_expand")
