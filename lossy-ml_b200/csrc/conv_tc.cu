@@ -1,7 +1,7 @@
 // Tensor-core (tcgen05 / TMEM / bulk-async-copy) back end of the autoencoder, LC_PREC_BF16 and
 // LC_PREC_FP16 modes.
 //
-// Plane-sweep implicit GEMM.  Common idea of all four kernels:
+// Plane-sweep implicit GEMM.  Common idea of all five kernel modes:
 //   * activations are 16-bit group-plane tensors (act.cuh): a 128-voxel tile of one time plane is a
 //     128-row K-major UMMA operand, and an in-plane tap (dh,dw) is the same operand started
 //     (dh*PW+dw) vectors later -- no im2col, no swizzle, one 1-D bulk copy per channel-group plane;
@@ -13,18 +13,23 @@
 //     is undone by thread-local register accumulation (no cross-lane traffic, fixed order);
 //   * K steps pair 8-channel groups across taps through the descriptor's leading-byte-offset
 //     (k=3: 27 groups -> 14 MMAs per plane instead of 18 with channels padded to 32);
-//   * warp-specialised: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected thread),
-//     warps 2-5 = epilogue (TMEM -> registers -> bias/skip/ReLU -> stores); smem ring of input
-//     planes, double-buffered TMEM accumulators.
+//   * warp-specialised (352 threads): warp 0 = bulk-copy producer, warps 1 and 10 = MMA issuers taking alternate
+//     accumulators (the whole warp runs the loop so that every tcgen05.mma operand is uniform, one elected lane
+//     issues), warps 2-9 = epilogue (two per TMEM lane quarter, 12 channels each: TMEM -> registers -> ReLU /
+//     16-bit packing -> stores); smem ring of input planes, ring of 2-4 TMEM accumulators; two CTAs per SM
+//     except DOWN and UP.
 // Modes:
-//   K3    Conv3D k=3 s=1 (the ResBlock convs, 80 % of the FLOPs): 9 taps x 3 groups, N = 3x24(+8)
-//   K4    Conv3D k=4 s=1: first layer (input pre-folded along w by the chunk gather: 4 taps x
-//         ceil(4*Cin/8) groups, N = 4x24) and last layer (16 taps x 3 groups, cout=1, N = 16,
-//         fp32 output scattered straight into the merged field = dataLoader.merge_data fused)
-//   DOWN  Conv3D k=4 s=2 on a parity-split input (stride-2 taps become stride-1 taps of the four
-//         (h,w)-parity planes), N = 2x24, weights selected by the parity of t_in
-//   UP    Conv3DTranspose k=4 s=2: one work item per output (h,w)-parity class, 4 taps x 3 groups,
-//         N = 4x24 (the four kt), outputs written at (2j+ph, 2j+pw)
+//   K3       Conv3D k=3 s=1 (the ResBlock convs, 80 % of the FLOPs): 9 taps x 3 groups, N = 3x24(+8); with a
+//            residual input, three more K groups multiply the skip tile by identity weights (15 MMAs per plane)
+//   K4       Conv3D k=4 s=1, first layer: input pre-folded along w by the chunk gather (4 taps x ceil(4*Cin/8)
+//            groups, N = 4x24)
+//   K4_OUT1  Conv3D k=4 s=1, last layer (cout = 1): time and w taps folded into N = 16, 4 h-taps x 3 groups,
+//            fp32 output scattered straight into the merged field (= dataLoader.merge_data fused)
+//   DOWN     Conv3D k=4 s=2 on a parity-split input (stride-2 taps become stride-1 taps of the four (h,w)-parity
+//            planes), N = 2x24, weights selected by the parity of t_in
+//   UP       Conv3DTranspose k=4 s=2: item = (chunk, output-line parity, tile); both output-column parities in
+//            the same CTA (two accumulators per input plane, 4 taps x 3 groups, N = 4x24 = the four kt each),
+//            packed results transposed across lanes so that every store covers 32 consecutive output columns
 // Everything is deterministic: each output voxel is produced by exactly one thread in a fixed
 // accumulation order, independent of the item -> CTA mapping.
 #include "act.cuh"
@@ -1201,8 +1206,7 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   LC_CUDA(cudaMemcpy(L.d_wtc, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   L.wtc_bytes = img.size() * 2;
   p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
-  // opt-in: with two issuer warps the smem skip tile showed a rare stale read of plane 0 (under investigation);
-  // the prefetched global-load path is 3 % slower and bit-deterministic
+  // a stage = the input slabs of one plane (+ the skip tile when the residual add runs on the tensor core)
   const int stage_bytes = p.in_NPG * p.slab_slots * 16 + (p.skip_mma ? G * p.skip_slots * 16 : 0);
   // dynamic shared memory per CTA; the single-channel mode also holds a 17.6 KB static exchange tile
   const int budget = (ctas_per_sm(mode) == 2 ? (mode == MODE_K4_OUT1 ? 90 : 110) : 200) * 1024;

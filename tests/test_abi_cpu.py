@@ -129,3 +129,28 @@ def test_native_table_builder_equals_reference_mirror():
         back, _ = HF.Table.from_bytes(b.to_bytes())
         assert back.codes == b.codes
     assert not HF.build_table_native(deep).reference_tree and HF.build_table_native(deep).len.max() <= 32
+
+
+def test_native_decode_arrays_equal_python_builder():
+    """lc_huff_build_decode (host C) against Table.decode_arrays: same direct table and tree for random codes,
+    one-symbol alphabets and codes longer than the direct table."""
+    from lossycomp import huffman as HF
+    rng = np.random.default_rng(11)
+    hists = []
+    one = np.zeros(256, np.int64); one[17] = 3; hists.append(one)
+    fib = [1, 1]
+    while len(fib) < 40:
+        fib.append(fib[-1] + fib[-2])
+    deep = np.zeros(256, np.int64); deep[:40] = fib; hists.append(deep)          # code lengths up to 32 > LUT_BITS
+    for trial in range(200):
+        k = int(rng.integers(2, 257))
+        h = np.zeros(256, np.int64)
+        h[rng.choice(256, k, replace=False)] = [rng.integers(1, 5, k), rng.integers(1, 1 << 28, k),
+                                               (2.0 ** rng.uniform(0, 30, k)).astype(np.int64) + 1][trial % 3]
+        hists.append(h)
+    for h in hists:
+        t = HF.build_table_native(h)
+        a, b = t.decode_arrays(), t.decode_arrays_native()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        back, used = HF.Table.from_bytes(memoryview(t.to_bytes()))
+        assert used == len(t.to_bytes()) and np.array_equal(back.code, t.code) and np.array_equal(back.len, t.len)
