@@ -268,6 +268,15 @@ def run_ours(args):
         tms = torch.tensor([e2e_s], dtype=torch.float64, device=eng.dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e_s = float(tms.item())
+    # bulk-job variant: the same K calls through compress_stream(), which overlaps the H2D copy of field k+1 with
+    # the kernels of field k (every step still copies its 199 MB in and its blob out)
+    from lossycomp.compress import compress_stream
+    list(compress_stream([xh, xh], ABS_ERR, precision=args.precision, codec=args.codec))
+    barrier()
+    t0 = time.perf_counter()
+    n_stream = sum(1 for _ in compress_stream([xh] * args.steps, ABS_ERR, precision=args.precision, codec=args.codec))
+    torch.cuda.synchronize()
+    e2e_stream = (time.perf_counter() - t0) / max(n_stream, 1)
     xp = np.array(xh)                       # the same field in ordinary (pageable) memory
     compress(xp, ABS_ERR, precision=args.precision, codec=args.codec)
     t0 = time.perf_counter()
@@ -344,6 +353,7 @@ def run_ours(args):
         "e2e": {"value": world * in_bytes / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": in_bytes * 2,
                 "d2h_bytes_per_step": len(b), "ms_per_step": e2e_s * 1e3,
                 "pageable_input_GBps": in_bytes / e2e_pageable / 1e9,
+                "compress_stream_GBps": in_bytes / e2e_stream / 1e9,
                 "decompress_GBps": in_bytes / e2e_d / 1e9, "violations": e2e_viol},
         "decompress": {"value": dvalue, "unit": UNIT, "ms_per_step": dms / args.steps},
         "compression_factor": cf, "violations": viol, "max_abs_err": max_err,

@@ -510,3 +510,21 @@ def test_latent_f16_codec_roundtrip_and_join(torch):
     joined = e16.join_latents(parts)
     back, _ = e16.unpack_latent(joined, slots[1])
     assert torch.equal(back, lat)
+
+
+def test_compress_stream_equals_compress(torch):
+    """compress_stream() (H2D of field k+1 overlapped with the kernels of field k, double-buffered) yields exactly
+    the blobs of separate compress() calls, for pinned and pageable inputs and changing shapes."""
+    from lossycomp.compress import compress, compress_stream
+    from oracle import lossycomp_oracle as O
+    fields = [O.synthetic_field(16, 64, 80, seed=s) for s in (1, 2, 3)] + [O.synthetic_field(33, 50, 70, seed=4)]
+    pinned = []
+    for f in fields:
+        p = torch.empty(f.shape, dtype=torch.float32, pin_memory=True)
+        p.copy_(torch.from_numpy(f))
+        pinned.append(p.numpy())
+    want = [compress(f, 0.05) for f in fields]
+    assert list(compress_stream(pinned, 0.05)) == want
+    assert list(compress_stream(fields, 0.05)) == want              # pageable
+    assert list(compress_stream([], 0.05)) == []
+    assert list(compress_stream(pinned[:1], 0.05)) == want[:1]
