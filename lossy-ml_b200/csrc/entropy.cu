@@ -122,7 +122,8 @@ rle_tokens_kernel(const uint8_t* __restrict__ sym, long long n, int run_sym, int
   __shared__ uint8_t s_tok[kRleTile];
   __shared__ uint32_t s_hist[256], s_hin[256];
   if (threadIdx.x < 256) { s_hist[threadIdx.x] = 0; s_hin[threadIdx.x] = 0; }
-  const int tile = take_ticket(ws);   // contains a __syncthreads
+  __syncthreads();   // the shared tables above are read by every thread below
+  const int tile = take_ticket(ws);
   const long long i0 = (long long)tile * kRleTile + (long long)threadIdx.x * kRleSeg;
   uint8_t b[kRleSeg];
   int len = 0;                         // valid bytes of this thread's segment
@@ -300,7 +301,8 @@ huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t*
     s_code[threadIdx.x] = code[threadIdx.x];
     s_len[threadIdx.x] = len[threadIdx.x];
   }
-  const int tile = take_ticket(ws);   // contains a __syncthreads
+  __syncthreads();   // the shared tables above are read by every thread below
+  const int tile = take_ticket(ws);
   const long long i0 = (long long)tile * kTileSyms + (long long)threadIdx.x * kSegItems;
   uint8_t s[kSegItems];
   if (i0 + kSegItems <= n && (reinterpret_cast<uintptr_t>(sym) & 15) == 0) {
