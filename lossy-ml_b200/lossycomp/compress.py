@@ -11,8 +11,12 @@ TensorFlow and no CPU fallback.  Keyword-only extensions (defaults keep the refe
          |x - xhat| <= abs_err holds on every element after the float32 rounding of the final add
          (the reference itself exceeds it by <= 1/2 ulp); slot 8 = 2*thr'.
          "parity": exactly the reference arithmetic, slot 8 = 2*abs_err.
-  codec  "huff" (default): GPU Huffman containers in slots 6/7;  "bz2": the reference's bz2 level 9
-         of the first-differenced int32 / int8 streams (byte-identical slots 6/7 for identical codes).
+  codec  "huff" (default): GPU Huffman containers in slots 6/7 (run tokens first when one symbol dominates);
+         "bz2": the reference's bz2 level 9 of the first-differenced int32 / int8 streams (byte-identical
+         slots 6/7 for identical codes).
+Slot 0 (fpzip in the reference) is an 'LCL1' container: half-precision latent codes with a Huffman-coded high
+byte plane on the 16-bit engines (the decoder consumes the rounded latent on both sides), raw fp32 on the fp32
+engine, bz2 of the fp32 latent with codec="bz2".  compress_stream() is the bulk-job variant of compress().
 """
 from __future__ import annotations
 
