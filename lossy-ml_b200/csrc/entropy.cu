@@ -371,6 +371,7 @@ huff_decode_kernel(const uint32_t* __restrict__ words, long long n, int seg,
   const uint32_t* wp = words + (pos >> 5);
   unsigned long long buf = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
   wp += 2;
+  uint32_t ahead = *wp;                                  // next word, loaded one refill early (the stream has 16 spare bytes)
   int used = (int)(pos & 31);
   const long long i0 = sg * seg;
   const long long i1 = (i0 + seg < n) ? i0 + seg : n;
@@ -397,8 +398,9 @@ huff_decode_kernel(const uint32_t* __restrict__ words, long long n, int seg,
     }
     used += l;
     if (used >= 32) {
-      buf = (buf << 32) | __byte_perm(*wp++, 0, 0x0123);
+      buf = (buf << 32) | __byte_perm(ahead, 0, 0x0123);
       used -= 32;
+      ahead = *++wp;
     }
     const int k = (int)(i - i0) & 3;
     pack |= (uint32_t)s << (8 * k);

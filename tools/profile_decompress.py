@@ -18,4 +18,4 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 for i in range(10): y = decompress_device(eng, slots)
 e1.record(); torch.cuda.synchronize()
-print("decompress_device ms/step", round(e0.elapsed_time(e1) / 10, 3), "side decode:", os.environ.get("LOSSYCOMP_NO_SIDE_DECODE") != "1")
+print("decompress_device ms/step", round(e0.elapsed_time(e1) / 10, 3))
