@@ -154,3 +154,21 @@ def test_native_decode_arrays_equal_python_builder():
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         back, used = HF.Table.from_bytes(memoryview(t.to_bytes()))
         assert used == len(t.to_bytes()) and np.array_equal(back.code, t.code) and np.array_equal(back.len, t.len)
+
+
+def test_dumps_slots_loads_like_pickle():
+    """The hand-assembled blob (one copy of the payloads) unpickles to exactly the list pickle.dumps would give,
+    and is a well-formed pickle stream (pickletools is stricter than the unpickler about memo keys)."""
+    import pickle
+    import pickletools
+    from lossycomp.compress import dumps_slots
+    rng = np.random.default_rng(0)
+    slots = [b"LCL1" + bytes(rng.integers(0, 255, 5000, dtype=np.uint8)), (900, 3, 3, 23), (24, 720, 1440, 2), (12345,),
+             np.float32(265.5), np.float32(16.25), bytes(rng.integers(0, 255, 70000, dtype=np.uint8)), b"", 0.19998]
+    blob = dumps_slots(slots)
+    back = pickle.loads(blob)
+    assert type(back) is list and len(back) == 9
+    for a, b in zip(slots, back):
+        assert type(a) is type(b) and a == b
+    assert back == pickle.loads(pickle.dumps(slots))
+    pickletools.dis(blob, out=open(os.devnull, "w"))
