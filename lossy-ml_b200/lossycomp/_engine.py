@@ -141,13 +141,6 @@ class Engine:
             side = self._small["side_stream"] = self.torch.cuda.Stream(device=self.dev)
         return side
 
-    def copy_stream(self):
-        """Stream for host->device uploads that should overlap kernels of the main stream."""
-        cs = self._small.get("copy_stream")
-        if cs is None:
-            cs = self._small["copy_stream"] = self.torch.cuda.Stream(device=self.dev)
-        return cs
-
     def _ae_ws(self, n_chunks):
         if self._ws is None or self._ws_chunks < n_chunks:
             nbytes = self.lib.lc_ae_workspace_bytes(self.h, n_chunks)
@@ -359,18 +352,11 @@ class Engine:
         hv[o_seg:o_lut] = offs.view(np.uint8)
         hv[o_lut:o_lut + 2 * lut.size] = lut.view(np.uint8)
         hv[o_tree:total] = tree.view(np.uint8)
-        # the upload runs on the copy stream, beside whatever the main stream is busy with (in decompress() the
-        # decoder's convolutions: copies need no SM, unlike the decode kernel, which stays on the main stream)
-        main = t.cuda.current_stream(self.dev)
-        cs = self.copy_stream()
-        with t.cuda.stream(cs):
-            dbuf = t.empty(total, dtype=t.uint8, device=self.dev)
-            dbuf.copy_(host[:total], non_blocking=True)
-            ev = t.cuda.Event()
-            ev.record(cs)
+        dbuf = t.empty(total, dtype=t.uint8, device=self.dev)
+        dbuf.copy_(host[:total], non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record(t.cuda.current_stream(self.dev))
         slot[1] = ev
-        main.wait_event(ev)
-        dbuf.record_stream(main)
         base = dbuf.data_ptr()
         N.check(self.lib.lc_huff_decode(C.c_void_p(base), n, seg, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
                                         HF.LUT_BITS, C.c_void_p(base + o_tree), _ptr(sym), self._stream()), "lc_huff_decode")
