@@ -322,8 +322,11 @@ class Engine:
         buf, ev = ring[i]
         if ev is not None:
             ev.synchronize()
+        # every slot is sized for the largest payload seen so far: slots rotate among streams of very different
+        # sizes (latent plane, codes, mask), and a pinned reallocation in the steady state costs milliseconds
+        cap = self._small["stage_cap"] = max(self._small.get("stage_cap", 1 << 16), int(nbytes * 1.25))
         if buf is None or buf.numel() < nbytes:
-            buf = t.empty(max(int(nbytes * 1.25), 1 << 16), dtype=t.uint8, pin_memory=True)
+            buf = t.empty(cap, dtype=t.uint8, pin_memory=True)
         ring[i] = [buf, None]
         return buf, ring[i]
 
