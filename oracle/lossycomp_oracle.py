@@ -318,3 +318,45 @@ def synthetic_field(T, H, W, seed=1234, level=0, t0=0, h0=0, w0=0, grid=(720, 14
     out[..., 0] = x.astype(np.float32)
     out[..., 1] = np.broadcast_to(lsm, (T, H, W))
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# Restatements of this package's own container extensions (not part of the reference): the run
+# tokens of sparse streams (include/lossycomp_b200.h: lc_rle_tokens / lc_rle_expand).
+# ------------------------------------------------------------------------------------------
+def rle_tokens(b, run_sym=0, run_first=243):
+    """Bytes -> run tokens: runs of `run_sym` inside 32-byte segments, decomposed largest power of two
+    first; a run of 2^(k+1) becomes token run_first + k (k = 0..4), everything else stays literal."""
+    b = np.asarray(b, dtype=np.uint8)
+    out = []
+    for s0 in range(0, len(b), 32):
+        seg = b[s0:s0 + 32]
+        i = 0
+        while i < len(seg):
+            if seg[i] != run_sym:
+                out.append(int(seg[i]))
+                i += 1
+                continue
+            r = 1
+            while i + r < len(seg) and seg[i + r] == run_sym:
+                r += 1
+            for k in range(5, -1, -1):
+                if r & (1 << k):
+                    out.append(run_sym if k == 0 else run_first - 1 + k)
+            i += r
+    return np.array(out, dtype=np.uint8)
+
+
+def rle_expand(tok, n, run_sym=0, run_first=243):
+    """Inverse of rle_tokens (n = number of bytes to produce)."""
+    out = np.full(n, run_sym, dtype=np.uint8)
+    pos = 0
+    for t in np.asarray(tok, dtype=np.uint8):
+        r = int(t) - run_first
+        if 0 <= r <= 4:
+            pos += 2 << r
+        else:
+            out[pos] = t
+            pos += 1
+    assert pos == n, (pos, n)
+    return out

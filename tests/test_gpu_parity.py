@@ -391,23 +391,9 @@ def test_full_size_field_properties(torch):
 
 
 def _rle_tokens_reference(b):
-    """NumPy/Python restatement of lc_rle_tokens: 32-byte segments, zero runs -> largest power of two first."""
-    out = []
-    for s0 in range(0, len(b), 32):
-        seg = b[s0:s0 + 32]
-        i = 0
-        while i < len(seg):
-            if seg[i] != 0:
-                out.append(int(seg[i])); i += 1
-                continue
-            r = 1
-            while i + r < len(seg) and seg[i + r] == 0:
-                r += 1
-            for k in range(5, -1, -1):
-                if r & (1 << k):
-                    out.append(0 if k == 0 else 242 + k)
-            i += r
-    return np.array(out, dtype=np.uint8)
+    """The oracle's restatement of lc_rle_tokens (mask parameters)."""
+    from oracle import lossycomp_oracle as O
+    return O.rle_tokens(b, 0, 243)
 
 
 @pytest.mark.parametrize("n,density", [(1, 0.0), (31, 0.5), (32, 0.0), (33, 0.02), (8192, 0.001), (8193, 0.3),

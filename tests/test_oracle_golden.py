@@ -88,3 +88,22 @@ def test_quantiser_edges():
     assert mask.reshape(-1).tolist() == [0, 1, 0, 2, 1, 1, 2]
     ref = np.round(np.abs(e[[1, 3, 4, 5, 6]]) / np.float32(0.2)).astype(np.int32)
     assert q.tolist() == ref.tolist()
+
+
+def test_run_token_restatement_roundtrip_and_known_answers():
+    """The run-token format of sparse streams (this package's extension; the GPU kernels are checked against this
+    restatement in tests/test_gpu_parity.py): known answers and round trips on the CPU."""
+    from oracle import lossycomp_oracle as O
+    z = np.zeros(37, np.uint8)
+    assert O.rle_tokens(z).tolist() == [247, 244, 0]                   # 32 zeros | 4 zeros + 1 zero (segments of 32)
+    b = np.array([0, 0, 0, 5, 0, 7, 0, 0, 0, 0, 0, 0], np.uint8)
+    assert O.rle_tokens(b).tolist() == [243, 0, 5, 0, 7, 244, 243]     # 3 = 2+1, 1, 6 = 4+2
+    assert O.rle_tokens(np.array([1, 1, 1, 2, 1], np.uint8), 1, 250).tolist() == [250, 1, 2, 1]
+    rng = np.random.default_rng(0)
+    for n, p in [(1, 0.0), (31, 0.5), (32, 0.0), (33, 0.02), (1000, 0.001), (1001, 0.3), (4096, 0.0), (777, 1.0)]:
+        x = np.where(rng.random(n) < p, rng.integers(1, 243, n), 0).astype(np.uint8)
+        t = O.rle_tokens(x)
+        assert np.array_equal(O.rle_expand(t, n), x)
+        assert t.size <= n
+        c = np.where(x == 0, 1, np.where(x == 1, 2, np.minimum(x, 200))).astype(np.uint8)
+        assert np.array_equal(O.rle_expand(O.rle_tokens(c, 1, 250), n, 1, 250), c)
