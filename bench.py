@@ -3,20 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision P]
 
-A step = one compress() of one synthetic ERA5-shaped field (BASELINE.json configs[1]:
-24 h x 1 level x 720 x 1440 float32 + land-sea channel, abs_error 0.1) per GPU.  Under torchrun
-every rank compresses its own 24-hour time shard of the month (weak scaling, no data-path
-collective: chunks are independent); value = bytes of channel-0 input all ranks compressed / max
-over ranks of the device time.
+N = 1: a step = one compress() of one synthetic ERA5-shaped field (BASELINE.json configs[1]: 24 h x 1 level x
+720 x 1440 float32 + land-sea channel, abs_error 0.1).
+N > 1 (torchrun): a step = compress() of ONE field of 24*N hours, time-sharded over the N ranks in whole
+16-step chunks (lossycomp.dist.compress_sharded): NCCL all-reduce of the per-block statistics and
+of strict mode's verdict, NCCL send/recv of the blob parts from the Huffman output buffers to one rank and one
+device->host copy there -- all inside the timed region.  After the timed region the sharded result is checked
+bit for bit (mask, codes, reconstruction) against a single-GPU call on the same field.
+value = bytes of channel-0 input all ranks compressed / max over ranks of the device time.
 
-Keys beyond the base contract: `roofline` (dominant kernel = the convolution stack, tensor bound
-against the measured bf16 peak, or CUDA-core fp32 when --precision fp32), `cpu_baseline` (the
-oracle timed on the host cores over a bounded sample), `decompress`, `compression_factor`,
-`violations`.
+Keys beyond the base contract: `roofline` (dominant kernel = the 3x3x3 tensor-core convolution, against the
+measured bf16 peak; also the conv stack, decompress and per-kernel numbers), `cpu_baseline` (the oracle timed on
+the host cores over a bounded sample, N = 1 only), `e2e` (public API with host buffers; also carries compression
+factor, violations, parity verdicts and the decompress numbers so that they survive the driver's key filter).
 """
 import argparse
 import json
 import os
+import pickle
 import subprocess
 import sys
 import threading
@@ -33,9 +37,10 @@ METRIC = "compress_throughput_fp32_input"
 UNIT = "GB/s"
 ABS_ERR = 0.1
 FIELD = (24, 720, 1440)          # configs[1] of BASELINE.json
-CPU_SAMPLE = (24, 336, 720)      # bounded sample of the same field for the CPU legs (~10-20 s)
-# DRAM bytes per chunk per launch of the dominant kernel, from the ncu --set full capture under profiles/
-NCU_DRAM_BYTES_PER_CHUNK = {"sweep_tc_kernel<K3>": 4.16e6}   # mean of its 4 layers: 3.08 MB (plain), 5.24 MB (with skip)
+HOURS_PER_RANK = 24              # N > 1: one field of 24*N hours
+CPU_SAMPLE = (24, 336, 720)      # bounded sample of the same field for the CPU leg inside the GPU arm (~4 s)
+MODEL_NAME = "final_models/model_2 (F=23,k=4,res=1)"
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # ncu --set full DRAM bytes per launch, by kernel
 
 
 def parse():
@@ -47,16 +52,37 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("LOSSYCOMP_PRECISION", "fp16"))
     ap.add_argument("--codec", default="huff")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", action="store_true",
-                    help="N>1: also gather every rank's blob into rank 0's HBM inside the timed region")
-    ap.add_argument("--field", default=None, help="T,H,W override (tests)")
+    ap.add_argument("--field", default=None, help="T,H,W override of the per-rank field (tests)")
+    ap.add_argument("--hours-per-rank", type=int, default=HOURS_PER_RANK,
+                    help="N > 1: the field has N times this many hours (32 = two whole time chunks per rank)")
+    ap.add_argument("--dst", type=int, default=None, help="N > 1: rank that receives the blob (default: the last)")
+    ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the single-GPU comparison")
     return ap.parse_args()
 
 
+def workload_config(world, T, H, W, n_chunks, codec, precision, in_bytes, dst=None):
+    """The `config` object; the reference arm prints the same one (its CPU sample is described in cpu_baseline)."""
+    if world == 1:
+        par = "1 rank"
+        wl = (f"compress() of one synthetic ERA5 slice {T}x{H}x{W} fp32 + lsm channel, abs_err {ABS_ERR}, "
+              f"strict bound, {n_chunks} chunks of 16x48x48, codec {codec}")
+    else:
+        par = (f"one field time-sharded over {world} ranks in whole 16-step chunks (dist.compress_sharded): NCCL "
+               f"all-reduce of per-block statistics and of the strict-mode verdict, NCCL send/recv of the blob parts "
+               f"from the Huffman output buffers to rank {dst}, one device->host copy there; all inside the timed region")
+        wl = (f"compress() of ONE synthetic ERA5 field {T}x{H}x{W} fp32 + lsm channel ({T // world} h per rank), "
+              f"abs_err {ABS_ERR}, strict bound, {n_chunks} chunks of 16x48x48, codec {codec}")
+    return {"workload": wl, "model": MODEL_NAME, "precision": precision,
+            "l2": f"inputs {in_bytes * 2 / 1e6:.0f} MB per rank and step exceed the 126 MB L2",
+            "parallelism": par}
+
+
 # ------------------------------------------------------------------------------------------
-def cpu_leg(steps, warmup, sample=CPU_SAMPLE):
+def cpu_leg(steps, warmup, sample, threads=None):
     """The reference's CPU path (oracle port: NumPy + torch-CPU fp32 convs, batch 10, bz2 -9)."""
     import torch
+    if threads:
+        torch.set_num_threads(threads)           # torchrun exports OMP_NUM_THREADS=1: do not inherit it
     from lossycomp.models import load_model
     from oracle import lossycomp_oracle as O
     model = load_model()
@@ -66,10 +92,10 @@ def cpu_leg(steps, warmup, sample=CPU_SAMPLE):
     for _ in range(max(0, min(warmup, 1))):
         O.compress(x[:16, :96, :96], ABS_ERR, model)
     times, dtimes = [], []
-    blob = None
+    blob = parts = None
     for _ in range(steps):
         t0 = time.perf_counter()
-        blob = O.compress(x, ABS_ERR, model)
+        blob, parts = O.compress(x, ABS_ERR, model, return_parts=True)
         times.append(time.perf_counter() - t0)
     t0 = time.perf_counter()
     xhat = O.decompress(blob, model)
@@ -83,25 +109,35 @@ def cpu_leg(steps, warmup, sample=CPU_SAMPLE):
         "seconds_per_step": float(np.mean(times)), "decompress_GBps": nbytes / dtimes[0] / 1e9,
         "compression_factor": nbytes / len(blob), "violations_reference_arithmetic": viol,
         "host_cpus": os.cpu_count(),
-    }
+    }, x, parts
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (the oracle port: TensorFlow cannot be installed here),
+    all host threads, one full 24x720x1440 slice per step.  N > 1: rank 0 alone runs it, on the same per-step
+    slice (the field of 24*N hours is N such slices; GB/s is size-normalised), the other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    world = args.gpus
+    steps = max(1, min(args.steps, 2))
     t0 = time.perf_counter()
-    cb = cpu_leg(steps, args.warmup)
-    T, H, W = CPU_SAMPLE
+    T, H, W = FIELD if not args.field else tuple(int(v) for v in args.field.split(","))
+    cb, _, _ = cpu_leg(steps, args.warmup, (T, H, W), threads=os.cpu_count())
+    Tw = T if world == 1 else args.hours_per_rank * world
+    n_chunks = -(-Tw // 16) * -(-H // 48) * -(-W // 48)
+    if world > 1:
+        cb["sample"] += (f"; the GPU arm's field at {world} ranks is {Tw}x{H}x{W} = {world} such slices, the CPU arm "
+                         f"times one of them per step on all {cb['cores']} host threads")
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"compress() of one synthetic ERA5 slice 24x720x1440 fp32 + lsm, abs_err {ABS_ERR}; "
-                               f"each step a bounded {T}x{H}x{W} sample", "model": "final_models/model_2"},
+        "config": workload_config(world, Tw, H, W, n_chunks, args.codec, args.precision, T * H * W * 4,
+                                  dst=(world - 1 if args.dst is None else args.dst)),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "compression_factor": cb["compression_factor"], "decompress_GBps": cb["decompress_GBps"]},
         "compression_factor": cb["compression_factor"], "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line))
@@ -160,12 +196,28 @@ def peaks():
             "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, n_chunks):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of THIS workload
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when the capture is of
+    another chunk count."""
+    try:
+        with open(TRAFFIC_FILE) as fh:
+            t = json.load(fh)
+        e = t["kernels"][kernel]
+        if int(t["n_chunks"]) != int(n_chunks):
+            return None, None
+        return float(e["dram_bytes_per_launch"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from lossycomp import _native as N
+    from lossycomp import dist as LD
     from lossycomp._engine import Engine
-    from lossycomp.compress import compress, compress_device
+    from lossycomp.compress import compress, compress_device, compress_stream
     from lossycomp.decompress import decompress, decompress_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,31 +228,39 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N.lib()
     eng = Engine.get(None, args.precision, local)
-    T, H, W = FIELD if not args.field else tuple(int(v) for v in args.field.split(","))
-    # synthetic month: rank r owns hours [24 r, 24 r + 24) (time sharding in whole 16-step chunks is
-    # not needed here because every rank's shard is its own compress() call)
-    x = torch.empty((T, H, W, 2), dtype=torch.float32, device=eng.dev)
-    N.check(eng.lib.lc_synth_field(x.data_ptr(), T, H, W, 24 * rank, 0, 1234, None), "lc_synth_field")
+    Tr, H, W = FIELD if not args.field else tuple(int(v) for v in args.field.split(","))
+    if world > 1:
+        Tr = args.hours_per_rank if not args.field else Tr
+    T = Tr * world                                   # rows of the whole field
+    dst = (world - 1) if args.dst is None else args.dst
+    shards = LD.shard_time(T, world) if world > 1 else [(0, T)]
+    t0r, t1r = shards[rank]
+    # this rank's rows of the synthetic field (window [t0r, t1r) of the global time axis)
+    x = torch.empty((t1r - t0r, H, W, 2), dtype=torch.float32, device=eng.dev)
+    if t1r > t0r:
+        N.check(eng.lib.lc_synth_field(x.data_ptr(), t1r - t0r, H, W, t0r, 0, 1234, None), "lc_synth_field")
     torch.cuda.synchronize()
-    in_bytes = T * H * W * 4
-    n_chunks = eng.n_chunks(T, H, W)
+    in_bytes = T * H * W * 4                          # whole job, channel 0
+    my_bytes = (t1r - t0r) * H * W * 4
+    n_chunks_all = eng.n_chunks(T, H, W)
+    n_chunks = eng.n_chunks(t1r - t0r, H, W) if t1r - t0r >= 16 else 0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    import pickle
-    from lossycomp import dist as LD
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tms = torch.tensor([v], dtype=torch.float64, device=eng.dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        return float(tms.item())
 
     def step():
-        # one compress() per 24 h slice (the reference's unit of work).  Slices are independent objects,
-        # so ranks exchange nothing (each keeps / writes its own blob); --gather adds an NCCL gather of
-        # the blobs into rank 0's HBM to the timed region (what compress_sharded() pays per field)
-        slots, info = compress_device(eng, x, ABS_ERR, mode="strict", codec=args.codec)
-        if world > 1 and args.gather:
-            info["gathered"] = LD.gather_bytes(LD.frame_slots(slots), 0, None, eng.dev, to_host=False)
-        return slots, info
+        if world == 1:
+            return compress_device(eng, x, ABS_ERR, mode="strict", codec=args.codec)
+        return LD.compress_sharded(eng, x, ABS_ERR, t0=t0r, T=T, mode="strict", codec=args.codec, dst=dst)
 
     for _ in range(args.warmup):
         slots, info = step()
@@ -220,77 +280,132 @@ def run_ours(args):
     e1.record()
     barrier()
     w1 = time.perf_counter()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launches - launches0
     layer_ms, layer_cnt = eng.profile_read()
     eng.profile(False)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
+    value = in_bytes * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- N > 1: the sharded blob against a single-GPU call on the same field (outside the timed region)
+    sharded = None
     if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=eng.dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    value = world * in_bytes * args.steps / (ms * 1e-3) / 1e9
+        verdict = [None]
+        if rank == dst and not args.skip_parity:
+            full = torch.empty((T, H, W, 2), dtype=torch.float32, device=eng.dev)
+            N.check(eng.lib.lc_synth_field(full.data_ptr(), T, H, W, 0, 0, 1234, None), "lc_synth_field")
+            ref, rinfo = compress_device(eng, full, ABS_ERR, mode="strict", codec=args.codec, return_parts=True)
+            same_mask = bool(torch.equal(eng.unpack_mask(slots[7]), rinfo["mask"]))
+            same_q = bool(torch.equal(eng.unpack_codes(slots[6]), rinfo["q"]))
+            whole = decompress_device(eng, slots)
+            same_x = bool(torch.equal(whole, decompress_device(eng, ref)))
+            v, mx = eng.verify(full, whole, ABS_ERR)
+            verdict[0] = {"mask_equal": same_mask, "codes_equal": same_q, "xhat_equal": same_x,
+                          "stats_equal": bool(slots[4] == ref[4] and slots[5] == ref[5]),
+                          "violations": v, "max_abs_err": mx,
+                          "cf_sharded": in_bytes / len(pickle.dumps(slots)),
+                          "cf_single_call": in_bytes / len(pickle.dumps(ref))}
+            del full, ref, rinfo, whole
+            torch.cuda.empty_cache()
+        dist.broadcast_object_list(verdict, src=dst)
+        sharded = verdict[0]
 
-    blob = pickle.dumps(slots)
-    cf = in_bytes / len(blob)
+    blob_len = len(pickle.dumps(slots)) if slots is not None else 0
+    if world > 1:
+        bl = [blob_len]
+        dist.broadcast_object_list(bl, src=dst)
+        blob_len = bl[0]
+    cf = in_bytes / blob_len
 
-    # ---- decompress (device resident) + exhaustive bound check
+    # ---- decompress (device resident) + exhaustive bound check of every rank's rows
+    def dstep():
+        if world == 1:
+            return decompress_device(eng, slots)
+        return LD.decompress_sharded(eng, slots, src=dst)[2]
+
     barrier()
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(max(args.warmup, 1)):
-        xhat = decompress_device(eng, slots)
+    for _ in range(max(min(args.warmup, 2), 1)):
+        xhat = dstep()
     barrier()
     d0.record()
     for _ in range(args.steps):
-        xhat = decompress_device(eng, slots)
+        xhat = dstep()
     d1.record()
     barrier()
-    dms = d0.elapsed_time(d1)
+    dms = max_over_ranks(d0.elapsed_time(d1))
+    dvalue = in_bytes * args.steps / (dms * 1e-3) / 1e9
+    viol, max_err = eng.verify(x, xhat, ABS_ERR) if t1r > t0r else (0, 0.0)
     if world > 1:
-        tms = torch.tensor([dms], dtype=torch.float64, device=eng.dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        dms = float(tms.item())
-    dvalue = world * in_bytes * args.steps / (dms * 1e-3) / 1e9
-    viol, max_err = eng.verify(x, xhat, ABS_ERR)
+        vv = torch.tensor([float(viol), max_err], dtype=torch.float64, device=eng.dev)
+        dist.all_reduce(vv[:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(vv[1:], op=dist.ReduceOp.MAX)
+        viol, max_err = int(vv[0].item()), float(vv[1].item())
 
-    # ---- end to end through the public API with host buffers (pinned input, blob bytes out)
-    host = torch.empty((T, H, W, 2), dtype=torch.float32, pin_memory=True)
+    # ---- end to end through the public API with host buffers (pinned input rows, blob bytes out)
+    host = torch.empty(tuple(x.shape), dtype=torch.float32, pin_memory=True)
     host.copy_(x)
     xh = host.numpy()
-    b = compress(xh, ABS_ERR, precision=args.precision, codec=args.codec)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        b = compress(xh, ABS_ERR, precision=args.precision, codec=args.codec)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    if world > 1:
-        tms = torch.tensor([e2e_s], dtype=torch.float64, device=eng.dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e_s = float(tms.item())
-    # bulk-job variant: the same K calls through compress_stream(), which overlaps the H2D copy of field k+1 with
-    # the kernels of field k (every step still copies its 199 MB in and its blob out)
-    from lossycomp.compress import compress_stream
-    list(compress_stream([xh, xh], ABS_ERR, precision=args.precision, codec=args.codec))
-    barrier()
-    t0 = time.perf_counter()
-    n_stream = sum(1 for _ in compress_stream([xh] * args.steps, ABS_ERR, precision=args.precision, codec=args.codec))
-    torch.cuda.synchronize()
-    e2e_stream = (time.perf_counter() - t0) / max(n_stream, 1)
-    xp = np.array(xh)                       # the same field in ordinary (pageable) memory
-    compress(xp, ABS_ERR, precision=args.precision, codec=args.codec)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        compress(xp, ABS_ERR, precision=args.precision, codec=args.codec)
-    e2e_pageable = (time.perf_counter() - t0) / args.steps
-    del xp
-    xr = decompress(b)                      # warm-up (pinned staging, allocator)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        xr = decompress(b)
-    e2e_d = (time.perf_counter() - t0) / args.steps
-    e2e_viol = int((np.abs(xh[..., 0].astype(np.float64) - xr[..., 0]) > ABS_ERR).sum())
 
+    def e2e_step():
+        if world == 1:
+            return compress(xh, ABS_ERR, precision=args.precision, codec=args.codec)
+        return LD.compress_sharded_host(xh, ABS_ERR, t0=t0r, T=T, precision=args.precision, codec=args.codec, dst=dst)
+
+    b = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e = {"value": in_bytes / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": my_bytes * 2 if world == 1 else in_bytes * 2,
+           "d2h_bytes_per_step": blob_len, "ms_per_step": e2e_s * 1e3}
+    if world == 1:
+        # bulk-job variant: the same K calls through compress_stream(), which overlaps the H2D copy of field k+1
+        # with the kernels of field k (every step still copies its 199 MB in and its blob out)
+        list(compress_stream([xh, xh], ABS_ERR, precision=args.precision, codec=args.codec))
+        barrier()
+        t0 = time.perf_counter()
+        n_stream = sum(1 for _ in compress_stream([xh] * args.steps, ABS_ERR, precision=args.precision, codec=args.codec))
+        torch.cuda.synchronize()
+        e2e["compress_stream_GBps"] = in_bytes / ((time.perf_counter() - t0) / max(n_stream, 1)) / 1e9
+        xp = np.array(xh)                       # the same field in ordinary (pageable) memory
+        compress(xp, ABS_ERR, precision=args.precision, codec=args.codec)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            compress(xp, ABS_ERR, precision=args.precision, codec=args.codec)
+        e2e["pageable_input_GBps"] = in_bytes / ((time.perf_counter() - t0) / args.steps) / 1e9
+        del xp
+        xr = decompress(b)                      # warm-up (pinned staging, allocator)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            xr = decompress(b)
+        e2e_d = (time.perf_counter() - t0) / args.steps
+        e2e_viol = int((np.abs(xh[..., 0].astype(np.float64) - xr[..., 0]) > ABS_ERR).sum())
+    else:
+        a_, b_, xr = LD.decompress_sharded_host(b, precision=args.precision, src=dst)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            a_, b_, xr = LD.decompress_sharded_host(b, precision=args.precision, src=dst)
+        e2e_d = max_over_ranks((time.perf_counter() - t0) / args.steps)
+        e2e_viol = int((np.abs(xh[..., 0].astype(np.float64) - xr[..., 0]) > ABS_ERR).sum()) if t1r > t0r else 0
+        vv = torch.tensor([float(e2e_viol)], dtype=torch.float64, device=eng.dev)
+        dist.all_reduce(vv, op=dist.ReduceOp.SUM)
+        e2e_viol = int(vv.item())
+    e2e.update(decompress_GBps=in_bytes / e2e_d / 1e9, violations=e2e_viol)
+
+    # per-layer times of every rank -> rank 0 reports the slowest rank's conv stack
+    conv_ms = sum(layer_ms)
+    if world > 1:
+        lm = torch.tensor(layer_ms + [float(n_chunks)], dtype=torch.float64, device=eng.dev)
+        alls = [torch.zeros_like(lm) for _ in range(world)]
+        dist.all_gather(alls, lm)
+        heavy = max(range(world), key=lambda r: float(alls[r][:-1].sum()))
+        layer_ms = alls[heavy][:-1].cpu().tolist()
+        n_chunks = int(alls[heavy][-1].item())
+        conv_ms = sum(layer_ms)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -311,69 +426,76 @@ def run_ours(args):
                           "tflops": (fl / (layer_ms[i] * 1e-3) / 1e12) if layer_ms[i] > 0 else None})
         g = groups.setdefault(kname, {"ms": 0.0, "flops": 0.0, "launches": 0})
         g["ms"] += layer_ms[i]; g["flops"] += fl; g["launches"] += layer_cnt[i]
-    conv_ms = sum(layer_ms)
     conv_flops = 2.0 * (macs["Encoder"] + macs["Decoder"]) * n_chunks * args.steps
     if args.precision == "fp32":
         peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA peak (148 SM x 128 lanes x 1.965 GHz), CUDA-core path"
+        burst = peak
     else:
         peak, peak_note = pk["bf16_tflops_sustained"], f"dense 16-bit tensor, sustained, {pk_src}"
+        burst = pk.get("bf16_tflops", peak)
     dom_name = max(groups, key=lambda k: groups[k]["ms"])
     dom = groups[dom_name]
     achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else None
-    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/), per chunk
-    traffic_per_chunk = NCU_DRAM_BYTES_PER_CHUNK.get(dom_name)
-    chunks_per_launch = n_chunks * args.steps * sum(1 for b in backends if eng.BACKENDS[b] == dom_name) / max(dom["launches"], 1)
+    chunks_per_launch = n_chunks * args.steps * sum(1 for bk in backends if eng.BACKENDS[bk] == dom_name) / max(dom["launches"], 1)
+    traffic, traffic_src = measured_traffic(dom_name, chunks_per_launch)
     roofline = {
         "bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if achieved else None,
-        "traffic": (traffic_per_chunk * chunks_per_launch) if traffic_per_chunk else None,
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                        "(profiles/r01_ncu_sweep_final.txt), scaled to the chunks one launch processes",
+        "frac_of_burst_peak": (achieved / burst) if achieved else None, "burst_peak": burst,
+        "traffic": traffic,
+        "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over this kernel's layers, from "
+                         f"{traffic_src}") if traffic else "no ncu --set full capture of this chunk count is committed",
         "peak_source": peak_note, "launch_ms": dom["ms"] / max(dom["launches"], 1), "launches": dom["launches"],
         "algorithmic_flops_per_launch": dom["flops"] / max(dom["launches"], 1),
         "share_of_step": dom["ms"] / ms,
         "conv_stack": {"achieved": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None, "ms_per_step":
-                       conv_ms / args.steps, "share_of_step": conv_ms / ms, "flops_per_chunk": 2.0 * (macs["Encoder"] + macs["Decoder"])},
+                       conv_ms / args.steps, "share_of_step": conv_ms / ms, "flops_per_chunk": 2.0 * (macs["Encoder"] + macs["Decoder"]),
+                       "frac": (conv_flops / (conv_ms * 1e-3) / 1e12 / peak) if conv_ms else None},
+        "decompress": {"value": dvalue, "unit": UNIT, "ms_per_step": dms / args.steps,
+                       "frac_of_decoder_ceiling": dvalue / (world * peak * 1e12 / (2.0 * macs["Decoder"] / (16 * 48 * 48 * 4)) / 1e9)},
         "per_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else None,
                            "launches": v["launches"]} for k, v in groups.items()},
         "per_layer": per_layer,
     }
+    e2e.update(compression_factor=cf, device_violations=viol, max_abs_err=max_err,
+               outlier_fraction=(info["n_out"] / max((t1r - t0r) * H * W, 1)))
+    if sharded is not None:
+        e2e["sharded_parity"] = bool(sharded["mask_equal"] and sharded["codes_equal"] and sharded["xhat_equal"]
+                                     and sharded["stats_equal"])
+        e2e["sharded"] = sharded
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic",
-        "config": {"workload": f"compress() of one synthetic ERA5 slice {T}x{H}x{W} fp32 + lsm channel per GPU, "
-                               f"abs_err {ABS_ERR}, strict bound, {n_chunks} chunks of 16x48x48, codec {args.codec}",
-                   "model": "final_models/model_2 (F=23,k=4,res=1)", "precision": args.precision,
-                   "l2": f"inputs {in_bytes * 2 / 1e6:.0f} MB per step exceed the 126 MB L2",
-                   "parallelism": f"{world} rank(s), one independent 24 h slice per rank per step, "
-                                  + ("blobs gathered to rank 0 over NCCL" if (world > 1 and args.gather)
-                                     else "no data-path collective")},
+        "config": workload_config(world, T, H, W, n_chunks_all, args.codec, args.precision, my_bytes, dst),
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": world * in_bytes / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": in_bytes * 2,
-                "d2h_bytes_per_step": len(b), "ms_per_step": e2e_s * 1e3,
-                "pageable_input_GBps": in_bytes / e2e_pageable / 1e9,
-                "compress_stream_GBps": in_bytes / e2e_stream / 1e9,
-                "decompress_GBps": in_bytes / e2e_d / 1e9, "violations": e2e_viol},
+        "e2e": e2e,
         "decompress": {"value": dvalue, "unit": UNIT, "ms_per_step": dms / args.steps},
         "compression_factor": cf, "violations": viol, "max_abs_err": max_err,
-        "outlier_fraction": info["n_out"] / (T * H * W),
-        "blob_bytes": {"latent": info["latent_bytes"], "codes": info["error_bytes"], "mask": info["mask_bytes"]},
         "roofline": roofline,
     }
+    if world == 1:
+        line["blob_bytes"] = {"latent": info["latent_bytes"], "codes": info["error_bytes"], "mask": info["mask_bytes"]}
+    else:
+        line["sharded_parity"] = e2e.get("sharded_parity")
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_leg(1, 1)
+        cb, xs, parts = cpu_leg(1, 1, CPU_SAMPLE)
         line["cpu_baseline"] = cb
-        # compression factor on the SAME input as the CPU oracle (north_star: within 1 % of the reference)
-        from oracle import lossycomp_oracle as O
-        xs = O.synthetic_field(*CPU_SAMPLE, seed=1234)
+        # the oracle's own input: (1) integer stages bit for bit given the oracle's reconstruction (2.9 M voxels,
+        # 2160 scan tiles), (2) compression factor within 1 % of the reference's coder (north_star)
         nb = xs[..., 0].nbytes
-        line["cf_same_input"] = {
+        xd = torch.from_numpy(xs).to(eng.dev)
+        mask, q = eng.quantize(xd, torch.from_numpy(np.ascontiguousarray(parts["recon_std"][..., 0])).to(eng.dev),
+                               parts["mean"], parts["std"], ABS_ERR)
+        e2e["oracle_parity_mask_codes"] = bool(np.array_equal(mask.cpu().numpy().reshape(parts["mask"].shape), parts["mask"])
+                                               and np.array_equal(q.cpu().numpy(), parts["q"]))
+        e2e["cf_same_input"] = {
             "oracle_bz2": cb["compression_factor"],
             "gpu_parity_mode_bz2_codec": nb / len(compress(xs, ABS_ERR, precision=args.precision, codec="bz2", mode="parity")),
             "gpu_strict_mode_bz2_codec": nb / len(compress(xs, ABS_ERR, precision=args.precision, codec="bz2")),
             "gpu_strict_mode_huff_codec": nb / len(compress(xs, ABS_ERR, precision=args.precision, codec="huff")),
             "input": "oracle.synthetic_field%s, abs_err %g" % (str(CPU_SAMPLE), ABS_ERR)}
+        line["cf_same_input"] = e2e["cf_same_input"]
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))

@@ -97,6 +97,13 @@ int lc_chunk_merge(const float* d_chunks, int T, int H, int W, int C, float* d_o
  * d_ws needs lc_stats_workspace_bytes(). */
 size_t lc_stats_workspace_bytes(void);
 int lc_stats(const float* d_x, int64_t n_vox, int C, double* d_out, void* d_ws, void* stream);
+/* Shard-invariant form of the same statistics: the voxels are cut into consecutive blocks of block_vox (the codec
+ * uses one 16-step time chunk = 16*H*W; the last block may be shorter) and each block is reduced on its own in a
+ * fixed order; d_out[4*b .. 4*b+3] = { sum, sum^2, max|x|, n } of block b.  The caller adds the blocks in index
+ * order, so the ranks of a time-sharded field (which exchange their blocks' partials) obtain bit for bit the mean
+ * and std of the single-GPU call.  Same workspace as lc_stats. */
+int lc_stats_blocks(const float* d_x, int64_t n_vox, int64_t block_vox, int C, double* d_out, void* d_ws,
+                    void* stream);
 
 /* compress.py:66-86 + dataLoader.py:437-481 + models.py:52-67 -- standardise channel 0,
  * cut chunks [chunk_begin, chunk_begin+chunk_count) of the (T,H,W,C) field (tail windows are

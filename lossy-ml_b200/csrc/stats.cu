@@ -117,6 +117,28 @@ extern "C" int lc_stats(const float* d_x, int64_t n_vox, int C, double* d_out, v
   return LC_OK;
 }
 
+// Shard-invariant form: the field is cut into blocks of `block_vox` voxels (the codec uses one 16-step time chunk,
+// 16*H*W) and every block is reduced on its own in the fixed order above; d_out receives {sum, sum^2, max|x|, n}
+// per block.  The caller adds the blocks in index order, so a time-sharded field (every rank reduces its own
+// blocks, the partials are exchanged) gets bit for bit the statistics of the single-GPU call.
+extern "C" int lc_stats_blocks(const float* d_x, int64_t n_vox, int64_t block_vox, int C, double* d_out, void* d_ws,
+                               void* stream) {
+  LC_REQUIRE(d_x && d_out && d_ws, "null argument");
+  LC_REQUIRE(n_vox > 0 && block_vox > 0 && C >= 1, "empty input");
+  cudaStream_t s = as_stream(stream);
+  int b = 0;
+  for (int64_t o = 0; o < n_vox; o += block_vox, ++b) {
+    const int64_t n = (n_vox - o < block_vox) ? (n_vox - o) : block_vox;
+    const float* x = d_x + o * C;
+    const bool vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    stats_partial_kernel<<<kBlocks, kThreads, 0, s>>>(x, n, C, vec, reinterpret_cast<double*>(d_ws));
+    LC_LAUNCH_CHECK();
+    final3_kernel<<<1, kThreads, 0, s>>>(reinterpret_cast<double*>(d_ws), kBlocks, (double)n, d_out + 4 * b);
+    LC_LAUNCH_CHECK();
+  }
+  return LC_OK;
+}
+
 extern "C" int lc_verify_bound(const float* d_x, int C, const float* d_xhat, int64_t n_vox, double abs_err,
                                double* d_out, void* d_ws, void* stream) {
   LC_REQUIRE(d_x && d_xhat && d_out && d_ws, "null argument");

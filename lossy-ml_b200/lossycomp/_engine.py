@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import bz2
 import ctypes as C
+import hashlib
 import json
 import math
 import os
@@ -62,6 +63,27 @@ def _new_bytes(n: int):
     return obj, view
 
 
+class DevPieces:
+    """A byte string whose large parts are still on the device: an ordered list of host pieces (bytes-like) and
+    uint8 CUDA tensors.  The multi-GPU path sends the device parts over NCCL straight from the buffers the
+    Huffman packer wrote (dist.compress_sharded); tobytes() is the single-GPU materialisation."""
+
+    __slots__ = ("pieces",)
+
+    def __init__(self, pieces):
+        self.pieces = [p for p in pieces if _plen(p)]
+
+    def __len__(self):
+        return sum(_plen(p) for p in self.pieces)
+
+    def tobytes(self) -> bytes:
+        return b"".join(bytes(p) if not hasattr(p, "is_cuda") else p.cpu().numpy().tobytes() for p in self.pieces)
+
+
+def _plen(p):
+    return int(p.numel()) if hasattr(p, "numel") else len(p)
+
+
 class Engine:
     """One codec instance per (device, model, precision); replaces the per-call Keras build +
     load_weights of compress.py:41-57 / decompress.py:33-48 by a one-time weight upload."""
@@ -89,9 +111,12 @@ class Engine:
         layers = model.layers
         arr = (N.LcLayer * len(layers))()
         self._keep = []
+        wh = hashlib.sha1()
         for i, L in enumerate(layers):
             k = np.ascontiguousarray(L.kernel, dtype=np.float32)
             b = np.ascontiguousarray(L.bias, dtype=np.float32)
+            wh.update(k.tobytes())
+            wh.update(b.tobytes())
             self._keep += [k, b]
             arr[i] = N.LcLayer(0 if L.kind == "conv" else 1, L.k, L.stride, L.cin, L.cout, int(L.relu),
                                int(L.res_save), int(L.res_add), k.ctypes.data, b.ctypes.data)
@@ -99,6 +124,7 @@ class Engine:
         N.check(self.lib.lc_create(arr, len(model.encoder), len(model.decoder), model.arch.in_channels,
                                    N.PRECISIONS[precision], device, C.byref(h)), "lc_create")
         self.h = h
+        self.weights_hash = wh.hexdigest()[:16]       # recorded in every blob: the decoder must be the compressor's
         self.latent_floats = self.lib.lc_latent_floats(h)
         self._ws = None
         self._ws_chunks = 0
@@ -157,26 +183,37 @@ class Engine:
         return b
 
     # -- stages ------------------------------------------------------------------
-    def stats_raw(self, x):
-        """(sum x, sum x^2, max|x|, n) of channel 0 as Python floats (the quantities ranks all-reduce)."""
+    def stats_blocks(self, x):
+        """Per-time-chunk partial statistics of channel 0: float64 device tensor (ceil(T/16), 4) of
+        {sum x, sum x^2, max|x|, n}.  No sync.  Blocks are reduced independently in a fixed order and added in
+        index order by combine_blocks(), so a time-sharded field reproduces the single-GPU mean/std bit for bit."""
         T, H, W, Cc = x.shape
-        out = self.torch.empty(4, dtype=self.torch.float64, device=self.dev)
+        nblk = -(-T // CHUNK[0])
+        out = self.torch.empty((nblk, 4), dtype=self.torch.float64, device=self.dev)
         ws = self._buf("stats", self.lib.lc_stats_workspace_bytes())
-        N.check(self.lib.lc_stats(_ptr(x), T * H * W, Cc, _ptr(out), _ptr(ws), self._stream()), "lc_stats")
-        self.launches += 2
-        return tuple(out.cpu().tolist())
+        N.check(self.lib.lc_stats_blocks(_ptr(x), T * H * W, CHUNK[0] * H * W, Cc, _ptr(out), _ptr(ws), self._stream()),
+                "lc_stats_blocks")
+        self.launches += 2 * nblk
+        return out
 
-    def stats(self, x):
-        """compress.py:64-65 -> (mean float32, std float32, max|x|).  Sync (reads 32 bytes)."""
-        T, H, W, Cc = x.shape
-        out = self.torch.empty(4, dtype=self.torch.float64, device=self.dev)
-        ws = self._buf("stats", self.lib.lc_stats_workspace_bytes())
-        N.check(self.lib.lc_stats(_ptr(x), T * H * W, Cc, _ptr(out), _ptr(ws), self._stream()), "lc_stats")
-        self.launches += 2
-        s, s2, mx, n = out.cpu().tolist()
+    @staticmethod
+    def combine_blocks(blocks):
+        """[(sum, sum^2, max|x|, n)] per 16-step block, in time order -> (mean float32, std float32, max|x|):
+        compress.py:64-65 with fp64 accumulation (blocks added sequentially in index order)."""
+        s = s2 = n = 0.0
+        mx = 0.0
+        for b in blocks:
+            s += b[0]
+            s2 += b[1]
+            mx = max(mx, b[2])
+            n += b[3]
         mean64 = s / n
         var = max(s2 / n - mean64 * mean64, 0.0)
         return np.float32(mean64), np.float32(math.sqrt(var)), mx
+
+    def stats(self, x):
+        """compress.py:64-65 -> (mean float32, std float32, max|x|).  Sync (reads 32 bytes per time chunk)."""
+        return self.combine_blocks(self.stats_blocks(x).cpu().tolist())
 
     def n_chunks(self, T, H, W):
         g = (C.c_int * 3)()
@@ -331,27 +368,33 @@ class Engine:
         return buf, ring[i]
 
     def huff_unpack(self, payload, n: int, seg_lens: np.ndarray, table: HF.Table, seg: int = SEG):
-        """Huffman bits (bytes-like) -> n uint8 symbols on the device.  Payload, segment offsets and the decode
-        tables travel in ONE pinned staging buffer and one asynchronous copy."""
+        """Huffman bits (bytes-like, or a uint8 CUDA tensor that is already on this device) -> n uint8 symbols on
+        the device.  Host payloads, segment offsets and the decode tables travel in ONE pinned staging buffer and
+        one asynchronous copy; a device payload is copied device-to-device into a word-aligned buffer with the
+        16 spare bytes the decoder's look-ahead reads."""
         t = self.torch
         sym = t.empty(n, dtype=t.uint8, device=self.dev)
         if n == 0:
             return sym
-        npay = len(payload)
+        on_dev = hasattr(payload, "is_cuda")
+        npay = int(payload.numel()) if on_dev else len(payload)
         pay_cap = ((npay + 3) // 4) * 4 + 16                      # the decoder reads whole words past the end
         offs = np.zeros(max(seg_lens.size, 1), dtype=np.int64)
         if seg_lens.size > 1:
             np.cumsum(seg_lens[:-1], dtype=np.int64, out=offs[1:])
+        if int(offs[-1]) + int(seg_lens[-1] if seg_lens.size else 0) > 8 * npay:
+            raise N.NativeError("corrupt 'LCH1' container: the segment lengths exceed the payload")
         lut, tree = table.decode_arrays_native()
-        o_seg = (pay_cap + 7) & ~7
+        o_seg = 0 if on_dev else (pay_cap + 7) & ~7
         o_lut = o_seg + 8 * offs.size
         o_tree = (o_lut + 2 * lut.size + 3) & ~3
         total = o_tree + 4 * tree.size
         host, slot = self._stage_ring(total)
         hv = host.numpy()
-        if npay:
-            hv[:npay] = np.frombuffer(payload, dtype=np.uint8)
-        hv[npay:pay_cap] = 0
+        if not on_dev:
+            if npay:
+                hv[:npay] = np.frombuffer(payload, dtype=np.uint8)
+            hv[npay:pay_cap] = 0
         hv[o_seg:o_lut] = offs.view(np.uint8)
         hv[o_lut:o_lut + 2 * lut.size] = lut.view(np.uint8)
         hv[o_tree:total] = tree.view(np.uint8)
@@ -361,7 +404,14 @@ class Engine:
         ev.record(t.cuda.current_stream(self.dev))
         slot[1] = ev
         base = dbuf.data_ptr()
-        N.check(self.lib.lc_huff_decode(C.c_void_p(base), n, seg, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
+        if on_dev:
+            dpay = t.empty(pay_cap, dtype=t.uint8, device=self.dev)
+            dpay[:npay].copy_(payload, non_blocking=True)
+            dpay[npay:].zero_()
+            bits_ptr = dpay.data_ptr()
+        else:
+            bits_ptr = base
+        N.check(self.lib.lc_huff_decode(C.c_void_p(bits_ptr), n, seg, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
                                         HF.LUT_BITS, C.c_void_p(base + o_tree), _ptr(sym), self._stream()), "lc_huff_decode")
         self.launches += 1
         return sym
@@ -380,15 +430,32 @@ class Engine:
         return b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), lens.size), mj, tb,
                          lens.tobytes(), payload])
 
-    def unpack_stream(self, blob):
+    @staticmethod
+    def stream_head_len(blob) -> int:
+        """Bytes of an 'LCH1' container in front of its Huffman payload (magic, lengths, JSON, table, segment
+        lengths)."""
         mv = memoryview(blob)
-        assert bytes(mv[:4]) == HUFF_MAGIC
+        if bytes(mv[:4]) != HUFF_MAGIC:
+            raise N.NativeError("not an 'LCH1' container")
+        lm, ltb, nl = struct.unpack("<III", mv[4:16])
+        return 16 + lm + ltb + 2 * nl
+
+    def unpack_stream(self, blob, dev_payload=None):
+        """'LCH1' container -> (symbols on the device, header dict).  With dev_payload (uint8 CUDA tensor) `blob`
+        holds only the part in front of the payload and the payload is taken from the device."""
+        mv = memoryview(blob)
+        if bytes(mv[:4]) != HUFF_MAGIC:
+            raise N.NativeError("not an 'LCH1' container")
         lm, ltb, nl = struct.unpack("<III", mv[4:16])
         p = 16
         meta = json.loads(bytes(mv[p:p + lm])); p += lm
         table, _ = HF.Table.from_bytes(mv[p:p + ltb]); p += ltb
         lens = np.frombuffer(mv, dtype=np.uint16, count=nl, offset=p); p += 2 * nl
-        sym = self.huff_unpack(mv[p:], meta["n"], lens, table, int(meta.get("seg", SEG)))   # payload copied once, into pinned memory
+        n, seg = int(meta["n"]), int(meta.get("seg", SEG))
+        if n < 0 or seg < 64 or seg > 4096 or seg & (seg - 1) or nl != (n + seg - 1) // seg:
+            raise N.NativeError("corrupt 'LCH1' container: symbol count, segment size and segment table disagree")
+        payload = dev_payload if dev_payload is not None else mv[p:]
+        sym = self.huff_unpack(payload, n, lens, table, seg)   # host payload: copied once, into pinned memory
         return sym, meta
 
     def pack_mask(self, mask) -> bytes:
@@ -400,13 +467,15 @@ class Engine:
         self.launches += 1
         return self.pack_stream(sym, {"kind": "mask5", "n_mask": int(n)})
 
-    def unpack_mask(self, blob: bytes):
+    def unpack_mask(self, blob: bytes, dev_payload=None):
+        """Slot 7 -> int8 mask on the device.  With dev_payload, `blob` is the container without its Huffman
+        payload, which is taken from the device tensor (multi-GPU decode)."""
         t = self.torch
         from .dist import unpack_multipart
         parts = unpack_multipart(blob)
         if len(parts) > 1:
             return t.cat([self.unpack_mask(p) for p in parts])
-        sym, meta = self.unpack_stream(blob)
+        sym, meta = self.unpack_stream(blob, dev_payload)
         n = meta["n_mask"]
         if meta.get("rle"):                  # zero-run tokens -> 5-trit bytes
             tok, ns = sym, int(meta["n_sym"])
@@ -450,7 +519,8 @@ class Engine:
         escb = esc[:ne].cpu().numpy().astype("<i4").tobytes() if ne else b""
         return body + escb
 
-    def unpack_codes(self, blob: bytes):
+    def unpack_codes(self, blob: bytes, dev_payload=None):
+        """Slot 6 -> int32 codes on the device (dev_payload: see unpack_mask; the escape list stays in `blob`)."""
         t = self.torch
         from .dist import unpack_multipart
         parts = unpack_multipart(blob)
@@ -458,11 +528,13 @@ class Engine:
             return t.cat([self.unpack_codes(p) for p in parts])
         # the escape list trails the container; its length is in the header
         lm = struct.unpack("<I", blob[4:8])[0]
-        meta = json.loads(blob[16:16 + lm])
-        ne = meta["n_esc"]
+        meta = json.loads(bytes(blob[16:16 + lm]))
+        ne = int(meta["n_esc"])
         mv = memoryview(blob)
+        if ne < 0 or 4 * ne > len(mv):
+            raise N.NativeError("corrupt code container: escape count exceeds the container")
         body, escb = (mv[:len(mv) - 4 * ne], mv[len(mv) - 4 * ne:]) if ne else (mv, b"")
-        sym, meta = self.unpack_stream(body)
+        sym, meta = self.unpack_stream(body, dev_payload)
         n = meta["n"]
         if meta.get("rle"):                  # run tokens -> code symbols
             tok, n = sym, int(meta["n_sym"])
@@ -490,9 +562,11 @@ class Engine:
             self._small["pin_" + name] = b
         return b
 
-    def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str, extra: dict, tail_len: int = 0, seg: int = SEG):
+    def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str, extra: dict, tail_len: int = 0, seg: int = SEG,
+                     device_out: bool = False):
         """Enqueue the Huffman packing of `sym` (no sync) and allocate the finished 'LCH1' container as one
-        uninitialised bytes object: everything but the segment lengths, the payload and the tail is known now."""
+        uninitialised bytes object: everything but the segment lengths, the payload and the tail is known now.
+        With device_out the payload stays on the device (no bytes object; _finish_pack returns DevPieces)."""
         t = self.torch
         n = sym.numel()
         nseg = (n + seg - 1) // seg
@@ -515,6 +589,9 @@ class Engine:
         tb = table.to_bytes()
         head = b"".join([HUFF_MAGIC, struct.pack("<III", len(mj), len(tb), nseg), mj, tb])
         pay_off = len(head) + 2 * nseg
+        if device_out:
+            return dict(nseg=nseg, bits=bits, nbytes=nbytes, h_seg=h_seg, head=head, out=out, keep=(segb, d_tab),
+                        device_out=True)
         blob, view = _new_bytes(pay_off + nbytes + tail_len)
         view[:len(head)] = np.frombuffer(head, dtype=np.uint8)
         return dict(nseg=nseg, bits=bits, nbytes=nbytes, h_seg=h_seg, head_len=len(head), pay_off=pay_off, blob=blob,
@@ -523,7 +600,7 @@ class Engine:
     def _collect_pack(self, job):
         """Copy the packed payload from the device straight into its place in the container (blocking)."""
         n = job["nbytes"]
-        if n:
+        if n and not job.get("device_out"):
             dst = self.torch.from_numpy(job["view"][job["pay_off"]:job["pay_off"] + n])
             dst.copy_(job["out"][:n])
 
@@ -532,6 +609,9 @@ class Engine:
         nseg, bits = job["nseg"], job["bits"]
         offs = np.frombuffer(job["h_seg"].numpy(), dtype=np.int64, count=nseg + 1)
         assert int(offs[nseg]) == bits
+        if job.get("device_out"):
+            lens = np.diff(offs[:nseg + 1]).astype("<u2").tobytes() if nseg else b""
+            return DevPieces([job["head"] + lens, job["out"][:job["nbytes"]], tail])
         if nseg:
             lens = np.diff(offs[:nseg + 1]).astype("<u2")                                           # <= 1024*32 bits
             job["view"][job["head_len"]:job["pay_off"]] = lens.view(np.uint8)
@@ -541,13 +621,15 @@ class Engine:
         job.clear()
         return blob
 
-    def pack_streams(self, mask, q):
+    def pack_streams(self, mask, q, device_out: bool = False):
         """Entropy-code the mask and the code stream together -> (comp_error, comp_mask).
-        Same containers as pack_codes()/pack_mask(); the two pipelines share their host syncs."""
+        Same containers as pack_codes()/pack_mask(); the two pipelines share their host syncs.
+        With device_out the results are DevPieces whose Huffman payloads stay in device memory."""
         t = self.torch
         n_m, n_q = mask.numel(), q.numel()
         if n_q == 0 or n_m == 0:
-            return self.pack_codes(q), self.pack_mask(mask)
+            ce, cm = self.pack_codes(q), self.pack_mask(mask)
+            return (DevPieces([ce]), DevPieces([cm])) if device_out else (ce, cm)
         # ---- pass 1 (async): symbols of the mask, histograms of everything
         sym_m = t.empty((n_m + 4) // 5, dtype=t.uint8, device=self.dev)
         N.check(self.lib.lc_pack_trits(_ptr(mask), n_m, _ptr(sym_m), self._stream()), "lc_pack_trits")
@@ -587,7 +669,7 @@ class Engine:
         N.check(self.lib.lc_symbolize_i32(_ptr(q), n_q, diff, bias, ESC, _ptr(sym_q), _ptr(esc), _ptr(nesc),
                                           _ptr(ws), self._stream()), "lc_symbolize_i32")
         self.launches += 1
-        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", mask_extra)
+        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", mask_extra, device_out=device_out)
         tab_q, hist_q = tabs_q[pick], hists_q[pick]
         code_extra = {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne}
         # Large abs_error: nearly every code is 1 and the one-bit floor of the Huffman code dominates the slot.
@@ -607,7 +689,8 @@ class Engine:
             if tab_t.encoded_bits(hist_t) + 16 * (n_tok // SEG) < tab_q.encoded_bits(hist_q) + 16 * (n_q // SEG):
                 sym_q, tab_q, hist_q = tok_q[:n_tok], tab_t, hist_t
                 code_extra.update(rle=1, n_sym=int(n_q), run_sym=CODE_RUN[0], run_first=CODE_RUN[1])
-        job_q = self._launch_pack(sym_q, tab_q, tab_q.encoded_bits(hist_q), "q", code_extra, tail_len=4 * ne)
+        job_q = self._launch_pack(sym_q, tab_q, tab_q.encoded_bits(hist_q), "q", code_extra, tail_len=4 * ne,
+                                  device_out=device_out)
         h_esc = None
         if ne:
             h_esc = self._pinned("esc", 4 * ne)
@@ -633,7 +716,27 @@ class Engine:
 
     def _latent_meta(self, codec, **extra):
         return dict({"precision": self.precision, "model": self.model.arch.name, "filters": self.model.arch.filters,
-                     "kernel": self.model.arch.kernel, "codec": codec, "rev": NUMERICS_REV}, **extra)
+                     "kernel": self.model.arch.kernel, "codec": codec, "rev": NUMERICS_REV,
+                     "whash": self.weights_hash}, **extra)
+
+    def check_latent_meta(self, meta, lat_cols=None):
+        """The error bound only holds when the decoder that runs now is the one the compressor ran: same
+        arithmetic revision, precision, architecture and weights.  Raises NativeError otherwise."""
+        if meta.get("rev", 1) != NUMERICS_REV:
+            raise N.NativeError(f"blob was written by kernel arithmetic revision {meta.get('rev', 1)}, this build is "
+                                f"revision {NUMERICS_REV}: its reconstruction would not be reproduced bit for bit")
+        if meta.get("precision") != self.precision:
+            raise N.NativeError(f"blob was written with decoder precision {meta.get('precision')!r}, engine is "
+                                f"{self.precision!r}: the error bound only holds with identical decoder numerics")
+        a = self.model.arch
+        if (meta.get("model"), meta.get("filters"), meta.get("kernel")) != (a.name, a.filters, a.kernel):
+            raise N.NativeError(f"blob was written with model {meta.get('model')!r} (filters {meta.get('filters')}, kernel "
+                                f"{meta.get('kernel')}), engine holds {a.name!r} (filters {a.filters}, kernel {a.kernel})")
+        if meta.get("whash", self.weights_hash) != self.weights_hash:
+            raise N.NativeError(f"blob was written with other weights of model {a.name!r} (hash {meta['whash']}, engine "
+                                f"{self.weights_hash}): its reconstruction would not be reproduced")
+        if lat_cols is not None and lat_cols != self.latent_floats:
+            raise N.NativeError(f"latent has {lat_cols} values per chunk, the engine's decoder expects {self.latent_floats}")
 
     def pack_latent(self, latent, codec="raw", staged=None) -> bytes:
         mj = json.dumps(self._latent_meta(codec)).encode()
@@ -663,7 +766,7 @@ class Engine:
         mj = json.dumps(self._latent_meta("f16", n=int(n))).encode()
         return b"".join([LATENT_MAGIC, struct.pack("<I", len(mj)), mj, lo_bytes, hi_container])
 
-    def pack_latent_f16(self, lo, hi, ev) -> bytes:
+    def pack_latent_f16(self, lo, hi, ev, device_out: bool = False):
         """Entropy-code the planes of quantize_latent() on a side stream.  Call it after the decoder has been
         enqueued: only the side stream is synchronised, so the two host syncs of the Huffman stage hide behind
         the decoder's kernels."""
@@ -677,14 +780,19 @@ class Engine:
             h = t.empty(256, dtype=t.int32, device=self.dev)
             N.check(self.lib.lc_hist_u8(_ptr(hi), n, _ptr(h), self._stream()), "lc_hist_u8")
             self.launches += 1
-            h_lo = self._pinned("lat_lo", n)
-            h_lo[:n].copy_(lo, non_blocking=True)
+            if not device_out:
+                h_lo = self._pinned("lat_lo", n)
+                h_lo[:n].copy_(lo, non_blocking=True)
             hist = h.cpu().numpy().astype(np.int64) & 0xFFFFFFFF                  # syncs the side stream only
             table = HF.build_table_native(hist)
-            job = self._launch_pack(hi, table, table.encoded_bits(hist), "lat", {"kind": "latent_hi"}, seg=LATENT_SEG)
+            job = self._launch_pack(hi, table, table.encoded_bits(hist), "lat", {"kind": "latent_hi"}, seg=LATENT_SEG,
+                                    device_out=device_out)
             self._collect_pack(job)
             side.synchronize()
             hi_container = self._finish_pack(job)
+        if device_out:          # header | low plane (device) | 'LCH1' of the high plane (payload on the device)
+            mj = json.dumps(self._latent_meta("f16", n=int(n))).encode()
+            return DevPieces([b"".join([LATENT_MAGIC, struct.pack("<I", len(mj)), mj]), lo] + hi_container.pieces)
         return self._f16_container(n, memoryview(h_lo.numpy())[:n], hi_container)
 
     def _split_f16(self, blob, meta, lm):
@@ -692,60 +800,52 @@ class Engine:
         off = 8 + lm
         return n, blob[off:off + n], blob[off + n:]
 
-    def join_latents(self, blobs) -> bytes:
-        """Concatenate the latent containers of consecutive chunk ranges (time shards) into one."""
+    def unpack_latent(self, blob: bytes, shape, dev=None):
+        """Slot 0 -> (latent (N, latent_floats) float32 on the device, header dict).  A multi-part container
+        ('LCM1', written by the time-sharded compressor) is the concatenation of its parts' chunks.  With
+        dev = (low plane, Huffman payload of the high plane) as uint8 CUDA tensors, `blob` is the 'f16' container
+        without those two parts (multi-GPU decode)."""
+        from .dist import unpack_multipart
         t = self.torch
-        metas, bodies = [], []
-        for b in blobs:
-            assert b[:4] == LATENT_MAGIC
-            (lm,) = struct.unpack("<I", b[4:8])
-            metas.append((json.loads(b[8:8 + lm]), lm))
-            bodies.append(b)
-        first = metas[0][0]
-        assert all(m["precision"] == first["precision"] and m["model"] == first["model"] and
-                   m.get("rev", 1) == first.get("rev", 1) for m, _ in metas)
-        if all(m.get("codec") == "f16" for m, _ in metas):
-            los, his = [], []
-            for (m, lm), b in zip(metas, bodies):
-                n, lo, hic = self._split_f16(b, m, lm)
-                los.append(lo)
-                his.append(self.unpack_stream(hic)[0])
-            hi = t.cat(his)
-            return self._f16_container(hi.numel(), b"".join(los), self.pack_stream(hi, {"kind": "latent_hi"}))
-        raws = []
-        for (m, lm), b in zip(metas, bodies):
-            if m.get("codec") == "f16":
-                n = int(m["n"])
-                raws.append(self.unpack_latent(b, (1, n))[0].cpu().numpy().astype("<f4").tobytes())
-            else:
-                raw = b[8 + lm:]
-                raws.append(bz2.decompress(raw) if m.get("codec") == "bz2" else raw)
-        mj = json.dumps(dict(first, codec="raw")).encode()
-        return LATENT_MAGIC + struct.pack("<I", len(mj)) + mj + b"".join(raws)
-
-    def unpack_latent(self, blob: bytes, shape):
+        parts = unpack_multipart(blob)
+        if len(parts) > 1:
+            outs, meta = [], None
+            for p in parts:
+                lat, meta = self.unpack_latent(p, None)
+                outs.append(lat)
+            lat = t.cat(outs)
+            if shape is not None and lat.shape[0] != int(shape[0]):
+                raise N.NativeError("latent parts do not add up to the chunk count of blob slot 1")
+            return lat, meta
         if blob[:4] != LATENT_MAGIC:
             raise N.NativeError("blob slot 0 is not an 'LCL1' latent container (fpzip streams written by the "
                                 "TensorFlow reference cannot be decoded: fpzip is not available and the decoder "
                                 "numerics must match the compressor's, SURVEY.md H2)")
         (lm,) = struct.unpack("<I", blob[4:8])
-        meta = json.loads(blob[8:8 + lm])
-        if meta.get("rev", 1) != NUMERICS_REV:
-            raise N.NativeError(f"blob was written by kernel arithmetic revision {meta.get('rev', 1)}, this build is "
-                                f"revision {NUMERICS_REV}: its reconstruction would not be reproduced bit for bit")
+        meta = json.loads(bytes(blob[8:8 + lm]))
+        self.check_latent_meta(meta)
+        F = self.latent_floats
         if meta.get("codec") == "f16":
-            t = self.torch
-            n, lo_b, hic = self._split_f16(blob, meta, lm)
-            assert n == int(np.prod(shape))
-            lo = t.from_numpy(np.frombuffer(lo_b, dtype=np.uint8).copy()).to(self.dev, non_blocking=True)
-            hi = self.unpack_stream(hic)[0]
-            lat = t.empty((shape[0], n // shape[0]), dtype=t.float32, device=self.dev)
+            n = int(meta["n"])
+            if n % F or (shape is not None and n != int(np.prod(shape))):
+                raise N.NativeError("latent container does not match the chunk count / the engine's latent size")
+            if dev is not None:
+                lo, hi = dev[0], self.unpack_stream(blob[8 + lm:], dev[1])[0]
+            else:
+                _, lo_b, hic = self._split_f16(blob, meta, lm)
+                lo = t.from_numpy(np.frombuffer(lo_b, dtype=np.uint8).copy()).to(self.dev, non_blocking=True)
+                hi = self.unpack_stream(hic)[0]
+            if lo.numel() != n or hi.numel() != n:
+                raise N.NativeError("corrupt latent container: byte planes do not match the value count")
+            lat = t.empty((n // F, F), dtype=t.float32, device=self.dev)
             N.check(self.lib.lc_latent_dequantize(_ptr(lo), _ptr(hi), n, _ptr(lat), self._stream()), "lc_latent_dequantize")
             self.launches += 1
             return lat, meta
         raw = blob[8 + lm:]
         if meta.get("codec") == "bz2":
             raw = bz2.decompress(raw)
-        n = int(np.prod(shape))
-        lat = np.frombuffer(raw, dtype="<f4", count=n).reshape(shape[0], -1)
+        n = len(raw) // 4 if shape is None else int(np.prod(shape))
+        if n % F or len(raw) < 4 * n:
+            raise N.NativeError("latent container does not match the chunk count / the engine's latent size")
+        lat = np.frombuffer(raw, dtype="<f4", count=n).reshape(n // F, F)
         return self.torch.from_numpy(lat.copy()).to(self.dev), meta

@@ -46,6 +46,7 @@ SIGNATURES = {
     "lc_chunk_window": (_i, [_i, _i, _i, _i, C.POINTER(_i * 6)]),
     "lc_stats_workspace_bytes": (_sz, []),
     "lc_stats": (_i, [_p, _i64, _i, _p, _p, _p]),
+    "lc_stats_blocks": (_i, [_p, _i64, _i64, _i, _p, _p, _p]),
     "lc_ae_workspace_bytes": (_sz, [_p, _i]),
     "lc_encode": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _i, _p, _p, _sz, _p]),
     "lc_decode": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),

@@ -78,8 +78,12 @@ class _StageTimer:
 
 
 def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff", verify=None,
-                    inject=None, latent_codec=None, batch=None, return_parts=False, timing=False):
-    """x: torch float32 CUDA tensor (T,H,W,2).  Returns (slots list, info dict)."""
+                    inject=None, latent_codec=None, batch=None, return_parts=False, timing=False,
+                    device_out=False, agree=None):
+    """x: torch float32 CUDA tensor (T,H,W,2).  Returns (slots list, info dict).
+    device_out: slots 0/6/7 come back as _engine.DevPieces whose payloads are still in device memory (the
+    multi-GPU path sends them over NCCL from there).  agree(violations) -> the count every rank must act on
+    (dist.compress_sharded passes an all-reduce MAX so that all ranks widen the guard band together)."""
     assert err_threshold != 0, "The absolute error can't be 0."                      # compress.py:34
     assert x.dim() == 4 and x.shape[3] == eng.model.arch.in_channels, \
         "Input should have %d channels." % eng.model.arch.in_channels                # compress.py:55
@@ -108,7 +112,7 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         recon = eng.decode(latent, T, H, W, batch=batch)                             # compress.py:99-111
     comp_data = None
     if latent_codec == "f16":
-        comp_data = eng.pack_latent_f16(*planes)                                     # side stream, behind the decoder
+        comp_data = eng.pack_latent_f16(*planes, device_out=device_out)              # side stream, behind the decoder
     tm and tm.mark("decode")
     thr = abs_err
     info = {"mode": mode, "codec": codec}
@@ -133,6 +137,8 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
             mask, q = eng.quantize(x, recon, mean, std, thr)
             break
         info.update(violations=viol, max_err=max_err)
+        if agree is not None and mode == "strict":
+            viol = agree(viol)
         if viol == 0 or mode != "strict":
             break
         thr = abs_err - 2.0 * (abs_err - thr)    # widen the guard band and redo the cheap stages
@@ -149,7 +155,7 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         comp_error = bz2.compress(dq.tobytes(), 9)                                   # compress.py:156
         comp_mask = bz2.compress(dm.tobytes(), 9)                                    # compress.py:166
     elif codec == "huff":
-        comp_error, comp_mask = eng.pack_streams(mask, q)
+        comp_error, comp_mask = eng.pack_streams(mask, q, device_out=device_out)
         tm and tm.mark("pack_streams")
     else:
         raise ValueError("codec must be 'huff' or 'bz2'")

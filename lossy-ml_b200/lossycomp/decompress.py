@@ -35,9 +35,9 @@ def decompress_device(eng: Engine, slots, *, inject=None, batch=None, rows=None)
         c1 = c0 + (-(-(t1 - t0) // 16)) * per_tc
         latent = latent[c0:c1].contiguous()
         T = t1 - t0
-    if meta["precision"] != eng.precision:
-        raise N.NativeError(f"blob was written with decoder precision {meta['precision']!r}, engine is "
-                            f"{eng.precision!r}: the error bound only holds with identical decoder numerics")
+    if latent.shape[1] != eng.latent_floats:
+        raise N.NativeError(f"latent has {latent.shape[1]} values per chunk, the engine's decoder expects "
+                            f"{eng.latent_floats}")
     if inject and "recon_std" in inject:
         recon = inject["recon_std"]
     else:
@@ -53,7 +53,8 @@ def decompress_device(eng: Engine, slots, *, inject=None, batch=None, rows=None)
     else:                                                                            # decompress.py:81-84
         dm = np.frombuffer(bz2.decompress(comp_mask), dtype=np.int8).reshape((n,))
         mask = eng.cumsum(torch.from_numpy(dm.copy()).to(eng.dev))
-    assert q.numel() == int(error_shape[0]) and mask.numel() == n
+    if q.numel() != int(error_shape[0]) or mask.numel() != n:
+        raise N.NativeError("corrupt blob: the decoded streams do not have the lengths the blob declares")
     if rows is not None:                 # this shard's part of the global mask / code streams
         lo, hi = t0 * H * W, t1 * H * W
         off = int((mask[:lo] > 0).sum().item())
@@ -68,11 +69,19 @@ def decompress(compressed_data, verbose=False, *, precision=None, model=None, de
     `out` (optional, float32, T*H*W elements) is filled and returned instead of a new array."""
     N.require_cuda()
     slots = pickle.loads(compressed_data)                                            # decompress.py:54
+    try:
+        meta = _peek_meta(slots[0])
+    except Exception:
+        meta = {}
     if precision is None:
-        try:
-            precision = _peek_precision(slots[0])
-        except Exception:
-            precision = None
+        precision = meta.get("precision")
+    if model is None and meta.get("model"):
+        # the blob names the architecture it was written with: use the shipped weights of that name when there are
+        # any (Engine.check_latent_meta then verifies architecture and weight hash, and refuses a mismatch)
+        from .models import default_model_path, shipped_model_path
+        cand = shipped_model_path(meta["model"])
+        if cand and cand != default_model_path():
+            model = cand
     eng = Engine.get(model, precision, device)
     T, H, W = (int(v) for v in slots[2][:3])
     pending = ()
@@ -84,8 +93,11 @@ def decompress(compressed_data, verbose=False, *, precision=None, model=None, de
     return _hostio.d2h(eng, dev_out, (T, H, W, 1), out=out, wait=pending)            # decompress.py:104-108
 
 
-def _peek_precision(comp_data: bytes):
+def _peek_meta(comp_data: bytes) -> dict:
+    """Header of the (first) 'LCL1' container of blob slot 0."""
     import json
     import struct
-    (lm,) = struct.unpack("<I", comp_data[4:8])
-    return json.loads(comp_data[8:8 + lm])["precision"]
+    from .dist import unpack_multipart
+    first = unpack_multipart(comp_data)[0]
+    (lm,) = struct.unpack("<I", first[4:8])
+    return json.loads(bytes(first[8:8 + lm]))

@@ -7,16 +7,22 @@ the re-anchored tail window, which is anchored at the END of the axis both local
 is exactly its part of the global one.  To produce the blob a single compress() call would have
 produced, only three things cross ranks:
 
-  1. the statistics of channel 0 (compress.py:64-65 are global): all-reduce of {sum, sum^2, n} (SUM)
-     and max|x| (MAX) -- 32 bytes;
-  2. the outlier counts (slot 3) -- 8 bytes per rank;
-  3. the blob parts (latent rows, entropy-coded code / mask streams) gathered to rank 0.
+  1. the statistics of channel 0 (compress.py:64-65 are global): every rank reduces its own 16-step
+     time blocks (lc_stats_blocks) and the per-block partials are all-reduced (SUM over disjoint
+     entries, exact; MAX for max|x|) -- every rank then adds the blocks in time order, which is the
+     arithmetic of the single-GPU call, so mean and std are bit-identical for any rank count;
+  2. strict mode's verdict (the largest violation count), so that every rank widens its guard band
+     together -- 8 bytes;
+  3. the blob parts: latent rows and the entropy-coded code / mask streams go to rank `dst` with NCCL
+     send/recv straight from the device buffers the Huffman packer wrote (no host staging of the
+     payloads); rank `dst` copies them to its host once.
 
-The entropy containers of slots 6/7 become multi-part ('LCM1': one self-contained 'LCH1' stream per
-rank, first differences restarting at every part), so no seam values and no shared Huffman table are
+Slots 0/6/7 become multi-part containers ('LCM1': one self-contained 'LCL1' / 'LCH1' stream per rank,
+first differences restarting at every part), so no seam values and no shared Huffman table are
 needed; the decoded mask / codes / reconstruction are bit-identical to the single-GPU ones.
-NCCL carries the collectives on GPUs; the same code runs on gloo with CPU tensors for the host-logic
-tests.
+decompress_sharded() is the inverse: rank `src` sends every rank the parts of its own time shard and
+each rank decodes its rows only.  NCCL carries the collectives on GPUs; the host-logic tests run the
+same code on gloo with CPU tensors.
 """
 from __future__ import annotations
 
@@ -29,6 +35,7 @@ import numpy as np
 
 MULTI_MAGIC = b"LCM1"
 CHUNK_T = 16
+BIG = (0, 6, 7)          # the slots that are byte strings
 
 
 # ------------------------------------------------------------------------------------------
@@ -56,30 +63,44 @@ def shard_time(T: int, world: int) -> List[Tuple[int, int]]:
 
 
 def combine_stats(parts: Sequence[Sequence[float]]):
-    """[(sum, sum^2, max|x|, n)] per rank -> (mean float32, std float32, max|x|), the same formula the
-    single-GPU path applies to its own sums (Engine.stats)."""
-    s = sum(p[0] for p in parts)
-    s2 = sum(p[1] for p in parts)
-    mx = max(p[2] for p in parts)
-    n = sum(p[3] for p in parts)
+    """[(sum, sum^2, max|x|, n)] per 16-step time block, in time order -> (mean float32, std float32, max|x|),
+    the same formula (and the same order of additions) the single-GPU path applies to its own blocks
+    (Engine.combine_blocks)."""
+    s = s2 = n = 0.0
+    mx = 0.0
+    for p in parts:
+        s += p[0]
+        s2 += p[1]
+        mx = max(mx, p[2])
+        n += p[3]
     mean64 = s / n
     var = max(s2 / n - mean64 * mean64, 0.0)
     return np.float32(mean64), np.float32(math.sqrt(var)), mx
 
 
 def pack_multipart(parts: Sequence[bytes]) -> bytes:
-    """Several self-contained entropy streams -> one slot payload."""
+    """Several self-contained streams -> one slot payload."""
     if len(parts) == 1:
-        return parts[0]
+        return bytes(parts[0])
     return b"".join([MULTI_MAGIC, struct.pack("<I", len(parts)),
                      struct.pack(f"<{len(parts)}Q", *(len(p) for p in parts))] + list(parts))
 
 
-def unpack_multipart(blob: bytes) -> List[bytes]:
-    if blob[:4] != MULTI_MAGIC:
+def multipart_header(lens: Sequence[int]) -> bytes:
+    return b"".join([MULTI_MAGIC, struct.pack("<I", len(lens)), struct.pack(f"<{len(lens)}Q", *lens)])
+
+
+def unpack_multipart(blob) -> list:
+    """Inverse of pack_multipart; the parts are slices (views for a memoryview input).  Raises ValueError on a
+    container whose part table does not fit its length."""
+    if bytes(blob[:4]) != MULTI_MAGIC:
         return [blob]
     (n,) = struct.unpack("<I", blob[4:8])
+    if n <= 0 or 8 + 8 * n > len(blob):
+        raise ValueError("corrupt 'LCM1' container: part table exceeds the container")
     lens = struct.unpack(f"<{n}Q", blob[8:8 + 8 * n])
+    if 8 + 8 * n + sum(lens) != len(blob):
+        raise ValueError("corrupt 'LCM1' container: part lengths do not add up")
     out, p = [], 8 + 8 * n
     for ln in lens:
         out.append(blob[p:p + ln])
@@ -87,9 +108,9 @@ def unpack_multipart(blob: bytes) -> List[bytes]:
     return out
 
 
-def assemble_blob(rank_slots: Sequence[list], latent_join) -> list:
+def assemble_blob(rank_slots: Sequence[list], join=pack_multipart) -> list:
     """Per-rank slot lists (each describing its own time shard) -> the slot list of the whole field.
-    `latent_join(list of slot-0 payloads) -> payload` concatenates the latent containers."""
+    `join(list of payloads) -> payload` builds the multi-part containers of slots 0, 6 and 7."""
     first = rank_slots[0]
     n_chunks = sum(s[1][0] for s in rank_slots)
     T = sum(s[2][0] for s in rank_slots)
@@ -97,20 +118,19 @@ def assemble_blob(rank_slots: Sequence[list], latent_join) -> list:
     for s in rank_slots:
         assert s[4] == first[4] and s[5] == first[5] and s[8] == first[8], "ranks disagree on mean/std/threshold"
         assert tuple(s[2][1:]) == tuple(first[2][1:]) and tuple(s[1][1:]) == tuple(first[1][1:])
-    return [latent_join([s[0] for s in rank_slots]), (n_chunks,) + tuple(first[1][1:]),
+    return [join([s[0] for s in rank_slots]), (n_chunks,) + tuple(first[1][1:]),
             (T,) + tuple(first[2][1:]), (n_out,), first[4], first[5],
-            pack_multipart([s[6] for s in rank_slots]), pack_multipart([s[7] for s in rank_slots]), first[8]]
+            join([s[6] for s in rank_slots]), join([s[7] for s in rank_slots]), first[8]]
 
 
 def frame_slots(slots) -> list:
     """Slot list -> [small pickled header, payload 0, payload 6, payload 7]: the three large byte strings
     travel unpickled, so framing costs no extra copy of the payloads."""
-    big = (0, 6, 7)
     head = list(slots)
-    for i in big:
+    for i in BIG:
         head[i] = len(slots[i])
     h = pickle.dumps(head)
-    return [struct.pack("<I", len(h)), h] + [slots[i] for i in big]
+    return [struct.pack("<I", len(h)), h] + [slots[i] for i in BIG]
 
 
 def unframe_slots(buf) -> list:
@@ -119,121 +139,460 @@ def unframe_slots(buf) -> list:
     (hl,) = struct.unpack("<I", mv[:4])
     head = pickle.loads(mv[4:4 + hl])
     p = 4 + hl
-    for i in (0, 6, 7):
+    for i in BIG:
         n = head[i]
         head[i] = bytes(mv[p:p + n])
         p += n
     return head
 
 
+# ---- frames whose large parts stay on the device ---------------------------------------------------
+def _is_dev(p):
+    return hasattr(p, "is_cuda")
+
+
+def _pieces(v):
+    return v.pieces if hasattr(v, "pieces") else [v]
+
+
+def frame_layout(slots):
+    """Slot list whose big slots are bytes or _engine.DevPieces -> (pickled head, host pieces, device pieces).
+    The head is the slot list with every big slot replaced by its piece table [(is_device, length), ...]; a frame
+    is  u32 len(head) | head | host pieces | device pieces  and rank `dst` rebuilds each slot by walking the
+    tables."""
+    head = list(slots)
+    host, dev = [], []
+    for i in BIG:
+        table = []
+        for p in _pieces(slots[i]):
+            if _is_dev(p):
+                table.append((1, int(p.numel())))
+                dev.append(p)
+            else:
+                table.append((0, len(p)))
+                host.append(p)
+        head[i] = table
+    return pickle.dumps(head), host, dev
+
+
+def parse_frame(buf):
+    """Inverse of frame_layout on a host copy of a frame: -> slot list whose big slots are lists of memoryview
+    pieces (in order) of `buf`."""
+    mv = memoryview(buf)
+    (hl,) = struct.unpack("<I", mv[:4])
+    head = pickle.loads(mv[4:4 + hl])
+    hp = 4 + hl
+    dp = hp + sum(n for i in BIG for d, n in head[i] if not d)
+    for i in BIG:
+        parts = []
+        for d, n in head[i]:
+            if d:
+                parts.append(mv[dp:dp + n])
+                dp += n
+            else:
+                parts.append(mv[hp:hp + n])
+                hp += n
+        head[i] = parts
+    return head
+
+
 # ------------------------------------------------------------------------------------------
 # collectives (NCCL on GPUs, gloo on CPU tensors)
 # ------------------------------------------------------------------------------------------
-def all_reduce_stats(local, group=None, device=None):
-    """local = (sum, sum^2, max|x|, n) -> the same tuple over all ranks."""
+def comm_device(dev, group=None):
+    """Where collective operands live: the GPU for NCCL; host memory for gloo (the CPU tests, and the two-process
+    test that shares one GPU, where NCCL cannot run)."""
+    import torch.distributed as dist
+    return dev if dist.get_backend(group) == "nccl" else "cpu"
+
+
+def all_reduce_blocks(local_blocks, block0: int, n_blocks: int, group=None, device=None):
+    """local_blocks: (k, 4) float64 tensor of {sum, sum^2, max|x|, n} of this rank's time blocks, which are blocks
+    [block0, block0 + k) of the whole field's n_blocks -> list of n_blocks tuples, identical on every rank.
+    Sums travel in one all-reduce over disjoint entries (x + 0 is exact in any order), the maxima in another."""
     import torch
     import torch.distributed as dist
-    a = torch.tensor([local[0], local[1], local[3]], dtype=torch.float64, device=device)
-    m = torch.tensor([local[2]], dtype=torch.float64, device=device)
+    k = int(local_blocks.shape[0]) if local_blocks is not None else 0
+    a = torch.zeros((n_blocks, 3), dtype=torch.float64, device=device)
+    m = torch.zeros((n_blocks,), dtype=torch.float64, device=device)
+    if k:
+        lb = local_blocks.to(device)
+        a[block0:block0 + k, 0] = lb[:, 0]
+        a[block0:block0 + k, 1] = lb[:, 1]
+        a[block0:block0 + k, 2] = lb[:, 3]
+        m[block0:block0 + k] = lb[:, 2]
     dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
     a = a.cpu().tolist()
-    return (a[0], a[1], float(m.item()), a[2])
+    m = m.cpu().tolist()
+    return [(a[i][0], a[i][1], m[i], a[i][2]) for i in range(n_blocks)]
 
 
-_pinned = {}
-
-
-def _stage(parts, device):
-    """Concatenate byte strings straight into a (reused) pinned host tensor and start the copy to `device`."""
+def all_reduce_max(value: int, group=None, device=None) -> int:
     import torch
-    total = sum(len(p) for p in parts)
-    use_pin = device is not None and torch.device(device).type == "cuda"
-    key = str(device)
-    host = _pinned.get(key)
-    if host is None or host.numel() < total:
-        host = torch.empty(max(int(total * 1.25), 1 << 16), dtype=torch.uint8, pin_memory=use_pin)
-        _pinned[key] = host
-    hv = host.numpy()
-    off = 0
-    for p in parts:
-        n = len(p)
-        if n:
-            hv[off:off + n] = np.frombuffer(p, dtype=np.uint8)
-        off += n
-    return host, total
+    import torch.distributed as dist
+    v = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX, group=group)
+    return int(v.item())
 
 
-def gather_bytes(payload, dst: int = 0, group=None, device=None, to_host: bool = True):
-    """Variable-length byte strings of all ranks -> list on rank `dst` (None elsewhere).  `payload` is a
-    bytes object or a list of bytes objects (sent as their concatenation).  Lengths travel in an
-    all-gather, payloads in one padded gather (NCCL over NVLink on GPUs).  With to_host=False rank `dst`
-    keeps the parts as uint8 tensors on its device (no PCIe trip)."""
+def gather_tensors(frame, meta: int = 0, dst: int = 0, group=None):
+    """Variable-length uint8 tensors of all ranks -> on rank `dst` (recv buffer holding all frames back to back,
+    [(offset, length, meta)] per rank), None elsewhere.  `meta` is one integer per rank that travels with the
+    lengths (the frames' host-section length).  Lengths: one all-gather; payloads: point-to-point send/recv posted
+    as one group (NCCL over NVLink on GPUs), straight from / into device memory."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    parts = payload if isinstance(payload, (list, tuple)) else [payload]
-    host, total = _stage(parts, device)
-    n = torch.tensor([total], dtype=torch.int64, device=device)
+    if frame.is_cuda and dist.get_backend(group) != "nccl":
+        frame = frame.cpu()
+    dev = frame.device
+    n = torch.tensor([int(frame.numel()), int(meta)], dtype=torch.int64, device=dev)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
-    sizes = [int(v) for v in torch.cat(sizes).cpu().tolist()]
-    cap = max(max(sizes), 1)
-    buf = torch.empty(cap, dtype=torch.uint8, device=device)
-    if total:
-        buf[:total].copy_(host[:total], non_blocking=True)
-    if rank == dst:
-        recv = torch.empty((world, cap), dtype=torch.uint8, device=device)
-        dist.gather(buf, list(recv.unbind(0)), dst=dst, group=group)
-        if not to_host:
-            return [recv[i, :sizes[i]] for i in range(world)]
-        hostr = recv.cpu()
-        return [hostr[i, :sizes[i]].numpy().tobytes() for i in range(world)]
-    dist.gather(buf, None, dst=dst, group=group)
-    return None
+    sizes = torch.stack(sizes).cpu().tolist()
+    if rank != dst:
+        if frame.numel():
+            dist.send(frame, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        return None
+    offs, o = [], 0
+    for ln, _ in sizes:
+        offs.append(o)
+        o += (int(ln) + 15) & ~15
+    recv = torch.empty(max(o, 16), dtype=torch.uint8, device=dev)
+    ops = []
+    for r, (ln, _) in enumerate(sizes):
+        if not ln:
+            continue
+        view = recv[offs[r]:offs[r] + int(ln)]
+        if r == rank:
+            view.copy_(frame, non_blocking=True)
+        else:
+            src = dist.get_global_rank(group, r) if group is not None else r
+            ops.append(dist.P2POp(dist.irecv, view, src, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return recv, [(offs[r], int(sizes[r][0]), int(sizes[r][1])) for r in range(world)]
+
+
+def gather_bytes(payload, dst: int = 0, group=None, device=None, to_host: bool = True):
+    """Variable-length byte strings of all ranks -> list on rank `dst` (None elsewhere).  `payload` is a
+    bytes object or a list of bytes objects (sent as their concatenation)."""
+    import torch
+    parts = payload if isinstance(payload, (list, tuple)) else [payload]
+    raw = b"".join(bytes(p) for p in parts)
+    frame = torch.frombuffer(bytearray(raw), dtype=torch.uint8) if raw else torch.empty(0, dtype=torch.uint8)
+    if device is not None:
+        frame = frame.to(device)
+    got = gather_tensors(frame, 0, dst, group)
+    if got is None:
+        return None
+    recv, table = got
+    if not to_host:
+        return [recv[o:o + n] for o, n, _ in table]
+    host = recv.cpu().numpy()
+    return [host[o:o + n].tobytes() for o, n, _ in table]
 
 
 # ------------------------------------------------------------------------------------------
 # sharded codec
 # ------------------------------------------------------------------------------------------
-def compress_sharded(eng, x_local, err_threshold, *, mode="strict", codec="huff", group=None, dst=0):
-    """Every rank passes its own rows (a time shard made with shard_time) as a CUDA tensor
-    (T_local, H, W, 2); rank `dst` gets the slot list of the WHOLE field (others None), plus an info
-    dict on every rank."""
+def build_frame(eng, slots):
+    """Slot list (big slots bytes or DevPieces) -> (uint8 device tensor holding the frame, length of its host
+    section).  Host pieces go through one pinned staging copy, device pieces are copied device to device."""
+    import torch
+    head, host, dev = frame_layout(slots)
+    n_host = 4 + len(head) + sum(len(p) for p in host)
+    total = n_host + sum(int(p.numel()) for p in dev)
+    frame = torch.empty(total, dtype=torch.uint8, device=eng.dev)
+    stage, slot = eng._stage_ring(n_host)
+    hv = stage.numpy()
+    hv[:4] = np.frombuffer(struct.pack("<I", len(head)), dtype=np.uint8)
+    o = 4
+    for p in [head] + host:
+        n = len(p)
+        hv[o:o + n] = np.frombuffer(p, dtype=np.uint8)
+        o += n
+    frame[:n_host].copy_(stage[:n_host], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(eng.dev))
+    slot[1] = ev
+    for p in dev:
+        n = int(p.numel())
+        frame[o:o + n].copy_(p, non_blocking=True)
+        o += n
+    return frame, n_host
+
+
+def _copy_views(dst_views, src_views, pool=None):
+    """Copy pairs of equally long uint8 numpy views, large ones in the thread pool (numpy releases the GIL)."""
+    jobs = []
+    for d, s in zip(dst_views, src_views):
+        if pool is not None and d.size > (1 << 20):
+            jobs.append(pool.submit(np.copyto, d, s))
+        else:
+            np.copyto(d, s)
+    for j in jobs:
+        j.result()
+
+
+def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="strict", codec="huff", group=None,
+                     dst=0, as_bytes=True):
+    """Every rank passes its own rows [t0, t0 + T_local) of a field of T rows (a time shard made with shard_time)
+    as a CUDA tensor (T_local, H, W, 2); rank `dst` gets the slot list of the WHOLE field (others None), plus an
+    info dict on every rank.  t0 / T default to this rank's shard of shard_time(sum of T_local, world).
+    as_bytes=False leaves rank dst's big slots as memoryviews over a pinned buffer that the next call reuses."""
+    import torch
     import torch.distributed as dist
+    from . import _hostio
+    from ._engine import DevPieces, _new_bytes
     from .compress import compress_device
     dev = eng.dev
+    cdev = comm_device(dev, group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     T_local = int(x_local.shape[0])
-    local = eng.stats_raw(x_local) if T_local else (0.0, 0.0, 0.0, 0.0)
-    mean, std, max_abs = combine_stats([all_reduce_stats(local, group, dev)])
+    if t0 is None or T is None:
+        tl = torch.tensor([T_local], dtype=torch.int64, device=cdev)
+        alls = [torch.zeros_like(tl) for _ in range(world)]
+        dist.all_gather(alls, tl, group=group)
+        alls = [int(v) for v in torch.cat(alls).cpu().tolist()]
+        t0, T = sum(alls[:rank]), sum(alls)
+    assert t0 % CHUNK_T == 0, "a time shard must start on a 16-step chunk boundary"
+    n_blocks = -(-int(T) // CHUNK_T)
+    blocks = all_reduce_blocks(eng.stats_blocks(x_local) if T_local else None, t0 // CHUNK_T, n_blocks, group, cdev)
+    mean, std, max_abs = combine_stats(blocks)
     if T_local:
-        slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec,
-                                      inject={"mean": mean, "std": std, "max_abs": max_abs})
-        mine = frame_slots(slots)
+        slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec, device_out=True,
+                                      inject={"mean": mean, "std": std, "max_abs": max_abs},
+                                      agree=lambda v: all_reduce_max(v, group, cdev))
+        for i in BIG:
+            if not isinstance(slots[i], DevPieces):
+                slots[i] = DevPieces([slots[i]])
+        frame, n_host = build_frame(eng, slots)
     else:
-        slots, info, mine = None, {"n_out": 0}, b""
-    parts = gather_bytes(mine, dst, group, dev)
-    if dist.get_rank(group) != dst:
+        if mode == "strict":                       # take part in the verdict exchange of the retry loop
+            while all_reduce_max(0, group, cdev):
+                pass
+        info = {"n_out": 0}
+        frame, n_host = torch.empty(0, dtype=torch.uint8, device=dev), 0
+    got = gather_tensors(frame, n_host, dst, group)
+    if got is None:
         return None, info
-    rank_slots = [unframe_slots(p) for p in parts if p]
-    return assemble_blob(rank_slots, eng.join_latents), info
+    recv, table = got
+    # one device->host copy of everything, then the slot byte strings are cut out of the pinned buffer
+    total = int(recv.numel())
+    if recv.is_cuda:
+        pin = eng._pinned("gather", total)
+        pin[:total].copy_(recv, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    else:
+        pin = recv
+    hv = memoryview(pin.numpy())
+    rank_slots = [parse_frame(hv[o:o + n]) for o, n, _ in table if n]
+
+    def join(parts_per_rank):
+        """[[piece views of rank r's container]] -> the multi-part container (one copy of the payloads)."""
+        lens = [sum(len(p) for p in parts) for parts in parts_per_rank]
+        hdr = multipart_header(lens) if len(parts_per_rank) > 1 else b""
+        if not as_bytes:
+            return [hdr] + [p for parts in parts_per_rank for p in parts]
+        obj, view = _new_bytes(len(hdr) + sum(lens))
+        view[:len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
+        o = len(hdr)
+        dsts, srcs = [], []
+        for parts in parts_per_rank:
+            for p in parts:
+                dsts.append(view[o:o + len(p)])
+                srcs.append(np.frombuffer(p, dtype=np.uint8))
+                o += len(p)
+        _copy_views(dsts, srcs, _hostio._threads())
+        return obj
+
+    return assemble_blob(rank_slots, join), info
+
+
+def _cut(blob, head_len, tail_len=0):
+    """(container without its payload, payload view) of an 'LCH1' container with a trailing list."""
+    mv = memoryview(blob)
+    end = len(mv) - tail_len
+    return bytes(mv[:head_len]) + bytes(mv[end:]), mv[head_len:end]
+
+
+def split_for_ranks(eng, slots, world: int):
+    """Slot list of a field -> per-rank (meta dict, [payload views]) for decompress_sharded, or None when the
+    blob's parts do not line up with the time shards of `world` ranks (the caller then decodes everything and
+    slices).  Rank r's meta holds its containers without the large payloads; the payloads (latent low plane,
+    latent high-plane bits, code bits, mask bits) are what travels over NCCL."""
+    import json
+    from ._engine import HUFF_MAGIC, LATENT_MAGIC
+    T, H, W = (int(v) for v in slots[2][:3])
+    shards = [s for s in shard_time(T, world) if s[1] > s[0]]
+    parts = [unpack_multipart(memoryview(slots[i])) for i in BIG]
+    if not all(len(p) == len(shards) for p in parts):
+        return None
+    out = []
+    for r, (a, b) in enumerate(shards):
+        lat, codes, mask = (bytes(parts[0][r][:4]), parts[1][r], parts[2][r])
+        if lat != LATENT_MAGIC or bytes(codes[:4]) != HUFF_MAGIC or bytes(mask[:4]) != HUFF_MAGIC:
+            return None
+        lb = parts[0][r]
+        (lm,) = struct.unpack("<I", lb[4:8])
+        lmeta = json.loads(bytes(lb[8:8 + lm]))
+        if lmeta.get("codec") != "f16":
+            return None
+        n = int(lmeta["n"])
+        hic = lb[8 + lm + n:]
+        hl = eng.stream_head_len(hic)
+        lat_meta = bytes(lb[:8 + lm]) + bytes(hic[:hl])
+        cmeta = json.loads(bytes(codes[16:16 + struct.unpack("<I", codes[4:8])[0]]))
+        c_meta, c_pay = _cut(codes, eng.stream_head_len(codes), 4 * int(cmeta["n_esc"]))
+        m_meta, m_pay = _cut(mask, eng.stream_head_len(mask))
+        pays = [lb[8 + lm:8 + lm + n], hic[hl:], c_pay, m_pay]
+        meta = dict(rows=(a, b), shape=(T, H, W), mean=slots[4], std=slots[5], thr2=slots[8], latent=lat_meta,
+                    codes=c_meta, mask=m_meta, sizes=[len(p) for p in pays])
+        out.append((meta, pays))
+    return out
 
 
 def decompress_sharded(eng, slots_or_none, *, group=None, src=0):
-    """Rank `src` holds the slot list; every rank decodes the autoencoder for its own time shard only
-    and returns (rows_begin, rows_end, tensor (T_local, H, W)) of the reconstruction."""
+    """Rank `src` holds the slot list; every rank decodes its own time shard only and returns (rows_begin,
+    rows_end, tensor (T_local, H, W)) of the reconstruction.  When the blob was written by compress_sharded on
+    the same number of ranks, rank r receives exactly its own parts (metadata through a scatter of small pickles,
+    the payloads over NCCL into device memory) and decodes them without touching the other shards; otherwise the
+    slot list is broadcast and every rank decodes the streams and keeps its rows."""
     import torch
     import torch.distributed as dist
+    from . import _hostio
     from .decompress import decompress_device
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    obj = [slots_or_none]
-    dist.broadcast_object_list(obj, src=src, group=group)
-    slots = obj[0]
-    T, H, W = (int(v) for v in slots[2][:3])
+    dev = eng.dev
+    nccl = dist.get_backend(group) == "nccl"
+    plan = split_for_ranks(eng, slots_or_none, world) if rank == src else None
+    flag = [None]
+    if rank == src:
+        flag[0] = (tuple(int(v) for v in slots_or_none[2][:3]), plan is not None)
+    dist.broadcast_object_list(flag, src=src, group=group)
+    (T, H, W), aligned = flag[0]
     t0, t1 = shard_time(T, world)[rank]
-    if t1 <= t0:
-        return t0, t1, torch.empty((0, H, W), dtype=torch.float32, device=eng.dev)
-    out = decompress_device(eng, slots, rows=(t0, t1))
+    if not aligned:
+        obj = [slots_or_none]
+        dist.broadcast_object_list(obj, src=src, group=group)
+        if t1 <= t0:
+            return t0, t1, torch.empty((0, H, W), dtype=torch.float32, device=dev)
+        return t0, t1, decompress_device(eng, obj[0], rows=(t0, t1))
+    metas = [None] * world
+    if rank == src:
+        for r in range(len(plan)):
+            metas[r] = plan[r][0]
+    mine = [None]
+    dist.scatter_object_list(mine, metas if rank == src else None, src=src, group=group)
+    meta = mine[0]
+    ops, keep = [], []
+    pay = None
+    if rank == src:
+        # stage every rank's payloads in pinned memory (thread pool), one H2D, then one send per rank
+        sizes = [sum((n + 15) & ~15 for n in m["sizes"]) for m, _ in plan]
+        total = sum(sizes)
+        pin = eng._pinned("scatter", total)
+        pv = pin.numpy()
+        dsts, srcs, o = [], [], 0
+        for m, pays in plan:
+            for p in pays:
+                dsts.append(pv[o:o + len(p)])
+                srcs.append(np.frombuffer(p, dtype=np.uint8))
+                o += (len(p) + 15) & ~15
+        _copy_views(dsts, srcs, _hostio._threads())
+        dbuf = torch.empty(max(total, 16), dtype=torch.uint8, device=dev)
+        dbuf[:total].copy_(pin[:total], non_blocking=True)
+        sbuf = dbuf if nccl else pin            # gloo: send from host memory
+        o = 0
+        for r, n in enumerate(sizes):
+            if r == rank:
+                pay = dbuf[o:o + n]
+            elif n:
+                dstr = dist.get_global_rank(group, r) if group is not None else r
+                ops.append(dist.P2POp(dist.isend, sbuf[o:o + n], dstr, group))
+            o += n
+        keep.append(dbuf)
+    elif meta is not None:
+        n = sum((v + 15) & ~15 for v in meta["sizes"])
+        pay = torch.empty(max(n, 16), dtype=torch.uint8, device=dev if nccl else "cpu")
+        srcr = dist.get_global_rank(group, src) if group is not None else src
+        ops.append(dist.P2POp(dist.irecv, pay, srcr, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if pay is not None and not pay.is_cuda:
+        pay = pay.to(dev)
+    if meta is None:
+        return t0, t1, torch.empty((0, H, W), dtype=torch.float32, device=dev)
+    views, o = [], 0
+    for n in meta["sizes"]:
+        views.append(pay[o:o + n])
+        o += (n + 15) & ~15
+    a, b = meta["rows"]
+    assert (a, b) == (t0, t1)
+    latent, _ = eng.unpack_latent(meta["latent"], None, dev=(views[0], views[1]))
+    recon = eng.decode(latent, b - a, H, W)
+    q = eng.unpack_codes(meta["codes"], views[2])
+    mask = eng.unpack_mask(meta["mask"], views[3])
+    if mask.numel() != (b - a) * H * W:
+        raise ValueError("mask part does not cover this rank's rows")
+    out = eng.reconstruct(recon, mask, q, meta["mean"], meta["std"], meta["thr2"])
     return t0, t1, out
+
+
+# ------------------------------------------------------------------------------------------
+# numpy-facing entry points (what a user of the multi-GPU codec calls; host buffers in, host buffers out)
+# ------------------------------------------------------------------------------------------
+def compress_sharded_host(array_local, err_threshold, *, t0, T, precision=None, model=None, device=None,
+                          mode="strict", codec="huff", group=None, dst=0):
+    """compress() of one field whose rows [t0, t0 + len(array_local)) live in this rank's host memory
+    (numpy float32 (T_local, H, W, 2); pinned memory is copied directly, pageable memory is staged).  Returns the
+    blob (bytes, same layout as compress()) on rank `dst`, None elsewhere."""
+    import torch.distributed as dist
+    from . import _hostio
+    from . import _native as N
+    from ._engine import Engine
+    from .compress import dumps_slots
+    torch = N.require_cuda()
+    eng = Engine.get(model, precision, device)
+    if array_local.dtype != np.float32:
+        array_local = np.array(array_local, dtype=np.float32)
+    assert array_local.ndim == 4 and array_local.shape[3] == 2, "Input should have 2 channels."
+    if array_local.shape[0]:
+        x = _hostio.h2d(eng, array_local)
+    else:
+        x = torch.empty(array_local.shape, dtype=torch.float32, device=eng.dev)
+    slots, _ = compress_sharded(eng, x, err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=group, dst=dst)
+    if dist.get_rank(group) != dst:
+        return None
+    return dumps_slots(slots)
+
+
+def decompress_sharded_host(blob_or_none, *, precision=None, model=None, device=None, group=None, src=0):
+    """Inverse of compress_sharded_host: rank `src` passes the blob, every rank gets (rows_begin, rows_end, numpy
+    float32 (T_local, H, W, 1)) of its own time shard."""
+    import torch.distributed as dist
+    from . import _hostio
+    from . import _native as N
+    from ._engine import Engine
+    from .decompress import _peek_meta
+    N.require_cuda()
+    slots = pickle.loads(blob_or_none) if dist.get_rank(group) == src else None
+    meta = [None]
+    if slots is not None:
+        try:
+            meta[0] = _peek_meta(slots[0]).get("precision")
+        except Exception:
+            pass
+    dist.broadcast_object_list(meta, src=src, group=group)
+    eng = Engine.get(model, precision or meta[0], device)
+    a, b, rows = decompress_sharded(eng, slots, group=group, src=src)
+    H, W = int(rows.shape[1]), int(rows.shape[2])
+    if b <= a:
+        return a, b, np.empty((0, H, W, 1), dtype=np.float32)
+    return a, b, _hostio.d2h(eng, rows, (b - a, H, W, 1))

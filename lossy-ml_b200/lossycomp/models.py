@@ -215,6 +215,14 @@ def default_model_path() -> str:
     return os.environ.get("LOSSYCOMP_MODEL", os.path.join(_WEIGHT_DIR, "model_2.lcw"))
 
 
+def shipped_model_path(name: str):
+    """weights/<name>.lcw if this package ships weights of that name, else None."""
+    if not name or os.sep in name or name.startswith("."):
+        return None
+    p = os.path.join(_WEIGHT_DIR, f"{name}.lcw")
+    return p if os.path.exists(p) else None
+
+
 _cache: Dict[str, Model] = {}
 
 

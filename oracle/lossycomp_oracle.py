@@ -89,8 +89,8 @@ def _conv_layer(x, L):
     """x: torch (N,C,T,H,W) float32. L: lossycomp.models.Layer (Keras-layout weights)."""
     import torch
     import torch.nn.functional as F
-    w = torch.from_numpy(np.ascontiguousarray(L.kernel.transpose(4, 3, 0, 1, 2)))
-    b = torch.from_numpy(L.bias)
+    w = torch.from_numpy(np.ascontiguousarray(L.kernel.transpose(4, 3, 0, 1, 2))).to(x.device)
+    b = torch.from_numpy(L.bias).to(x.device)
     if L.kind == "conv":
         pads = []
         for n in reversed(x.shape[2:]):           # F.pad wants last axis first
@@ -106,13 +106,15 @@ def _conv_layer(x, L):
     return y + b.view(1, -1, 1, 1, 1)
 
 
-def run_layers(x_ndhwc, layers, batch=10, collect=None):
-    """Run a list of layers on channels-last numpy input (N,T,H,W,C) -> numpy channels-last."""
+def run_layers(x_ndhwc, layers, batch=10, collect=None, device="cpu"):
+    """Run a list of layers on channels-last numpy input (N,T,H,W,C) -> numpy channels-last.
+    device="cuda" runs the same layer statements through cuDNN (tests only: an independent cross-check of the
+    CUDA kernels, never a product path)."""
     import torch
     outs = []
     with torch.no_grad():
         for s in range(0, x_ndhwc.shape[0], batch):      # compress.py:84-86 (batch 10)
-            x = torch.from_numpy(np.array(x_ndhwc[s:s + batch], dtype=np.float32, order="C")).permute(0, 4, 1, 2, 3).contiguous()
+            x = torch.from_numpy(np.array(x_ndhwc[s:s + batch], dtype=np.float32, order="C")).permute(0, 4, 1, 2, 3).contiguous().to(device)
             skip = None
             for L in layers:
                 y = _conv_layer(x, L)
@@ -124,8 +126,8 @@ def run_layers(x_ndhwc, layers, batch=10, collect=None):
                     skip = y
                 x = y
                 if collect is not None:
-                    collect.setdefault(L.name, []).append(x.permute(0, 2, 3, 4, 1).numpy().copy())
-            outs.append(x.permute(0, 2, 3, 4, 1).contiguous().numpy())
+                    collect.setdefault(L.name, []).append(x.permute(0, 2, 3, 4, 1).cpu().numpy().copy())
+            outs.append(x.permute(0, 2, 3, 4, 1).contiguous().cpu().numpy())
     return np.concatenate(outs, axis=0)
 
 

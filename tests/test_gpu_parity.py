@@ -235,15 +235,17 @@ def test_time_sharded_compress_equals_single_call(eng, torch):
     ref_slots, ref_info = compress_device(eng, x, thr, mode="strict", codec="huff", return_parts=True)
     shards = D.shard_time(T, 2)
     assert shards == [(0, 16), (16, 33)]
-    raw = [eng.stats_raw(x[a:b].contiguous()) for a, b in shards]
+    raw = [blk for a, b in shards for blk in eng.stats_blocks(x[a:b].contiguous()).cpu().tolist()]
     mean, std, mx = D.combine_stats(raw)
+    # per-time-block partials added in time order: bit-identical to the single-GPU statistics, not merely close
     assert mean == ref_slots[4] and std == ref_slots[5]
+    assert raw == eng.stats_blocks(x).cpu().tolist()
     rank_slots = []
     for a, b in shards:
         s, _ = compress_device(eng, x[a:b].contiguous(), thr, mode="strict", codec="huff",
                                inject={"mean": mean, "std": std, "max_abs": mx})
         rank_slots.append(pickle.loads(pickle.dumps(s)))
-    slots = D.assemble_blob(rank_slots, eng.join_latents)
+    slots = D.assemble_blob(rank_slots)
     assert slots[1] == ref_slots[1] and slots[2] == ref_slots[2] and slots[3] == ref_slots[3]
     assert slots[8] == ref_slots[8]
     np.testing.assert_array_equal(eng.unpack_mask(slots[7]).cpu().numpy(), ref_info["mask"].cpu().numpy())
@@ -493,9 +495,20 @@ def test_latent_f16_codec_roundtrip_and_join(torch):
     for part in (lat[:half], lat[half:]):
         p = part.contiguous().clone()
         parts.append(e16.pack_latent_f16(*e16.quantize_latent(p)))
-    joined = e16.join_latents(parts)
+    from lossycomp.dist import pack_multipart
+    joined = pack_multipart(parts)
     back, _ = e16.unpack_latent(joined, slots[1])
     assert torch.equal(back, lat)
+    # device-resident containers (what the multi-GPU path sends over NCCL) hold the same bytes
+    dp = e16.pack_latent_f16(*e16.quantize_latent(lat.clone()), device_out=True)
+    assert dp.tobytes() == e16.pack_latent_f16(*e16.quantize_latent(lat.clone()))
+    ce, cm = e16.pack_streams(info["mask"], info["q"])
+    dce, dcm = e16.pack_streams(info["mask"], info["q"], device_out=True)
+    assert dce.tobytes() == ce and dcm.tobytes() == cm
+    # and decode from device payloads
+    hl = e16.stream_head_len(cm)
+    m2 = e16.unpack_mask(cm[:hl], dev(torch, np.frombuffer(cm[hl:], dtype=np.uint8).copy()))
+    assert torch.equal(m2, info["mask"])
 
 
 def test_compress_stream_equals_compress(torch):
@@ -514,3 +527,82 @@ def test_compress_stream_equals_compress(torch):
     assert list(compress_stream(fields, 0.05)) == want              # pageable
     assert list(compress_stream([], 0.05)) == []
     assert list(compress_stream(pinned[:1], 0.05)) == want[:1]
+
+
+@pytest.mark.parametrize("T,H,W,thr,seed", [(24, 336, 720, 0.1, 1234), (50, 241, 241, 0.6, 15)])
+def test_benchmark_scale_window_against_oracle(torch, T, H, W, thr, seed):
+    """The oracle on a 24x336x720 window of the benchmark field (5.8 M voxels, 2835 scan tiles, 210 chunks with a
+    re-anchored time tail; a few seconds of CPU) and on the notebook's shape and bound ((50,241,241,2) at 0.6,
+    notebooks/Compression_example.ipynb:128-135; tails on every axis, 3 % outliers; the oracle is pinned at this
+    shape by tests/golden/digests.json): with the oracle's statistics and reconstruction injected the CUDA path's
+    mask, codes, first differences, bz2 slots, reconstruction and violation set are bit-identical; the fp16
+    tensor-core autoencoder stays within its stated tolerance of the oracle's fp32 one; and the Huffman codec
+    decodes back to exactly the oracle's mask and codes."""
+    from lossycomp._engine import Engine
+    from lossycomp.compress import compress_device
+    from lossycomp.decompress import decompress_device
+    from lossycomp.models import load_model
+    from oracle import lossycomp_oracle as O
+    if seed == 1234:
+        x = O.synthetic_field(T, H, W, seed=seed)
+    else:
+        x = O.synthetic_field(T, H, W, seed=seed, h0=100 + 7 * seed, w0=200 + 31 * seed)
+    blob, p = O.compress(x, thr, load_model(), return_parts=True)
+    ref = pickle.loads(blob)
+    e32 = Engine.get(None, "fp32", 0)
+    xd = dev(torch, x)
+    recon = dev(torch, p["recon_std"][..., 0])
+    mask, q = e32.quantize(xd, recon, p["mean"], p["std"], thr)
+    np.testing.assert_array_equal(mask.cpu().numpy().reshape(p["mask"].shape), p["mask"])
+    np.testing.assert_array_equal(q.cpu().numpy(), p["q"])
+    np.testing.assert_array_equal(e32.diff(q).cpu().numpy(), p["dq"])
+    np.testing.assert_array_equal(e32.diff(mask).cpu().numpy(), p["dm"])
+    inj = {"mean": p["mean"], "std": p["std"], "recon_std": recon}
+    slots, _ = compress_device(e32, xd, thr, mode="parity", codec="bz2", inject=inj)
+    assert slots[6] == ref[6] and slots[7] == ref[7] and slots[3] == ref[3] and slots[8] == ref[8]
+    xhat = decompress_device(e32, slots, inject=inj)
+    want = O.decompress(blob, load_model(), inject={"recon_std": p["recon_std"]})[..., 0]
+    np.testing.assert_array_equal(xhat.cpu().numpy(), want)
+    v, _ = e32.verify(xd, xhat, thr)
+    assert v == int((np.abs(x[..., 0].astype(np.float64) - want.astype(np.float64)) > thr).sum())
+    # Huffman codec: containers decode to the oracle's streams
+    hs, _ = compress_device(e32, xd, thr, mode="parity", codec="huff", inject=inj)
+    np.testing.assert_array_equal(e32.unpack_mask(hs[7]).cpu().numpy().reshape(p["mask"].shape), p["mask"])
+    np.testing.assert_array_equal(e32.unpack_codes(hs[6]).cpu().numpy(), p["q"])
+    # statistics: fp64 GPU reduction vs NumPy's fp32 pairwise sums (SURVEY H6: last-bit differences allowed)
+    mean, std, _ = e32.stats(xd)
+    assert abs(float(mean) - float(p["mean"])) <= 4 * np.spacing(np.float32(p["mean"]))
+    assert abs(float(std) - float(p["std"])) <= 8 * np.spacing(np.float32(p["std"]))
+    # autoencoders: fp32 engine within 2e-4, fp16 tensor-core engine within 1e-2 * max(1, |latent|max) (latent) and
+    # 2e-2 (reconstruction, standardised units) of the oracle
+    lat_ref = p["latent"].reshape(p["latent"].shape[0], -1)
+    lat32 = e32.encode(xd, p["mean"], p["std"]).cpu().numpy()
+    assert np.abs(lat32 - lat_ref).max() <= AE_FP32_TOL * max(1.0, np.abs(lat_ref).max())
+    e16 = Engine.get(None, "fp16", 0)
+    lat16 = e16.encode(xd, p["mean"], p["std"]).cpu().numpy()
+    assert np.abs(lat16 - lat_ref).max() <= 1e-2 * max(1.0, np.abs(lat_ref).max())
+    rec16 = e16.decode(dev(torch, lat_ref), T, H, W).cpu().numpy()
+    assert np.abs(rec16 - p["recon_std"][..., 0]).max() <= 2e-2
+
+
+def test_fp32_engine_against_cudnn(eng, torch, model2):
+    """Independent cross-check of the convolution kernels (SURVEY.md 7.3 allows cuDNN in tests only): the oracle's
+    layer statements executed by torch on the GPU (cuDNN) against the fp32 CUDA-core engine, encoder and decoder,
+    on chunks with tails on every axis."""
+    from oracle import lossycomp_oracle as O
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden_case("odd_all_axes")
+    x = g["x"]
+    xs = x.copy()
+    xs[..., 0] = (x[..., 0] - g["mean"]) / g["std"]
+    chunks = O.chunk_data(xs)
+    lat_cudnn = O.run_layers(chunks, model2.encoder, device="cuda")
+    lat = eng.encode(dev(torch, x), g["mean"], g["std"]).cpu().numpy()
+    scale = max(1.0, float(np.abs(lat_cudnn).max()))
+    assert np.abs(lat - lat_cudnn.reshape(lat.shape)).max() <= AE_FP32_TOL * scale
+    rec_cudnn = O.merge_data(O.run_layers(lat_cudnn, model2.decoder, device="cuda"), x.shape)[..., 0]
+    rec = eng.decode(dev(torch, lat_cudnn.reshape(lat.shape)), *x.shape[:3]).cpu().numpy()
+    assert np.abs(rec - rec_cudnn).max() <= AE_FP32_TOL * max(1.0, float(np.abs(rec_cudnn).max()))
+    # and cuDNN agrees with the CPU oracle the goldens were made with
+    assert np.abs(lat_cudnn - g["latent"]).max() <= AE_FP32_TOL * scale

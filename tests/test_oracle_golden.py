@@ -107,3 +107,33 @@ def test_run_token_restatement_roundtrip_and_known_answers():
         assert t.size <= n
         c = np.where(x == 0, 1, np.where(x == 1, 2, np.minimum(x, 200))).astype(np.uint8)
         assert np.array_equal(O.rle_expand(O.rle_tokens(c, 1, 250), n, 1, 250), c)
+
+
+def test_notebook_shape_digest(model2):
+    """(50,241,241,2) at abs_err 0.6 -- the shape and bound of notebooks/Compression_example.ipynb:128-135 -- through
+    the reference's own compress.py/decompress.py under stubs (tools/make_goldens.py); the arrays are too large to
+    commit, so the golden keeps their SHA-256 and the scalars, and the input is regenerated from its seed."""
+    import json
+    with open(os.path.join(GOLDEN, "digests.json")) as fh:
+        d = json.load(fh)["notebook_50x241x241"]
+    T, H, W = d["shape"]
+    seed = d["seed"]
+    x = O.synthetic_field(T, H, W, seed=seed, h0=100 + 7 * seed, w0=200 + 31 * seed)
+    sha = lambda a: hashlib.sha256(a.tobytes() if hasattr(a, "tobytes") else a).hexdigest()
+    if sha(x) != d["x_sha"]:
+        pytest.skip("NumPy's normal() stream differs from the one the golden was made with")
+    blob, p = O.compress(x, d["abs_err"], model2, return_parts=True)
+    slots = pickle.loads(blob)
+    assert np.float32(p["mean"]).tobytes().hex() == d["mean_hex"] and np.float32(p["std"]).tobytes().hex() == d["std_hex"]
+    assert slots[1][0] == d["n_chunks"] == 144 and slots[8] == d["thr2"]
+    if sha(p["latent"].astype("<f4")) == d["latent_sha"]:          # same convolution kernels as the generating machine
+        assert sha(p["recon_std"].astype(np.float32)) == d["recon_std_sha"]
+        assert sha(p["dq"].astype("<i4")) == d["dq_sha"] and sha(p["dm"].astype("i1")) == d["dm_sha"]
+        assert sha(slots[6]) == d["comp_error_sha"] and sha(slots[7]) == d["comp_mask_sha"]
+        assert slots[3][0] == d["n_out"] and len(blob) == d["blob_len"]
+        xhat = O.decompress(blob, model2)
+        assert sha(xhat.astype("<f4")) == d["xhat_sha"]
+        viol = int((np.abs(x[..., 0].astype(np.float64) - xhat[..., 0]) > d["abs_err"]).sum())
+        assert viol == d["violations"] == 15
+    else:   # another CPU: the convolutions round differently, the integer stages still have to be consistent
+        assert abs(slots[3][0] - d["n_out"]) < 0.02 * d["n_out"]

@@ -135,8 +135,19 @@ CASES = [  # name, shape, abs_err, seed
 ]
 
 
+# digest-only goldens (arrays too large to commit: only hashes and scalars are kept, the input is regenerated from
+# its seed): the notebook's shape and error bound (notebooks/Compression_example.ipynb:128-135: (50,241,241,2), 0.6)
+DIGEST_CASES = [
+    ("notebook_50x241x241", (50, 241, 241), 0.6, 15),
+]
+
+
 def sha(b):
     return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def digest_input(T, H, W, seed):
+    return oracle.synthetic_field(T, H, W, seed=seed, h0=100 + 7 * seed, w0=200 + 31 * seed)
 
 
 def main():
@@ -169,6 +180,31 @@ def main():
         print(f"{name}: shape {x.shape} thr {thr} chunks {latent.shape[0]} outliers {dq.size} "
               f"({dq.size / (T * H * W):.3f}) blob {len(blob)} B  CF {x[..., 0].nbytes / len(blob):.2f} "
               f"violations {viol} max|e| {np.abs(x[..., 0] - xhat[..., 0]).max():.7f}")
+
+    import json
+    digests = {}
+    for name, (T, H, W), thr, seed in DIGEST_CASES:
+        x = digest_input(T, H, W, seed)
+        _bz2_log.clear()
+        CAPTURE.clear()
+        blob = ref_c.compress(x, thr)
+        slots = pickle.loads(blob)
+        dq, dm = _bz2_log[0], _bz2_log[1]
+        recon_std = ref_dl.merge_data(CAPTURE["decoded"], x.shape).astype(np.float32)
+        xhat = ref_d.decompress(blob)
+        viol = int((np.abs(x[..., 0].astype(np.float64) - xhat[..., 0].astype(np.float64)) > thr).sum())
+        digests[name] = dict(
+            shape=[T, H, W], abs_err=thr, seed=seed, x_sha=sha(x.tobytes()), mean=float(slots[4]), std=float(slots[5]),
+            mean_hex=np.float32(slots[4]).tobytes().hex(), std_hex=np.float32(slots[5]).tobytes().hex(),
+            latent_sha=sha(CAPTURE["latent"].astype("<f4").tobytes()), recon_std_sha=sha(recon_std.tobytes()),
+            dq_sha=sha(dq.astype("<i4").tobytes()), dm_sha=sha(dm.astype("i1").tobytes()),
+            comp_error_sha=sha(slots[6]), comp_mask_sha=sha(slots[7]), xhat_sha=sha(xhat.astype("<f4").tobytes()),
+            n_chunks=int(slots[1][0]), n_out=int(slots[3][0]), thr2=float(slots[8]), violations=viol,
+            blob_len=len(blob), cf=x[..., 0].nbytes / len(blob),
+            max_abs_err=float(np.abs(x[..., 0].astype(np.float64) - xhat[..., 0]).max()))
+        print(name, digests[name])
+    with open(os.path.join(OUT, "digests.json"), "w") as fh:
+        json.dump(digests, fh, indent=1, sort_keys=True)
 
     # chunk/merge known answers (notebooks/Chunking_data.ipynb cells 4, 8, 15, 19)
     facts = {}
