@@ -66,6 +66,9 @@ int lc_version(void);
  * n_dec decoder layers, in execution order. */
 int lc_create(const lc_layer_t* layers, int n_enc, int n_dec, int in_channels, int precision,
               int device, lc_handle_t* out);
+/* Device rule for every other entry point: kernels are launched on the calling thread's CURRENT device, which must
+ * be the device the handle, the pointers and the stream belong to (lc_create itself restores the caller's current
+ * device before it returns). */
 int lc_destroy(lc_handle_t h);
 int lc_latent_floats(lc_handle_t h);
 /* Which kernel runs layer i: 0 = CUDA-core direct conv, 1 = tcgen05 k3, 2 = k4 first layer, 3 = k4 last
@@ -110,6 +113,15 @@ int lc_stats_blocks(const float* d_x, int64_t n_vox, int64_t block_vox, int C, d
  * re-anchored at axis_len-size) and run the encoder.  d_latent receives
  * (chunk_count, latent_floats) float32 in Keras order (t,h,w,f). */
 size_t lc_ae_workspace_bytes(lc_handle_t h, int max_chunks);
+/* Workspace contract (16-bit precisions): the tensor-core kernels read the halo / guard slots of their activation
+ * planes as zeros and never write them, so a workspace has to be zeroed ONCE before its first use and must then
+ * belong to the codec alone (not shared with other work, not used as scratch between calls; lc_encode and lc_decode
+ * calls on one workspace must be stream-ordered).  lc_ae_workspace_init enqueues the zeroing on `stream` and
+ * registers the buffer with the handle; lc_encode / lc_decode return LC_EINVAL for a buffer that was not registered
+ * (up to 16 buffers per handle; lc_ae_workspace_release forgets one before it is freed).  The fp32 precision has
+ * no such requirement. */
+int lc_ae_workspace_init(lc_handle_t h, void* d_ws, size_t ws_bytes, void* stream);
+int lc_ae_workspace_release(lc_handle_t h, void* d_ws);
 int lc_encode(lc_handle_t h, const float* d_x, int T, int H, int W, int C, float mean, float std,
               int chunk_begin, int chunk_count, float* d_latent, void* d_ws, size_t ws_bytes,
               void* stream);
@@ -156,8 +168,11 @@ int lc_cumsum_i8(const int8_t* d_in, int64_t n, int8_t* d_out, void* d_ws, void*
 
 /* decompress.py:86-104 -- scatter de-quantised residuals by mask and add:
  *   val = m>0 ? fl32(double(q_j)*thr2) : 0, negated where m==2 (j = rank of the outlier);
- *   out = fl32(fl32(fl32(r*std)+mean) + val).   thr2 is the double stored in blob slot 8. */
-int lc_reconstruct(const float* d_recon, const int8_t* d_mask, const int32_t* d_q, int64_t n_vox,
+ *   out = fl32(fl32(fl32(r*std)+mean) + val).   thr2 is the double stored in blob slot 8.
+ * d_q holds n_q codes; a mask with more outliers than that (a damaged blob) reads zeros instead of memory past
+ * the list, and the first 8 bytes of d_ws receive the outlier count of the mask (uint64) so that the caller can
+ * compare it with n_q after its next synchronisation. */
+int lc_reconstruct(const float* d_recon, const int8_t* d_mask, const int32_t* d_q, int64_t n_q, int64_t n_vox,
                    float mean, float std, double thr2, float* d_out, void* d_ws, void* stream);
 
 /* exhaustive |x - xhat| <= abs_err check in fp64.  d_x has C interleaved channels (channel 0
@@ -219,8 +234,9 @@ int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d_code, cons
 int lc_huff_build_decode(const uint32_t* code, const uint8_t* len, const uint8_t* used, int lut_bits, uint16_t* lut,
                          int32_t* tree, int* n_tree);
 /* Decode: d_lut is a 2^lut_bits table of (len << 8 | sym) for codes no longer than lut_bits;
- * longer codes walk d_tree (node = {child0, child1}, leaves are ~sym). */
-int lc_huff_decode(const uint8_t* d_bits, int64_t n, int seg, const unsigned long long* d_seg_bits,
+ * longer codes walk d_tree (node = {child0, child1}, leaves are ~sym).  d_bits is n_bytes long (a multiple of 4,
+ * zero padded by at least 16 bytes past the last code bit); reads are clamped to it. */
+int lc_huff_decode(const uint8_t* d_bits, int64_t n_bytes, int64_t n, int seg, const unsigned long long* d_seg_bits,
                    const uint16_t* d_lut, int lut_bits, const int32_t* d_tree, uint8_t* d_sym,
                    void* stream);
 

@@ -45,11 +45,18 @@ extern "C" int lc_create(const lc_layer_t* layers, int n_enc, int n_dec, int in_
   LC_REQUIRE(n_enc > 0 && n_dec > 0 && n_enc + n_dec <= kMaxLayers, "bad layer count");
   LC_REQUIRE(precision == LC_PREC_FP32 || precision == LC_PREC_BF16 || precision == LC_PREC_FP16,
              "unknown precision");
+  // the codec lives on `device`; the calling thread's current device is restored before returning
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  LC_CUDA(cudaGetDevice(&guard.prev));
   LC_CUDA(cudaSetDevice(device));
   lc_codec* h = new lc_codec();
   memset(h, 0, sizeof(*h));
   h->spans = new std::vector<ProfSpan>();
   h->pool = new std::vector<cudaEvent_t>();
+  h->ws_ready = new std::vector<std::pair<void*, size_t>>();
   h->device = device;
   h->precision = precision;
   h->in_channels = in_channels;
@@ -115,6 +122,8 @@ extern "C" int lc_create(const lc_layer_t* layers, int n_enc, int n_dec, int in_
 
 extern "C" int lc_destroy(lc_handle_t h) {
   if (!h) return LC_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(h->device);
   for (int i = 0; i < h->n_enc + h->n_dec; ++i) {
     cudaFree(h->layers[i].d_w);
@@ -126,7 +135,9 @@ extern "C" int lc_destroy(lc_handle_t h) {
   for (auto& e : *h->pool) cudaEventDestroy(e);
   delete h->spans;
   delete h->pool;
+  delete h->ws_ready;
   delete h;
+  if (prev >= 0) cudaSetDevice(prev);
   return LC_OK;
 }
 
@@ -232,6 +243,35 @@ extern "C" size_t lc_ae_workspace_bytes(lc_handle_t h, int max_chunks) {
   return 3 * act_floats_per_chunk(h) * sizeof(float) * (size_t)max_chunks + 1024;
 }
 
+// The tensor-core kernels read the halo and guard slots of the 16-bit activation planes as zeros and never write
+// them (act.cuh), so a workspace must be zeroed once before its first use and must not be used for anything else
+// afterwards.  lc_ae_workspace_init does the zeroing and registers the buffer with the handle; lc_encode / lc_decode
+// refuse a buffer that was not registered (fresh cudaMalloc memory would silently give different convolutions on the
+// compressor and the decompressor, i.e. a broken error bound).
+extern "C" int lc_ae_workspace_init(lc_handle_t h, void* d_ws, size_t ws_bytes, void* stream) {
+  LC_REQUIRE(h && d_ws && ws_bytes > 0, "bad argument");
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes, as_stream(stream)));
+  for (auto& e : *h->ws_ready)
+    if (e.first == d_ws) { e.second = ws_bytes; return LC_OK; }
+  if (h->ws_ready->size() >= 16) h->ws_ready->erase(h->ws_ready->begin());
+  h->ws_ready->push_back({d_ws, ws_bytes});
+  return LC_OK;
+}
+
+extern "C" int lc_ae_workspace_release(lc_handle_t h, void* d_ws) {
+  LC_REQUIRE(h, "null handle");
+  for (size_t i = 0; i < h->ws_ready->size(); ++i)
+    if ((*h->ws_ready)[i].first == d_ws) { h->ws_ready->erase(h->ws_ready->begin() + i); break; }
+  return LC_OK;
+}
+
+static bool ws_is_ready(const lc_codec* h, const void* d_ws, size_t need) {
+  if (h->precision == LC_PREC_FP32) return true;      // the fp32 back end writes every value it reads
+  for (auto& e : *h->ws_ready)
+    if (e.first == d_ws && e.second >= need) return true;
+  return false;
+}
+
 // Runs layers [first, first+count) with the fp32 direct back end.  bufs: 3 activation buffers.
 static int run_layers_fp32(lc_codec* h, int first, int count, float* cur, float* bufs[3],
                            int n_chunks, float* final_out, float** last, cudaStream_t s) {
@@ -288,6 +328,8 @@ extern "C" int lc_encode(lc_handle_t h, const float* d_x, int T, int H, int W, i
   LC_REQUIRE(chunk_begin >= 0 && chunk_count > 0 && chunk_begin + chunk_count <= g.gt * g.gh * g.gw,
              "chunk range out of bounds");
   LC_REQUIRE(ws_bytes >= lc_ae_workspace_bytes(h, chunk_count), "workspace too small");
+  LC_REQUIRE(ws_is_ready(h, d_ws, lc_ae_workspace_bytes(h, chunk_count)),
+             "workspace was not prepared with lc_ae_workspace_init (the 16-bit kernels need zeroed halos)");
   cudaStream_t s = as_stream(stream);
   if (h->precision != LC_PREC_FP32)
     return tc_encode(h, d_x, g, C, mean, stdv, chunk_begin, chunk_count, d_latent, d_ws, s);
@@ -311,6 +353,8 @@ extern "C" int lc_decode(lc_handle_t h, const float* d_latent, int T, int H, int
   LC_REQUIRE(chunk_begin >= 0 && chunk_count > 0 && chunk_begin + chunk_count <= g.gt * g.gh * g.gw,
              "chunk range out of bounds");
   LC_REQUIRE(ws_bytes >= lc_ae_workspace_bytes(h, chunk_count), "workspace too small");
+  LC_REQUIRE(ws_is_ready(h, d_ws, lc_ae_workspace_bytes(h, chunk_count)),
+             "workspace was not prepared with lc_ae_workspace_init (the 16-bit kernels need zeroed halos)");
   cudaStream_t s = as_stream(stream);
   if (h->precision != LC_PREC_FP32)
     return tc_decode(h, d_latent, g, chunk_begin, chunk_count, d_recon, d_ws, s);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <utility>
 #include <vector>
 
 #include "../../include/lossycomp_b200.h"
@@ -64,6 +65,7 @@ struct lc_codec {
   DevLayer layers[kMaxLayers];
   int num_sms;
   void* tc_plan;             // TcPlan* (conv_tc.cu), null in LC_PREC_FP32 mode
+  std::vector<std::pair<void*, size_t>>* ws_ready;   // workspaces zeroed by lc_ae_workspace_init
 };
 
 // chunk index -> origin in the field (dataLoader.py:457-481): lon fastest, tail re-anchored.

@@ -934,10 +934,13 @@ int ctas_per_sm(int mode) {
 
 template <int MODE, int H16, int RELU>
 int launch_variant(const SweepParams& p, int grid, int smem, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the attribute belongs to the (function, device) pair: one flag per device, not per process
+  static bool attr_done[64] = {};
+  int dev = 0;
+  LC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     LC_CUDA(cudaFuncSetAttribute(sweep_tc_kernel<MODE, H16, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   sweep_tc_kernel<MODE, H16, RELU><<<grid, kTcThreads, smem, s>>>(p);
   return LC_OK;

@@ -358,7 +358,7 @@ huff_encode_kernel(const uint8_t* __restrict__ sym, long long n, const uint32_t*
 // big-endian within bytes), 12-bit direct table in shared memory, tree walk for longer codes,
 // symbols stored four at a time.
 __global__ void __launch_bounds__(128)
-huff_decode_kernel(const uint32_t* __restrict__ words, long long n, int seg,
+huff_decode_kernel(const uint32_t* __restrict__ words, long long n_words, long long n, int seg,
                    const unsigned long long* __restrict__ seg_bits, const uint16_t* __restrict__ lut,
                    int lut_bits, const int32_t* __restrict__ tree, uint8_t* __restrict__ sym) {
   extern __shared__ uint16_t s_lut[];
@@ -367,7 +367,12 @@ huff_decode_kernel(const uint32_t* __restrict__ words, long long n, int seg,
   const long long nseg = (n + seg - 1) / seg;
   const long long sg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sg >= nseg) return;
-  const unsigned long long pos = seg_bits[sg];
+  // Reads never leave the buffer whatever a corrupted container holds: the start offset is clamped and the word
+  // pointer saturates at the last word (a damaged stream then decodes to garbage symbols, which the caller's
+  // length / count checks reject, instead of faulting).
+  const uint32_t* const wend = words + (n_words - 1);
+  unsigned long long pos = seg_bits[sg];
+  if ((long long)(pos >> 5) > n_words - 3) pos = 0;
   const uint32_t* wp = words + (pos >> 5);
   unsigned long long buf = ((unsigned long long)__byte_perm(wp[0], 0, 0x0123) << 32) | __byte_perm(wp[1], 0, 0x0123);
   wp += 2;
@@ -387,7 +392,7 @@ huff_decode_kernel(const uint32_t* __restrict__ words, long long n, int seg,
         s = ~tree[0];
       } else {
         int node = 0;
-        while (true) {
+        while (l < 32) {                                   // codes are at most 32 bits (lc_huff_build_decode checks)
           const int bit = (int)((win >> (63 - l)) & 1);
           ++l;
           const int nx = tree[2 * node + bit];
@@ -400,7 +405,8 @@ huff_decode_kernel(const uint32_t* __restrict__ words, long long n, int seg,
     if (used >= 32) {
       buf = (buf << 32) | __byte_perm(ahead, 0, 0x0123);
       used -= 32;
-      ahead = *++wp;
+      wp = (wp < wend) ? wp + 1 : wp;
+      ahead = *wp;
     }
     const int k = (int)(i - i0) & 3;
     pack |= (uint32_t)s << (8 * k);
@@ -561,20 +567,21 @@ extern "C" int lc_huff_encode(const uint8_t* d_sym, int64_t n, const uint32_t* d
   return LC_OK;
 }
 
-extern "C" int lc_huff_decode(const uint8_t* d_bits, int64_t n, int seg, const unsigned long long* d_seg_bits,
-                              const uint16_t* d_lut, int lut_bits, const int32_t* d_tree, uint8_t* d_sym,
-                              void* stream) {
+extern "C" int lc_huff_decode(const uint8_t* d_bits, int64_t n_bytes, int64_t n, int seg,
+                              const unsigned long long* d_seg_bits, const uint16_t* d_lut, int lut_bits,
+                              const int32_t* d_tree, uint8_t* d_sym, void* stream) {
   if (n <= 0) return LC_OK;
   LC_REQUIRE(d_bits && d_seg_bits && d_lut && d_tree && d_sym, "null argument");
   LC_REQUIRE(lut_bits >= 1 && lut_bits <= 14 && seg > 0, "bad decode table");
+  LC_REQUIRE(n_bytes >= 16 && n_bytes % 4 == 0, "the bit buffer must be a multiple of 4 bytes with 16 spare bytes");
   const long long nseg = (n + seg - 1) / seg;
   // the caller guarantees the bit buffer is readable up to the last byte holding a code bit and
   // zero padded to 8 more bytes; pass the conservative size bound
   LC_REQUIRE((reinterpret_cast<uintptr_t>(d_bits) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_sym) & 3) == 0 &&
                  seg % 4 == 0, "bit stream and symbol buffers must be 4-byte aligned");
   huff_decode_kernel<<<(unsigned)((nseg + 127) / 128), 128, (size_t)(1 << lut_bits) * 2,
-                       as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(d_bits), n, seg, d_seg_bits, d_lut,
-                                            lut_bits, d_tree, d_sym);
+                       as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(d_bits), n_bytes / 4, n, seg, d_seg_bits,
+                                            d_lut, lut_bits, d_tree, d_sym);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

@@ -113,6 +113,7 @@ extern "C" int lc_huff_build_decode(const uint32_t* code, const uint8_t* len, co
     const int L = len[s];
     LC_REQUIRE(L >= 1 && L <= 32, "code length out of range");
     const uint32_t c = code[s];
+    LC_REQUIRE(L == 32 || (c >> L) == 0, "code has bits above its length");
     if (L <= lut_bits) {
       const uint32_t base = c << (lut_bits - L);
       for (uint32_t k = 0; k < (1u << (lut_bits - L)); ++k) lut[base + k] = (uint16_t)((L << 8) | s);
@@ -121,10 +122,12 @@ extern "C" int lc_huff_build_decode(const uint32_t* code, const uint8_t* len, co
     for (int i = 0; i < L; ++i) {
       const int bit = (int)((c >> (L - 1 - i)) & 1u);
       if (i == L - 1) {
+        LC_REQUIRE(tree[2 * node + bit] == 0, "not a prefix code (a code repeats or extends another)");
         tree[2 * node + bit] = ~s;
       } else {
-        if (tree[2 * node + bit] <= 0) {
-          LC_REQUIRE(nodes < 2 * kMaxSyms, "not a prefix code");
+        LC_REQUIRE(tree[2 * node + bit] >= 0, "not a prefix code (a code extends another)");
+        if (tree[2 * node + bit] == 0) {
+          LC_REQUIRE(nodes < kMaxSyms - 1, "not a prefix code (more inner nodes than a 256-leaf tree has)");
           tree[2 * nodes] = 0;
           tree[2 * nodes + 1] = 0;
           tree[2 * node + bit] = nodes++;
@@ -133,6 +136,9 @@ extern "C" int lc_huff_build_decode(const uint32_t* code, const uint8_t* len, co
       }
     }
   }
+  // a Huffman code is complete: every inner node has two children.  The decoder relies on it (every bit
+  // pattern reaches a leaf within 32 steps, whatever a corrupted bit stream contains).
+  for (int i = 0; i < 2 * nodes; ++i) LC_REQUIRE(tree[i] != 0, "incomplete prefix code");
   *n_tree = 2 * nodes;
   return LC_OK;
 }

@@ -139,7 +139,7 @@ quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ re
 
 __global__ void __launch_bounds__(kThreads)
 reconstruct_kernel(const float* __restrict__ recon, const int8_t* __restrict__ mask,
-                   const int32_t* __restrict__ q, long long n, float mean, float stdv, double thr2,
+                   const int32_t* __restrict__ q, long long n_q, long long n, float mean, float stdv, double thr2,
                    float* __restrict__ out, unsigned long long* ws, bool vec_r, bool vec_m,
                    bool vec_o) {
   const int tile = take_ticket(ws);
@@ -165,9 +165,15 @@ reconstruct_kernel(const float* __restrict__ recon, const int8_t* __restrict__ m
   float y[kItems];
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    const int qk = (m[k] > 0) ? q[o++] : 0;
+    int qk = 0;
+    if (m[k] > 0) {               // never read past the code list, whatever the mask of a damaged blob claims
+      if (o < n_q) qk = q[o];
+      ++o;
+    }
     y[k] = decoded_value(rv[k], mean, stdv, m[k], qk, thr2);
   }
+  // the number of outliers the mask holds, for the caller's consistency check against the code count
+  if ((long long)(tile + 1) * kTile >= n && threadIdx.x == 0) ws[0] = base + (unsigned long long)total;
   if (i0 + kItems <= n && vec_o) {
     float4* po = reinterpret_cast<float4*>(out + i0);
     po[0] = make_float4(y[0], y[1], y[2], y[3]);
@@ -284,15 +290,15 @@ extern "C" int lc_quantize_checked(const float* d_x, int C, const float* d_recon
   return LC_OK;
 }
 
-extern "C" int lc_reconstruct(const float* d_recon, const int8_t* d_mask, const int32_t* d_q,
+extern "C" int lc_reconstruct(const float* d_recon, const int8_t* d_mask, const int32_t* d_q, int64_t n_q,
                               int64_t n_vox, float mean, float stdv, double thr2, float* d_out,
                               void* d_ws, void* stream) {
   LC_REQUIRE(d_recon && d_mask && d_out && d_ws, "null argument");
-  LC_REQUIRE(n_vox > 0, "empty input");
+  LC_REQUIRE(n_vox > 0 && n_q >= 0 && (n_q == 0 || d_q), "empty input");
   cudaStream_t s = as_stream(stream);
   const long long nt = tiles_for(n_vox);
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
-  reconstruct_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_recon, d_mask, d_q, n_vox, mean, stdv, thr2,
+  reconstruct_kernel<<<(unsigned)nt, kThreads, 0, s>>>(d_recon, d_mask, d_q, n_q, n_vox, mean, stdv, thr2,
                                                        d_out, reinterpret_cast<unsigned long long*>(d_ws),
                                                        aligned16(d_recon), aligned8(d_mask),
                                                        aligned16(d_out));

@@ -45,8 +45,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded: a pipeline bug (a barrier nobody arrives on) must not hang the GPU until the watchdog kills the
+// process.  try_wait suspends the thread for a hardware-defined time slice, so the loop turns over slowly; after
+// ~2^26 unsuccessful slices (tens of seconds, orders of magnitude beyond any legitimate wait of these kernels) the
+// thread traps, the launch fails with an error the host reports ("... barrier timed out"), and the box survives.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins == (1u << 26)) asm volatile("trap;");
   }
 }
 

@@ -158,6 +158,10 @@ class Engine:
 
     # -- buffers ---------------------------------------------------------------
     def _stream(self):
+        # kernels launch on the calling thread's current device: make it this engine's (several engines on
+        # different GPUs may live in one process)
+        if self.torch.cuda.current_device() != self.device:
+            self.torch.cuda.set_device(self.device)
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
 
     def side_stream(self):
@@ -170,8 +174,12 @@ class Engine:
     def _ae_ws(self, n_chunks):
         if self._ws is None or self._ws_chunks < n_chunks:
             nbytes = self.lib.lc_ae_workspace_bytes(self.h, n_chunks)
+            if self._ws is not None:
+                self.lib.lc_ae_workspace_release(self.h, _ptr(self._ws))
             self._ws = None
-            self._ws = self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.dev)
+            self._ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.dev)
+            # zeroes the halo / guard slots the 16-bit kernels rely on and registers the buffer with the handle
+            N.check(self.lib.lc_ae_workspace_init(self.h, _ptr(self._ws), nbytes, self._stream()), "lc_ae_workspace_init")
             self._ws_chunks = n_chunks
         return self._ws
 
@@ -281,11 +289,23 @@ class Engine:
         """decompress.py:86-104 -> (T,H,W) float32."""
         n = recon.numel()
         out = self.torch.empty_like(recon)
-        ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n))
-        N.check(self.lib.lc_reconstruct(_ptr(recon), _ptr(mask), _ptr(q), n, float(mean), float(std),
+        ws = self._buf("scan_rec", self.lib.lc_scan_workspace_bytes(n))
+        N.check(self.lib.lc_reconstruct(_ptr(recon), _ptr(mask), _ptr(q), q.numel(), n, float(mean), float(std),
                                         float(thr2), _ptr(out), _ptr(ws), self._stream()), "lc_reconstruct")
         self.launches += 1
+        self._rec_check = (ws, int(q.numel()))
         return out
+
+    def check_reconstruct(self):
+        """After the stream has been synchronised: the mask of the last reconstruct() must hold exactly as many
+        outliers as there were codes (a damaged blob otherwise decodes silently wrong)."""
+        chk = getattr(self, "_rec_check", None)
+        if chk is None:
+            return
+        self._rec_check = None
+        got = int(chk[0][:8].view(self.torch.int64).item())
+        if got != chk[1]:
+            raise N.NativeError(f"corrupt blob: the mask marks {got} outliers, the code stream holds {chk[1]}")
 
     def verify(self, x, xhat, abs_err):
         """Exhaustive fp64 bound check -> (violations, max |x - xhat|).  Sync."""
@@ -411,7 +431,7 @@ class Engine:
             bits_ptr = dpay.data_ptr()
         else:
             bits_ptr = base
-        N.check(self.lib.lc_huff_decode(C.c_void_p(bits_ptr), n, seg, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
+        N.check(self.lib.lc_huff_decode(C.c_void_p(bits_ptr), pay_cap, n, seg, C.c_void_p(base + o_seg), C.c_void_p(base + o_lut),
                                         HF.LUT_BITS, C.c_void_p(base + o_tree), _ptr(sym), self._stream()), "lc_huff_decode")
         self.launches += 1
         return sym

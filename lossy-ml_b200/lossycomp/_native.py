@@ -48,6 +48,8 @@ SIGNATURES = {
     "lc_stats": (_i, [_p, _i64, _i, _p, _p, _p]),
     "lc_stats_blocks": (_i, [_p, _i64, _i64, _i, _p, _p, _p]),
     "lc_ae_workspace_bytes": (_sz, [_p, _i]),
+    "lc_ae_workspace_init": (_i, [_p, _p, _sz, _p]),
+    "lc_ae_workspace_release": (_i, [_p, _p]),
     "lc_encode": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _i, _p, _p, _sz, _p]),
     "lc_decode": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "lc_scan_workspace_bytes": (_sz, [_i64]),
@@ -59,7 +61,7 @@ SIGNATURES = {
     "lc_diff_i8": (_i, [_p, _i64, _p, _p]),
     "lc_cumsum_i32": (_i, [_p, _i64, _p, _p, _p]),
     "lc_cumsum_i8": (_i, [_p, _i64, _p, _p, _p]),
-    "lc_reconstruct": (_i, [_p, _p, _p, _i64, _f, _f, _d, _p, _p, _p]),
+    "lc_reconstruct": (_i, [_p, _p, _p, _i64, _i64, _f, _f, _d, _p, _p, _p]),
     "lc_verify_bound": (_i, [_p, _i, _p, _i64, _d, _p, _p, _p]),
     "lc_hist_u8": (_i, [_p, _i64, _p, _p]),
     "lc_hist_codes": (_i, [_p, _i64, _i, _i, _i, _p, _p]),
@@ -75,7 +77,7 @@ SIGNATURES = {
     "lc_huff_max_bytes": (_sz, [_i64]),
     "lc_huff_workspace_bytes": (_sz, [_i64, _i]),
     "lc_huff_encode": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p]),
-    "lc_huff_decode": (_i, [_p, _i64, _i, _p, _p, _i, _p, _p, _p]),
+    "lc_huff_decode": (_i, [_p, _i64, _i64, _i, _p, _p, _i, _p, _p, _p]),
     "lc_synth_field": (_i, [_p, _i, _i, _i, _i, _i, C.c_uint64, _p]),
     "lc_chunk_gather": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "lc_chunk_merge": (_i, [_p, _i, _i, _i, _i, _p, _p]),

@@ -90,7 +90,9 @@ def decompress(compressed_data, verbose=False, *, precision=None, model=None, de
     dev_out = decompress_device(eng, slots)
     if verbose:
         print("Done.")
-    return _hostio.d2h(eng, dev_out, (T, H, W, 1), out=out, wait=pending)            # decompress.py:104-108
+    res = _hostio.d2h(eng, dev_out, (T, H, W, 1), out=out, wait=pending)             # decompress.py:104-108
+    eng.check_reconstruct()              # the copy synchronised the stream: outlier count of the mask == code count
+    return res
 
 
 def _peek_meta(comp_data: bytes) -> dict:
