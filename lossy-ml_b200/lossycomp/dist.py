@@ -359,7 +359,7 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
         dist.all_gather(alls, tl, group=group)
         alls = [int(v) for v in torch.cat(alls).cpu().tolist()]
         t0, T = sum(alls[:rank]), sum(alls)
-    assert t0 % CHUNK_T == 0, "a time shard must start on a 16-step chunk boundary"
+    assert T_local == 0 or t0 % CHUNK_T == 0, "a time shard must start on a 16-step chunk boundary"
     n_blocks = -(-int(T) // CHUNK_T)
     blocks = all_reduce_blocks(eng.stats_blocks(x_local) if T_local else None, t0 // CHUNK_T, n_blocks, group, cdev)
     mean, std, max_abs = combine_stats(blocks)

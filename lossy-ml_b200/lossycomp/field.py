@@ -53,7 +53,7 @@ def decompress_field(container: bytes, *, precision=None, model=None, device=Non
     for i, lev in enumerate(c["levels"]):
         slots = pickle.loads(c["blobs"][lev])
         if eng is None:
-            from .decompress import _peek_precision
-            eng = Engine.get(model, precision or _peek_precision(slots[0]), device)
+            from .decompress import _peek_meta
+            eng = Engine.get(model, precision or _peek_meta(slots[0]).get("precision"), device)
         out[:, i] = decompress_device(eng, slots).cpu().numpy()
     return out

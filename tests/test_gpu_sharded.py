@@ -81,10 +81,22 @@ def test_sharded_ranks_reproduce_single_call(shape, world):
     procs = [ctx.Process(target=_rank_main, args=(r, world, port, shape, 0.1, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    import queue as _queue
+    res = []
+    for _ in range(3000):                      # up to 5 minutes, but give up as soon as a rank has died
+        try:
+            res.append(q.get(timeout=0.1))
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+        if len(res) == len(procs):
+            break
     for p in procs:
         p.join(timeout=120)
+        if p.is_alive():
+            p.kill()
         assert p.exitcode == 0
+    assert len(res) == len(procs)
     res.sort(key=lambda r: r["rank"])
     assert all(r["err"] <= 0.1 and r["unaligned_equal"] for r in res)
     d = res[-1]
