@@ -31,19 +31,22 @@ from . import _native as N
 from ._engine import Engine
 
 
-def dumps_slots(slots) -> bytes:
-    """pickle.dumps(slots) for the 9-slot list (compress.py:168), written with a single copy of the payloads.
+def pickle_parts(slots) -> list:
+    """The pickle stream of the 9-slot list (compress.py:168) as a list of buffers whose concatenation
+    pickle.loads() turns back into the list.  A byte-string slot may be given as a list of bytes-like pieces
+    (its concatenation is the slot): the multi-GPU path assembles the blob straight from the pieces it received.
 
-    pickle.dumps grows its output buffer while it appends the multi-megabyte byte strings and then copies the
-    result once more (1.0 ms for the 7.7 MB benchmark blob); here the stream is assembled by hand -- PROTO 4,
-    EMPTY_LIST, MARK, one BINBYTES8 opcode per bytes object with the object itself as the operand, the small
-    items as protocol-2 fragments, APPENDS, STOP -- and joined once (0.45 ms).  pickle.loads() of the result is
-    the same list, which is all decompress.py:54 relies on."""
+    The stream is assembled by hand -- PROTO 4, EMPTY_LIST, MARK, one BINBYTES8 opcode per bytes object with the
+    object itself as the operand, the small items as protocol-2 fragments, APPENDS, STOP -- so that the
+    multi-megabyte payloads are copied exactly once (pickle.dumps grows its buffer while appending them and then
+    copies the result again: 1.0 ms against 0.45 ms for the 7.7 MB benchmark blob)."""
     import struct
     parts = [b"\x80\x04", b"]", b"("]
     for item in slots:
-        if isinstance(item, bytes):
+        if isinstance(item, (bytes, bytearray, memoryview)):
             parts += [b"\x8e", struct.pack("<Q", len(item)), item]
+        elif isinstance(item, list) and all(isinstance(p, (bytes, bytearray, memoryview)) for p in item):
+            parts += [b"\x8e", struct.pack("<Q", sum(len(p) for p in item))] + item
         else:
             buf = io.BytesIO()
             pk = pickle.Pickler(buf, protocol=2)
@@ -51,7 +54,13 @@ def dumps_slots(slots) -> bytes:
             pk.dump(item)
             parts.append(buf.getvalue()[2:-1])                      # strip the PROTO header and the STOP opcode
     parts += [b"e", b"."]
-    return b"".join(parts)
+    return parts
+
+
+def dumps_slots(slots) -> bytes:
+    """pickle.dumps(slots) for the 9-slot list (compress.py:168), written with a single copy of the payloads;
+    pickle.loads() of the result is the same list, which is all decompress.py:54 relies on."""
+    return b"".join(pickle_parts(slots))
 
 
 def _guard(max_abs: float, abs_err: float) -> float:

@@ -327,23 +327,74 @@ def build_frame(eng, slots):
 
 
 def _copy_views(dst_views, src_views, pool=None):
-    """Copy pairs of equally long uint8 numpy views, large ones in the thread pool (numpy releases the GIL)."""
+    """Copy pairs of equally long uint8 numpy views, large ones cut into 1 MB slices that run in the thread pool
+    (numpy releases the GIL)."""
     jobs = []
     for d, s in zip(dst_views, src_views):
         if pool is not None and d.size > (1 << 20):
-            jobs.append(pool.submit(np.copyto, d, s))
+            for a in range(0, d.size, 1 << 20):
+                jobs.append(pool.submit(np.copyto, d[a:a + (1 << 20)], s[a:a + (1 << 20)]))
         else:
             np.copyto(d, s)
     for j in jobs:
         j.result()
 
 
+class PendingBlob:
+    """Result of compress_sharded(..., wait=False) on rank `dst`: the blob's device->host copy runs on a copy
+    stream and its assembly in a host thread, behind whatever the caller does next (the next field's kernels).
+    result() returns the slot list."""
+
+    def __init__(self, fn):
+        import threading
+        self._out = self._err = None
+
+        def run():
+            try:
+                self._out = fn()
+            except BaseException as e:       # surfaced by result()
+                self._err = e
+        self._th = threading.Thread(target=run, name="lossycomp-gather", daemon=True)
+        self._th.start()
+
+    def done(self):
+        return not self._th.is_alive()
+
+    def result(self):
+        self._th.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
+
+
+def _sliced_copies(dst_view, pieces, pool, slice_bytes=1 << 20):
+    """Copy the pieces back to back into dst_view (uint8 numpy), every piece cut into <= 1 MB slices that run in
+    the thread pool (numpy releases the GIL): returns the futures."""
+    jobs, o = [], 0
+    for p in pieces:
+        src = np.frombuffer(p, dtype=np.uint8)
+        n = src.size
+        for a in range(0, n, slice_bytes):
+            e = min(a + slice_bytes, n)
+            if e - a >= (64 << 10):
+                jobs.append(pool.submit(np.copyto, dst_view[o + a:o + e], src[a:e]))
+            else:
+                np.copyto(dst_view[o + a:o + e], src[a:e])
+        o += n
+    return jobs
+
+
 def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="strict", codec="huff", group=None,
-                     dst=0, as_bytes=True):
+                     dst=0, wait=True, pickled=False):
     """Every rank passes its own rows [t0, t0 + T_local) of a field of T rows (a time shard made with shard_time)
     as a CUDA tensor (T_local, H, W, 2); rank `dst` gets the slot list of the WHOLE field (others None), plus an
     info dict on every rank.  t0 / T default to this rank's shard of shard_time(sum of T_local, world).
-    as_bytes=False leaves rank dst's big slots as memoryviews over a pinned buffer that the next call reuses."""
+    wait=False: rank `dst` gets a PendingBlob instead -- the device->host copy of the gathered parts (copy stream)
+    and the assembly of the slots (host thread) then overlap the caller's next call; .result() is the slot list.
+    pickled=True: the result is the finished blob (bytes, what compress() returns) instead of the slot list, written
+    with one multi-threaded copy straight from the pinned receive buffer."""
+    import os
+    import time
     import torch
     import torch.distributed as dist
     from . import _hostio
@@ -353,6 +404,17 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
     cdev = comm_device(dev, group)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     T_local = int(x_local.shape[0])
+    tm = [] if os.environ.get("LOSSYCOMP_SHARD_TIMING") else None
+
+    def mark(name):
+        if tm is not None:
+            torch.cuda.synchronize(dev)
+            tm.append((name, time.perf_counter()))
+
+    def timing(info):
+        if tm is not None:
+            info["shard_timing_ms"] = {b[0]: (b[1] - a[1]) * 1e3 for a, b in zip(tm, tm[1:])}
+    mark("start")
     if t0 is None or T is None:
         tl = torch.tensor([T_local], dtype=torch.int64, device=cdev)
         alls = [torch.zeros_like(tl) for _ in range(world)]
@@ -363,6 +425,7 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
     n_blocks = -(-int(T) // CHUNK_T)
     blocks = all_reduce_blocks(eng.stats_blocks(x_local) if T_local else None, t0 // CHUNK_T, n_blocks, group, cdev)
     mean, std, max_abs = combine_stats(blocks)
+    mark("stats")
     if T_local:
         slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec, device_out=True,
                                       inject={"mean": mean, "std": std, "max_abs": max_abs},
@@ -377,40 +440,85 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
                 pass
         info = {"n_out": 0}
         frame, n_host = torch.empty(0, dtype=torch.uint8, device=dev), 0
+    mark("compress+frame")
     got = gather_tensors(frame, n_host, dst, group)
+    mark("gather")
     if got is None:
+        timing(info)
         return None, info
     recv, table = got
-    # one device->host copy of everything, then the slot byte strings are cut out of the pinned buffer
+    # one device->host copy of everything on the copy stream (into one of three pinned buffers, each guarded by
+    # the job that last read it); the slot byte strings are then cut out of the pinned buffer by a host thread
     total = int(recv.numel())
+    done = None
     if recv.is_cuda:
-        pin = eng._pinned("gather", total)
-        pin[:total].copy_(recv, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        ring = eng._small.setdefault("gather_ring", [None, None, None])
+        k = eng._small["gather_next"] = (eng._small.get("gather_next", -1) + 1) % 3
+        if ring[k] is not None and ring[k][1] is not None:
+            ring[k][1].result()                                         # the job that used this buffer last
+        pin = ring[k][0] if ring[k] is not None else None
+        if pin is None or pin.numel() < total:
+            pin = torch.empty(max(int(total * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        main = torch.cuda.current_stream(dev)
+        copy = eng._small.get("gather_stream")
+        if copy is None:
+            copy = eng._small["gather_stream"] = torch.cuda.Stream(device=dev)
+        copy.wait_stream(main)
+        with torch.cuda.stream(copy):
+            pin[:total].copy_(recv, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(copy)
+        recv.record_stream(copy)
     else:
-        pin = recv
-    hv = memoryview(pin.numpy())
-    rank_slots = [parse_frame(hv[o:o + n]) for o, n, _ in table if n]
+        pin, k, ring = recv, None, None
 
-    def join(parts_per_rank):
-        """[[piece views of rank r's container]] -> the multi-part container (one copy of the payloads)."""
-        lens = [sum(len(p) for p in parts) for parts in parts_per_rank]
-        hdr = multipart_header(lens) if len(parts_per_rank) > 1 else b""
-        if not as_bytes:
-            return [hdr] + [p for parts in parts_per_rank for p in parts]
-        obj, view = _new_bytes(len(hdr) + sum(lens))
-        view[:len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
-        o = len(hdr)
-        dsts, srcs = [], []
-        for parts in parts_per_rank:
-            for p in parts:
-                dsts.append(view[o:o + len(p)])
-                srcs.append(np.frombuffer(p, dtype=np.uint8))
-                o += len(p)
-        _copy_views(dsts, srcs, _hostio._threads())
-        return obj
+    def finish():
+        if done is not None:
+            done.synchronize()
+        hv = memoryview(pin.numpy())
+        rank_slots = [parse_frame(hv[o:o + n]) for o, n, _ in table if n]
+        pool = _hostio._threads()
+        jobs = []
+        if pickled:
+            # the pickle stream of the whole blob, cut straight out of the pinned buffer: every payload byte is
+            # copied once, in 1 MB slices across the thread pool
+            def pieces(parts_per_rank):
+                lens = [sum(len(p) for p in parts) for parts in parts_per_rank]
+                hdr = [multipart_header(lens)] if len(parts_per_rank) > 1 else []
+                return hdr + [p for parts in parts_per_rank for p in parts]
+            from .compress import pickle_parts
+            parts = pickle_parts(assemble_blob(rank_slots, pieces))
+            obj, view = _new_bytes(sum(len(p) for p in parts))
+            for j in _sliced_copies(view, parts, pool):
+                j.result()
+            return obj
 
-    return assemble_blob(rank_slots, join), info
+        def join(parts_per_rank):
+            """[[piece views of rank r's container]] -> the multi-part container (one copy of the payloads)."""
+            lens = [sum(len(p) for p in parts) for parts in parts_per_rank]
+            hdr = multipart_header(lens) if len(parts_per_rank) > 1 else b""
+            obj, view = _new_bytes(len(hdr) + sum(lens))
+            view[:len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
+            jobs.extend(_sliced_copies(view[len(hdr):], [p for parts in parts_per_rank for p in parts], pool))
+            return obj
+
+        out = assemble_blob(rank_slots, join)
+        for j in jobs:
+            j.result()
+        return out
+
+    if not wait:
+        pend = PendingBlob(finish)
+        if ring is not None:
+            ring[k] = (pin, pend)
+        timing(info)
+        return pend, info
+    out = finish()
+    if ring is not None:
+        ring[k] = (pin, None)
+    mark("d2h+assemble")
+    timing(info)
+    return out, info
 
 
 def _cut(blob, head_len, tail_len=0):
@@ -567,10 +675,76 @@ def compress_sharded_host(array_local, err_threshold, *, t0, T, precision=None, 
         x = _hostio.h2d(eng, array_local)
     else:
         x = torch.empty(array_local.shape, dtype=torch.float32, device=eng.dev)
-    slots, _ = compress_sharded(eng, x, err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=group, dst=dst)
-    if dist.get_rank(group) != dst:
-        return None
-    return dumps_slots(slots)
+    blob, _ = compress_sharded(eng, x, err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=group, dst=dst,
+                               pickled=True)
+    return blob if dist.get_rank(group) == dst else None
+
+
+def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=None, model=None, device=None,
+                            mode="strict", codec="huff", group=None, dst=0):
+    """Bulk-job form of compress_sharded_host: a sequence of fields (each given by this rank's rows of it, all with
+    the same sharding) -> one blob per field on rank `dst` (None elsewhere), each identical to the blob
+    compress_sharded_host returns.  The host->device copy of field k+1 runs on a second stream behind the kernels
+    of field k (pinned inputs), and the gathered blob of field k reaches the host (copy stream + host thread)
+    behind the kernels of field k+1."""
+    import torch.distributed as dist
+    from . import _hostio
+    from . import _native as N
+    from ._engine import Engine
+    from .compress import dumps_slots
+    torch = N.require_cuda()
+    eng = Engine.get(model, precision, device)
+    main = torch.cuda.current_stream(eng.dev)
+    copy = torch.cuda.Stream(device=eng.dev)
+    is_dst = dist.get_rank(group) == dst
+    bufs, ready, freed = [None, None], [None, None], [None, None]
+
+    def upload(slot, array):
+        if array.dtype != np.float32:
+            array = np.array(array, dtype=np.float32)
+        assert array.ndim == 4 and array.shape[3] == 2, "Input should have 2 channels."
+        src = torch.from_numpy(np.ascontiguousarray(array))
+        if not src.is_pinned() or not array.shape[0]:
+            bufs[slot] = _hostio.h2d(eng, array) if array.shape[0] else \
+                torch.empty(array.shape, dtype=torch.float32, device=eng.dev)
+            ready[slot] = None
+            return
+        if bufs[slot] is None or bufs[slot].shape != src.shape:
+            bufs[slot] = torch.empty(src.shape, dtype=torch.float32, device=eng.dev)
+        if freed[slot] is not None:
+            copy.wait_event(freed[slot])
+        with torch.cuda.stream(copy):
+            bufs[slot].copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        ready[slot] = (ev, src)
+
+    it = iter(arrays_local)
+    try:
+        upload(0, next(it))
+    except StopIteration:
+        return
+    k, prev = 0, None
+    while True:
+        slot = k & 1
+        if ready[slot] is not None:
+            main.wait_event(ready[slot][0])
+        try:
+            upload(slot ^ 1, next(it))
+            more = True
+        except StopIteration:
+            more = False
+        pend, _ = compress_sharded(eng, bufs[slot], err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=group,
+                                   dst=dst, wait=False, pickled=True)
+        freed[slot] = torch.cuda.Event()
+        freed[slot].record(main)
+        if prev is not None:                      # the previous field's blob was finished behind this field's kernels
+            yield prev.result() if is_dst else None
+        prev = pend if is_dst else True
+        if not more:
+            yield prev.result() if is_dst else None
+            return
+        k += 1
 
 
 def decompress_sharded_host(blob_or_none, *, precision=None, model=None, device=None, group=None, src=0):

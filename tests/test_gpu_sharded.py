@@ -40,8 +40,15 @@ def _rank_main(rank, world, port, shape, abs_err, q):
         t0, t1 = D.shard_time(T, world)[rank]
         dst = world - 1
         slots, info = D.compress_sharded(eng, full[t0:t1].contiguous(), abs_err, t0=t0, T=T, dst=dst)
-        # the same call without telling the ranks where they are (one more tiny all-gather)
-        slots2, _ = D.compress_sharded(eng, full[t0:t1].contiguous(), abs_err, dst=dst)
+        # the same call without telling the ranks where they are (one more tiny all-gather), asynchronously
+        pend, _ = D.compress_sharded(eng, full[t0:t1].contiguous(), abs_err, dst=dst, wait=False)
+        slots2 = pend.result() if pend is not None else None
+        # host-facing entry points: numpy rows in, pickled blob out on dst; the streamed form gives the same blobs
+        import pickle
+        xl = full[t0:t1].cpu().numpy()
+        blob = D.compress_sharded_host(xl, abs_err, t0=t0, T=T, precision="fp16", dst=dst)
+        blobs = list(D.compress_sharded_stream([xl, xl, xl], abs_err, t0=t0, T=T, precision="fp16", dst=dst))
+        a3, b3, rows3 = D.decompress_sharded_host(blob, precision="fp16", src=dst)
         a, b, rows = D.decompress_sharded(eng, slots, src=dst)                       # aligned: parts scattered
         assert (a, b) == (t0, t1)
         err = float((full[a:b, :, :, 0].double() - rows.double()).abs().max()) if b > a else 0.0
@@ -58,11 +65,15 @@ def _rank_main(rank, world, port, shape, abs_err, q):
                 rows_equal=bool(torch.equal(whole[a:b], rows)),
                 same_without_hints=bool(all(bytes(slots[i]) == bytes(slots2[i]) for i in (0, 6, 7))),
                 n_parts=len(D.unpack_multipart(slots[7])),
+                host_blob_equal=bool(pickle.loads(blob) == [bytes(v) if isinstance(v, (bytes, memoryview)) else v
+                                                            for v in slots]),
+                stream_equal=bool(blobs == [blob] * 3),
                 types=[type(s).__name__ for s in slots])
             unaligned = ref                      # a single-part blob on two ranks: the broadcast + slice path
         else:
-            assert slots is None and slots2 is None
+            assert slots is None and slots2 is None and blob is None and blobs == [None] * 3
             unaligned = None
+        res["host_rows_equal"] = bool((a3, b3) == (a, b) and np.array_equal(rows3[..., 0], rows.cpu().numpy()))
         a2, b2, rows2 = D.decompress_sharded(eng, unaligned, src=dst)
         res["unaligned_equal"] = bool(torch.equal(rows2, rows)) if b > a else True
         q.put(res)
@@ -98,10 +109,10 @@ def test_sharded_ranks_reproduce_single_call(shape, world):
         assert p.exitcode == 0
     assert len(res) == len(procs)
     res.sort(key=lambda r: r["rank"])
-    assert all(r["err"] <= 0.1 and r["unaligned_equal"] for r in res)
+    assert all(r["err"] <= 0.1 and r["unaligned_equal"] and r["host_rows_equal"] for r in res)
     d = res[-1]
     assert d["stats_equal"] and d["shapes_equal"] and d["mask_equal"] and d["codes_equal"] and d["xhat_equal"]
-    assert d["rows_equal"] and d["same_without_hints"]
+    assert d["rows_equal"] and d["same_without_hints"] and d["host_blob_equal"] and d["stream_equal"]
     assert d["types"] == ["bytes", "tuple", "tuple", "tuple", "float32", "float32", "bytes", "bytes", "float"]
     n_nonempty = sum(1 for a, b in __import__("lossycomp.dist", fromlist=["x"]).shard_time(shape[0], world) if b > a)
     assert d["n_parts"] == n_nonempty
