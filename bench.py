@@ -278,16 +278,26 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
     barrier()
+    slots, info = step()                 # one more untimed step: the GPUs idled while the clock sampler started
+    slots = finish(slots)
+    eng.profile_read()
+    barrier()
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     e0.record()
     pending = []
+    marks = [time.perf_counter()]
     for _ in range(args.steps):
         slots, info = step()
         pending.append(slots)
+        marks.append(time.perf_counter())
     slots = [finish(p) for p in pending][-1]          # all K blobs are in host memory before the clock stops
+    marks.append(time.perf_counter())
     e1.record()
+    if os.environ.get("LOSSYCOMP_BENCH_TRACE"):
+        print(f"[bench trace] rank {rank}: host ms per step " + " ".join(f"{1e3 * (b - a):.1f}" for a, b in zip(marks, marks[1:])),
+              file=sys.stderr, flush=True)
     barrier()
     w1 = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1))

@@ -88,11 +88,12 @@ class _StageTimer:
 
 def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff", verify=None,
                     inject=None, latent_codec=None, batch=None, return_parts=False, timing=False,
-                    device_out=False, agree=None):
+                    device_out=False, guard_scale=1.0, retry=True):
     """x: torch float32 CUDA tensor (T,H,W,2).  Returns (slots list, info dict).
     device_out: slots 0/6/7 come back as _engine.DevPieces whose payloads are still in device memory (the
-    multi-GPU path sends them over NCCL from there).  agree(violations) -> the count every rank must act on
-    (dist.compress_sharded passes an all-reduce MAX so that all ranks widen the guard band together)."""
+    multi-GPU path sends them over NCCL from there).  guard_scale multiplies strict mode's guard band; retry=False
+    reports a bound violation in info["violations"] instead of widening the band and quantising again
+    (dist.compress_sharded makes that decision for all ranks together)."""
     assert err_threshold != 0, "The absolute error can't be 0."                      # compress.py:34
     assert x.dim() == 4 and x.shape[3] == eng.model.arch.in_channels, \
         "Input should have %d channels." % eng.model.arch.in_channels                # compress.py:55
@@ -126,7 +127,7 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     thr = abs_err
     info = {"mode": mode, "codec": codec}
     if mode == "strict":
-        g = _guard(max_abs, abs_err)
+        g = _guard(max_abs, abs_err) * float(guard_scale)
         assert abs_err > 2 * g, "abs_error is below the float32 resolution of the data"
         thr = abs_err - g
     elif mode != "parity":
@@ -146,9 +147,7 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
             mask, q = eng.quantize(x, recon, mean, std, thr)
             break
         info.update(violations=viol, max_err=max_err)
-        if agree is not None and mode == "strict":
-            viol = agree(viol)
-        if viol == 0 or mode != "strict":
+        if viol == 0 or mode != "strict" or not retry:
             break
         thr = abs_err - 2.0 * (abs_err - thr)    # widen the guard band and redo the cheap stages
         assert thr > 0.5 * abs_err, "cannot meet the bound in float32"

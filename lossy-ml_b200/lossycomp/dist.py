@@ -209,23 +209,16 @@ def comm_device(dev, group=None):
 def all_reduce_blocks(local_blocks, block0: int, n_blocks: int, group=None, device=None):
     """local_blocks: (k, 4) float64 tensor of {sum, sum^2, max|x|, n} of this rank's time blocks, which are blocks
     [block0, block0 + k) of the whole field's n_blocks -> list of n_blocks tuples, identical on every rank.
-    Sums travel in one all-reduce over disjoint entries (x + 0 is exact in any order), the maxima in another."""
+    ONE all-reduce (SUM): every block belongs to exactly one rank, so each entry receives one value plus zeros,
+    which is exact in any order -- for the sums and for the per-block maxima alike."""
     import torch
     import torch.distributed as dist
     k = int(local_blocks.shape[0]) if local_blocks is not None else 0
-    a = torch.zeros((n_blocks, 3), dtype=torch.float64, device=device)
-    m = torch.zeros((n_blocks,), dtype=torch.float64, device=device)
+    a = torch.zeros((n_blocks, 4), dtype=torch.float64, device=device)
     if k:
-        lb = local_blocks.to(device)
-        a[block0:block0 + k, 0] = lb[:, 0]
-        a[block0:block0 + k, 1] = lb[:, 1]
-        a[block0:block0 + k, 2] = lb[:, 3]
-        m[block0:block0 + k] = lb[:, 2]
+        a[block0:block0 + k] = local_blocks.to(device)
     dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
-    a = a.cpu().tolist()
-    m = m.cpu().tolist()
-    return [(a[i][0], a[i][1], m[i], a[i][2]) for i in range(n_blocks)]
+    return [tuple(r) for r in a.cpu().tolist()]
 
 
 def all_reduce_max(value: int, group=None, device=None) -> int:
@@ -236,11 +229,13 @@ def all_reduce_max(value: int, group=None, device=None) -> int:
     return int(v.item())
 
 
-def gather_tensors(frame, meta: int = 0, dst: int = 0, group=None):
+def gather_tensors(frame, meta: int = 0, dst: int = 0, group=None, veto=None):
     """Variable-length uint8 tensors of all ranks -> on rank `dst` (recv buffer holding all frames back to back,
     [(offset, length, meta)] per rank), None elsewhere.  `meta` is one integer per rank that travels with the
     lengths (the frames' host-section length).  Lengths: one all-gather; payloads: point-to-point send/recv posted
-    as one group (NCCL over NVLink on GPUs), straight from / into device memory."""
+    as one group (NCCL over NVLink on GPUs), straight from / into device memory.
+    veto: an integer per rank that travels with the lengths too; when any rank's is non-zero nothing is sent and
+    every rank gets the string "veto" back (the sharded compressor's strict-mode verdict: all ranks retry)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -248,10 +243,13 @@ def gather_tensors(frame, meta: int = 0, dst: int = 0, group=None):
     if frame.is_cuda and dist.get_backend(group) != "nccl":
         frame = frame.cpu()
     dev = frame.device
-    n = torch.tensor([int(frame.numel()), int(meta)], dtype=torch.int64, device=dev)
+    n = torch.tensor([int(frame.numel()), int(meta), int(veto or 0)], dtype=torch.int64, device=dev)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
     sizes = torch.stack(sizes).cpu().tolist()
+    if veto is not None and any(v for _, _, v in sizes):
+        return "veto"
+    sizes = [(a_, b_) for a_, b_, _ in sizes]
     if rank != dst:
         if frame.numel():
             dist.send(frame, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
@@ -426,22 +424,28 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
     blocks = all_reduce_blocks(eng.stats_blocks(x_local) if T_local else None, t0 // CHUNK_T, n_blocks, group, cdev)
     mean, std, max_abs = combine_stats(blocks)
     mark("stats")
-    if T_local:
-        slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec, device_out=True,
-                                      inject={"mean": mean, "std": std, "max_abs": max_abs},
-                                      agree=lambda v: all_reduce_max(v, group, cdev))
-        for i in BIG:
-            if not isinstance(slots[i], DevPieces):
-                slots[i] = DevPieces([slots[i]])
-        frame, n_host = build_frame(eng, slots)
-    else:
-        if mode == "strict":                       # take part in the verdict exchange of the retry loop
-            while all_reduce_max(0, group, cdev):
-                pass
-        info = {"n_out": 0}
-        frame, n_host = torch.empty(0, dtype=torch.uint8, device=dev), 0
-    mark("compress+frame")
-    got = gather_tensors(frame, n_host, dst, group)
+    # Strict mode's verdict is collective: a rank that finds a bound violation must not widen its guard band alone
+    # (the ranks would disagree on the threshold of blob slot 8).  Every rank compresses with the same guard, the
+    # violation counts travel with the frame lengths, and if any is non-zero ALL ranks retry with twice the guard.
+    guard_scale = 1.0
+    while True:
+        if T_local:
+            slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec, device_out=True,
+                                          inject={"mean": mean, "std": std, "max_abs": max_abs},
+                                          guard_scale=guard_scale, retry=False)
+            for i in BIG:
+                if not isinstance(slots[i], DevPieces):
+                    slots[i] = DevPieces([slots[i]])
+            frame, n_host = build_frame(eng, slots)
+        else:
+            info = {"n_out": 0}
+            frame, n_host = torch.empty(0, dtype=torch.uint8, device=dev), 0
+        mark("compress+frame")
+        got = gather_tensors(frame, n_host, dst, group, veto=int(info.get("violations", 0)) if mode == "strict" else 0)
+        if not isinstance(got, str):
+            break
+        guard_scale *= 2.0
+        assert guard_scale <= 1024.0, "cannot meet the bound in float32"
     mark("gather")
     if got is None:
         timing(info)

@@ -118,6 +118,10 @@ def _worker(rank, world, port, q):
         else:
             assert g2 is None
         assert D.all_reduce_max(5 * rank) == 5
+        # strict mode's collective verdict: one rank's violation makes every rank retry, nothing is sent
+        assert D.gather_tensors(fr, 0, dst=1, veto=3 * rank) == "veto"
+        g3 = D.gather_tensors(fr, 0, dst=1, veto=0)
+        assert (g3 is None) == (rank == 0)
         q.put((rank, tot, got, empty))
     finally:
         dist.destroy_process_group()
