@@ -79,6 +79,11 @@ struct SweepParams {
   const float* bias;
   int cout, relu, half, out_T;
   int debug;   // ablation: bit0 no MMA issue, bit3 no bulk copies, bit4 single issuer warp
+  // sweep_acc_kernel (time taps accumulated in TMEM): weight image with the time blocks stored twice in decreasing
+  // order, 8-row-group pitch b2_rows, descriptors relative to its start
+  const uint4* wimg2;
+  int wimg2_bytes, b2_rows, stages2;
+  uint64_t b2_desc[kMaxKs];
 };
 
 // 12 consecutive accumulator columns of this thread's TMEM lane
@@ -670,6 +675,224 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// sweep_acc_kernel: the stride-1 layers with the time taps ACCUMULATED IN TMEM (second-generation form of the
+// K3 / K4 modes above).
+//
+// The plane-sweep MMA is unchanged -- D[voxel, (dt, co)] += X[t_in][voxel + tap][ci] * W[dt][tap][ci][co], N = NT
+// time blocks of 24 columns -- but the NT blocks no longer land in a fresh accumulator that the epilogue folds in
+// registers.  A bank of NT*24 TMEM columns holds the NT output planes currently under construction, plane p in
+// slot p mod NT, and the MMA of input plane t adds block dt straight onto output plane t - dt + 1: the weight
+// image stores the time blocks twice in decreasing order ([dt=NT-1 .. 0, NT-1 .. 1]) and the B descriptor of
+// input plane t starts ((NT-2-t) mod NT) blocks in, which rotates the blocks onto the right slots.  The epilogue
+// thread of a finished plane reads its 24 columns, writes the bias back into them (the slot's next plane starts
+// from the bias, so the bias add is free and every MMA accumulates) and hands the bank back; conversion, packing
+// and the global stores happen after that.  What this buys over the register fold:
+//   * a third of the TMEM reads, no accumulator adds, no register rotation: ~60 instead of ~180 instructions per
+//     voxel plane, and one thread owns all 24 channels of a voxel, so every store is a full 16-byte vector per lane
+//     (512 contiguous bytes per warp) -- the old 12-channel halves wrote half-filled 32-byte sectors;
+//   * one persistent CTA per SM with kAccBanks tiles in flight (bank b = tile 4r+b of the CTA, input planes
+//     interleaved plane by plane): while the epilogue of one bank drains, the tensor pipe works on the other three,
+//     the weights sit in shared memory once per SM, and 8-12 stages of input planes are in flight.
+// Warps: 0 producer (bulk copies), 1-2 MMA issuers (alternate steps), 3 TMEM allocation, 4.. epilogue (bank =
+// (warp-4)/4, TMEM lane quarter = warp % 4).  Deterministic: fixed accumulation order per output voxel.
+constexpr int kAccBanks = 4;
+constexpr int kAccThreads = 32 * (4 + 4 * kAccBanks);
+constexpr int kAccMaxStages = 12;
+
+template <int NT, int H16, int RELU>
+__global__ void __launch_bounds__(kAccThreads, 1)
+sweep_acc_kernel(const __grid_constant__ SweepParams p) {
+  constexpr int kBankCols = (NT * 24 + 15) & ~15;       // = the MMA's N (80 for NT = 3: 8 scratch columns)
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full[kAccMaxStages], empty[kAccMaxStages], tfull[kAccBanks], tempty[kAccBanks], wbar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[24];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int slab_bytes = p.slab_slots * 16;
+  const int skip_bytes = p.skip_mma ? p.skip.G * p.skip_slots * 16 : 0;
+  const int stage_bytes = p.in_NPG * slab_bytes + skip_bytes;
+  const int stages = p.stages2;
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + ((p.wimg2_bytes + 127) & ~127);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kAccBanks; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
+    umma::mbar_init(&wbar, 1);
+    umma::fence_barrier_init();
+  }
+  if (threadIdx.x < 24) s_bias[threadIdx.x] = (threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
+  if (warp == 3) umma::tmem_alloc(&tmem_base_s, 512u);
+  umma::tcgen05_fence_before();
+  __syncthreads();
+  umma::tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int T = p.in_T;
+  // this CTA's items: blockIdx.x + k * gridDim.x, k < cnt; round r works on items 4r .. 4r+3 (one per bank)
+  const int cnt = ((int)blockIdx.x < p.n_items) ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int rounds = (cnt + kAccBanks - 1) / kAccBanks;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      umma::mbar_arrive_expect_tx(&wbar, (uint32_t)p.wimg2_bytes);
+      umma::bulk_g2s(sB, p.wimg2, (uint32_t)p.wimg2_bytes, &wbar);
+      int stage = 0, phase = 0;
+      for (int r = 0; r < rounds; ++r) {
+        const int nb = min(kAccBanks, cnt - kAccBanks * r);
+        long long slab0[kAccBanks];
+        const uint4* sk0[kAccBanks];
+#pragma unroll
+        for (int b = 0; b < kAccBanks; ++b) {
+          const int item = (int)blockIdx.x + (kAccBanks * r + b) * (int)gridDim.x;
+          const int n = item / p.tiles_per_chunk;
+          const int tile = item - n * p.tiles_per_chunk;
+          slab0[b] = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start;
+          sk0[b] = p.skip_mma ? reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride +
+                                    p.skip.GL + p.row0 + tile * 128 - p.skip_pad
+                              : nullptr;
+        }
+        for (int t = 0; t < T; ++t) {
+          for (int b = 0; b < nb; ++b) {
+            umma::mbar_wait(&empty[stage], phase ^ 1);
+            if (p.debug & 8) { umma::mbar_arrive(&full[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
+            umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            uint8_t* dst = sA + stage * stage_bytes;
+            for (int g = 0; g < p.in_NPG; ++g)
+              umma::bulk_g2s(dst + g * slab_bytes, p.in + slab0[b] + (long long)(t * p.in_NPG + g) * p.in_S,
+                             (uint32_t)slab_bytes, &full[stage]);
+            if (p.skip_mma)
+              for (int g = 0; g < p.skip.G; ++g)
+                umma::bulk_g2s(dst + p.in_NPG * slab_bytes + g * p.skip_slots * 16,
+                               sk0[b] + (long long)(t * p.skip.G + g) * p.skip.S, (uint32_t)(p.skip_slots * 16),
+                               &full[stage]);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers (alternate steps) =====================
+    const int me = warp - 1;
+    umma::mbar_wait(&wbar, 0);
+    const uint32_t idesc = umma::make_idesc(128, kBankCols, H16 ? 0 : 1);
+    const uint64_t sA_add = (uint64_t)(umma::smem_u32(sA) >> 4), sB_add = (uint64_t)(umma::smem_u32(sB) >> 4);
+    int stage = 0, phase = 0, step = 0;
+    (void)step;
+    for (int r = 0; r < rounds; ++r) {
+      const int nb = min(kAccBanks, cnt - kAccBanks * r);
+      for (int t = 0; t < T; ++t) {
+        // start block of the rotated weight image: block i holds dt = (NT-1-i) mod NT; slot s must receive
+        // dt = (t+1-s) mod NT  =>  i0 = (NT-2-t) mod NT
+        const int i0 = (((NT - 2 - t) % NT) + NT) % NT;
+        const uint64_t b_add = sB_add + (uint64_t)(i0 * 24);      // 24 rows of 16 bytes, in 16-byte units
+        const int kb = r * T + t;                                 // this bank-step's index (all banks alike)
+        for (int b = 0; b < nb; ++b, ++step) {
+          // a bank always belongs to the same issuer: its steps must be issued in order, each after the epilogue
+          // of the one before (alternating issuers by step would let one run a whole phase ahead of the other on
+          // the same bank whenever the number of active banks is odd)
+          if ((b & 1) == me) {
+            umma::mbar_wait(&tempty[b], kb & 1);
+            umma::mbar_wait(&full[stage], phase);
+            umma::tcgen05_fence_after();
+            const uint64_t a_add = sA_add + (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
+            const uint32_t d_addr = tmem + b * kBankCols;
+            const int nks = (p.debug & 1) ? 0 : p.nks;
+#pragma unroll 2
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t a = p.a_desc[0][ks] + a_add, bd = p.b2_desc[ks] + b_add;
+              if (umma::elect_one()) umma::mma_f16(d_addr, a, bd, idesc, true);
+            }
+            __syncwarp();
+            if (umma::elect_one()) umma::commit(&tfull[b]);
+            __syncwarp();
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int b = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t bank_addr = tmem + ((uint32_t)(q * 32) << 16) + b * kBankCols;
+    uint32_t bias_u[24];
+#pragma unroll
+    for (int c = 0; c < 24; ++c) bias_u[c] = __float_as_uint(s_bias[c]);
+    auto init_slot = [&](int slot) {
+      umma::tmem_st8(bank_addr + slot * 24, bias_u);
+      umma::tmem_st8(bank_addr + slot * 24 + 8, bias_u + 8);
+      umma::tmem_st8(bank_addr + slot * 24 + 16, bias_u + 16);
+    };
+    auto hand_back = [&]() {
+      umma::tmem_st_wait();
+      umma::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tempty[b]);
+    };
+    // 24 accumulator columns of one slot -> 12 packed 16-bit pairs ((ReLU,) saturate, round to nearest even)
+    auto load_pack = [&](int slot, unsigned (&pk)[12]) {
+      uint32_t v[24];
+      umma::tmem_ld8(bank_addr + slot * 24, v);
+      umma::tmem_ld8(bank_addr + slot * 24 + 8, v + 8);
+      umma::tmem_ld8(bank_addr + slot * 24 + 16, v + 16);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 12; ++i) pk[i] = pack2_t<H16, RELU>(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    };
+    const int G = p.out.G;
+    // every slot starts from the bias
+#pragma unroll
+    for (int s = 0; s < NT; ++s) init_slot(s);
+    hand_back();
+    for (int r = 0; kAccBanks * r + b < cnt; ++r) {
+      const int nb = min(kAccBanks, cnt - kAccBanks * r);
+      const int item = (int)blockIdx.x + (kAccBanks * r + b) * (int)gridDim.x;
+      const RowInfo ri = row_info(p, item, row);
+      const VoxPtr vp = vox_ptr(p, ri.n, ri.h, ri.w);
+      auto store_plane = [&](int plane, const unsigned (&pk)[12]) {
+        uint4* o = vp.o + (long long)plane * vp.o_t;
+        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (G > 1) o[vp.o_g] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (G > 2) o[2 * vp.o_g] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+      };
+      for (int t = 0; t < T; ++t) {
+        const int kb = r * T + t;
+        umma::mbar_wait(&tfull[b], kb & 1);
+        umma::tcgen05_fence_after();
+        // the MMAs that read this step's stage are complete: hand the stage back to the producer
+        // (all earlier rounds were full, so the step index is 4*T*r + t*nb + b)
+        if (q == 0 && lane == 0) umma::mbar_arrive(&empty[(kAccBanks * T * r + t * nb + b) % stages]);
+        const int pc = t - (NT - 2);                              // the plane that completed with this step
+        if (t + 1 < T) {
+          unsigned pk[12];
+          const int slot = (pc + NT) % NT;
+          if (pc >= 0) load_pack(slot, pk);
+          init_slot(slot);
+          hand_back();
+          if (pc >= 0 && ri.valid) store_plane(pc, pk);
+        } else {
+          // last input plane: the remaining NT-1 planes are complete; all slots restart from the bias
+          unsigned pk[NT - 1][12];
+#pragma unroll
+          for (int j = 0; j < NT - 1; ++j)
+            if (pc + j >= 0) load_pack((pc + j + NT) % NT, pk[j]);
+#pragma unroll
+          for (int s = 0; s < NT; ++s) init_slot(s);
+          hand_back();
+#pragma unroll
+          for (int j = 0; j < NT - 1; ++j)
+            if (pc + j >= 0 && ri.valid) store_plane(pc + j, pk[j]);
+        }
+      }
+    }
+  }
+  umma::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 3) umma::tmem_dealloc(tmem, 512u);
+}
+
+// ------------------------------------------------------------------------------------------
 // plan: tensors of one chunk block
 // ------------------------------------------------------------------------------------------
 enum { LAYOUT_PLAIN = 0, LAYOUT_PARITY = 1, LAYOUT_WFOLD = 2 };
@@ -687,6 +910,8 @@ struct LayerPlan {
   float* d_w16;            // fp32 weights rounded through the 16-bit operand format [tap][cin][cout]
   SweepParams sp;          // template (pointers filled per call)
   int smem_bytes;
+  int acc_smem_bytes;      // > 0: the layer runs sweep_acc_kernel (time taps accumulated in TMEM)
+  void* d_wimg2;
 };
 
 struct TcPlan {
@@ -953,7 +1178,29 @@ int launch_mode(const lc_codec* h, const SweepParams& p, int grid, int smem, cud
   return p.relu ? launch_variant<MODE, 0, 1>(p, grid, smem, s) : launch_variant<MODE, 0, 0>(p, grid, smem, s);
 }
 
+template <int NT, int H16, int RELU>
+int launch_acc_variant(const SweepParams& p, int grid, int smem, cudaStream_t s) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  LC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  sweep_acc_kernel<NT, H16, RELU><<<grid, kAccThreads, smem, s>>>(p);
+  return LC_OK;
+}
+
 int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStream_t s) {
+  if (lp.acc_smem_bytes > 0 && lp.backend == MODE_K3) {
+    int grid = h->num_sms < p.n_items ? h->num_sms : p.n_items;
+    int rc;
+    if (p.half) rc = p.relu ? launch_acc_variant<3, 1, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<3, 1, 0>(p, grid, lp.acc_smem_bytes, s);
+    else rc = p.relu ? launch_acc_variant<3, 0, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<3, 0, 0>(p, grid, lp.acc_smem_bytes, s);
+    if (rc != LC_OK) return rc;
+    LC_LAUNCH_CHECK();
+    return LC_OK;
+  }
   const int smem = lp.smem_bytes;
   const int per_sm = ctas_per_sm(lp.backend);
   int grid = per_sm * h->num_sms;
@@ -1211,6 +1458,58 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   p.wimg = reinterpret_cast<const uint4*>(L.d_wtc);
   // a stage = the input slabs of one plane (+ the skip tile when the residual add runs on the tensor core)
   const int stage_bytes = p.in_NPG * p.slab_slots * 16 + (p.skip_mma ? G * p.skip_slots * 16 : 0);
+  lp.acc_smem_bytes = 0;
+  lp.d_wimg2 = nullptr;
+  if (mode == MODE_K3 && (!L.res_add || p.skip_mma) && cout <= 24 && !getenv("LOSSYCOMP_NO_ACC")) {
+    // weight image of sweep_acc_kernel: per 8-channel K group, the NT time blocks twice in decreasing order
+    // ([dt = NT-1 .. 0, NT-1 .. 1], 24 rows each) so that a start offset of i0 blocks rotates them onto the TMEM
+    // slots; padded to the rows the widest start (NT-1 blocks in) reads with N = bank columns
+    const int NT = k;
+    const int bank_cols = (NT * 24 + 15) & ~15;
+    const int rows = ((NT - 1) * 24 + bank_cols + 7) & ~7;
+    std::vector<unsigned short> img2((size_t)p.nks * 2 * rows * 8, 0);
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const KGroup& kg = groups[0][gi];
+      for (int i = 0; i < 2 * NT - 1; ++i) {
+        const int kt = (NT - 1 - i % NT + NT) % NT;
+        for (int co = 0; co < cout; ++co) {
+          unsigned short* dst = &img2[((size_t)gi * rows + (size_t)i * 24 + co) * 8];
+          if (kg.plane < 0) {   // skip group: identity into the centre time block
+            if (kt == L.pad_lo && co >= kg.ci0 && co < kg.ci0 + 8) dst[co - kg.ci0] = to_h16_host(1.0f, half);
+            continue;
+          }
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int ci = kg.ci0 + k8;
+            if (ci >= cin) continue;
+            dst[k8] = to_h16_host(w16[((size_t)((kt * k + kg.tap_h) * k + kg.tap_w) * cin + ci) * cout + co], half);
+          }
+        }
+      }
+    }
+    auto host_desc2 = [](uint32_t addr, uint32_t lbo, uint32_t sbo) {
+      uint64_t d = 0;
+      d |= (uint64_t)((addr >> 4) & 0x3FFF);
+      d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+      d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+      d |= (uint64_t)1 << 46;
+      return d;
+    };
+    for (int ks = 0; ks < p.nks; ++ks)
+      p.b2_desc[ks] = host_desc2((uint32_t)((size_t)ks * 2 * rows * 16), (uint32_t)rows * 16, 128);
+    p.wimg2_bytes = (int)(img2.size() * 2);
+    p.b2_rows = rows;
+    LC_CUDA(cudaMalloc(&lp.d_wimg2, img2.size() * 2));
+    LC_CUDA(cudaMemcpy(lp.d_wimg2, img2.data(), img2.size() * 2, cudaMemcpyHostToDevice));
+    p.wimg2 = reinterpret_cast<const uint4*>(lp.d_wimg2);
+    const int fixed2 = ((p.wimg2_bytes + 127) & ~127) + 256;
+    int st2 = (200 * 1024 - fixed2) / stage_bytes;
+    if (st2 > kAccMaxStages) st2 = kAccMaxStages;
+    if (getenv("LOSSYCOMP_ACC_STAGES")) st2 = atoi(getenv("LOSSYCOMP_ACC_STAGES"));
+    if (st2 >= 4) {
+      p.stages2 = st2;
+      lp.acc_smem_bytes = fixed2 + st2 * stage_bytes;
+    }
+  }
   // dynamic shared memory per CTA; the single-channel mode also holds a 17.6 KB static exchange tile
   const int budget = (ctas_per_sm(mode) == 2 ? (mode == MODE_K4_OUT1 ? 90 : 110) : 200) * 1024;
   const int fixed = ((p.wimg_bytes + 127) & ~127) + 256;
@@ -1299,8 +1598,10 @@ int tc_prepare(lc_codec* h) {
 void tc_release(lc_codec* h) {
   TcPlan* P = plan_of(h);
   if (!P) return;
-  for (int i = 0; i < P->n_layers; ++i)
+  for (int i = 0; i < P->n_layers; ++i) {
     if (P->layer[i].d_w16) cudaFree(P->layer[i].d_w16);
+    if (P->layer[i].d_wimg2) cudaFree(P->layer[i].d_wimg2);
+  }
   delete P;
   h->tc_plan = nullptr;
 }

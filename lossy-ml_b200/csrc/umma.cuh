@@ -46,13 +46,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded: a pipeline bug (a barrier nobody arrives on) must not hang the GPU until the watchdog kills the
-// process.  try_wait suspends the thread for a hardware-defined time slice, so the loop turns over slowly; after
-// ~2^26 unsuccessful slices (tens of seconds, orders of magnitude beyond any legitimate wait of these kernels) the
-// thread traps, the launch fails with an error the host reports ("... barrier timed out"), and the box survives.
+// process.  try_wait suspends the thread for a hardware-defined time slice (measured: ~4 us per unsuccessful
+// slice), so 2^21 slices are ~8 s -- three orders of magnitude beyond any legitimate wait of these kernels; then
+// the thread traps, the launch fails with an error the host reports, and the box survives.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 26)) asm volatile("trap;");
+    if (++spins == (1u << 21)) asm volatile("trap;");
   }
 }
 
@@ -126,5 +126,12 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t v[4]) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> 8 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t v[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace umma

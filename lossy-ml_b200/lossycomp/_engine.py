@@ -34,7 +34,8 @@ CODE_RUN = (1, 250)             # run tokens of the code stream: runs of code 1 
 # Revision of the autoencoder kernels' arithmetic (summation order, rounding points).  The error bound only
 # holds when the decoder reproduces the compressor's reconstruction bit for bit, so blobs record the
 # revision they were written with and a build with different arithmetic refuses them.
-NUMERICS_REV = 3      # 2: bias folded into the first block of a plane; 3: residual add inside the MMA accumulation
+NUMERICS_REV = 4      # 2: bias folded into the first block of a plane; 3: residual add inside the MMA accumulation;
+# 4: the 3x3x3 layers accumulate their time taps in TMEM starting from the bias (sweep_acc_kernel)
 # chunks per convolution launch: large batches amortise kernel prologues and tails (900 chunks x 19 tiles =
 # 57.8 waves of the 296 resident CTAs); the activation workspace is 19.4 MB per chunk
 DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "1024"))

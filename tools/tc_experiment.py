@@ -1,5 +1,6 @@
-"""Timing experiments on the K3 tensor-core kernel with parts of the pipeline disabled (diagnostics)."""
-import os, sys, subprocess, json
+"""Timing experiments on the tensor-core kernels with parts of the pipeline disabled (diagnostics).
+   python tools/tc_experiment.py [label=ENV1=v1,ENV2=v2 ...]   (default: the standard ablation list)"""
+import os, sys, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
 import os, sys
@@ -18,13 +19,17 @@ eng.profile(True); eng.profile_read()
 for i in range(3):
     lat = eng.encode(x, mean, std); rec = eng.decode(lat, T, H, W)
 ms, cnt = eng.profile_read()
-print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms))
+print("RESULT", " ".join("%%.3f" %% (m / 3) for m in ms), "| sum %%.3f" %% (sum(ms) / 3))
 ''' % (ROOT, ROOT)
-for dbg, label in [(0, "full"), (16, "single issuer"), (1, "no MMA"), (8, "no copies"), (9, "no MMA no copies"),
-                   (103, "K4_OUT1 at 1 CTA/SM"), (105, "UP at 1 CTA/SM")]:
-    env = dict(os.environ, LOSSYCOMP_TC_DEBUG=str(dbg if dbg < 100 else 0))
-    if dbg >= 100:      # 10m: force mode m to one CTA per SM
-        env["LOSSYCOMP_TC_ONE_PER_SM"] = str(dbg - 100)
+configs = [("full", {}), ("no MMA", {"LOSSYCOMP_TC_DEBUG": "1"}), ("no copies", {"LOSSYCOMP_TC_DEBUG": "8"}),
+           ("no MMA no copies", {"LOSSYCOMP_TC_DEBUG": "9"}), ("old K3 kernel", {"LOSSYCOMP_NO_ACC": "1"})]
+if len(sys.argv) > 1:
+    configs = []
+    for a in sys.argv[1:]:
+        label, _, envs = a.partition("=")
+        configs.append((label, dict(e.split("=", 1) for e in envs.split(",") if e)))
+for label, envs in configs:
+    env = dict(os.environ, **envs)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
-    print(f"debug={dbg:2d} {label:28s}", line[0] if line else out.stderr[-300:])
+    print(f"{label:28s}", line[0] if line else out.stderr[-300:], flush=True)
