@@ -1460,7 +1460,11 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   const int stage_bytes = p.in_NPG * p.slab_slots * 16 + (p.skip_mma ? G * p.skip_slots * 16 : 0);
   lp.acc_smem_bytes = 0;
   lp.d_wimg2 = nullptr;
-  if (mode == MODE_K3 && (!L.res_add || p.skip_mma) && cout <= 24 && !getenv("LOSSYCOMP_NO_ACC")) {
+  // Layers with a residual input stay on sweep_tc_kernel unless LOSSYCOMP_ACC_SKIP=1: they are bound by HBM traffic
+  // (input + skip tile + output, 5.1 GB per launch on the benchmark field) rather than by the shared-memory operand
+  // fetch, and measured 4 % slower in the four-banks-per-SM form (1.17 vs 1.12 ms).
+  const bool acc_ok = !L.res_add || (p.skip_mma && getenv("LOSSYCOMP_ACC_SKIP") && atoi(getenv("LOSSYCOMP_ACC_SKIP")));
+  if (mode == MODE_K3 && acc_ok && cout <= 24 && !getenv("LOSSYCOMP_NO_ACC")) {
     // weight image of sweep_acc_kernel: per 8-channel K group, the NT time blocks twice in decreasing order
     // ([dt = NT-1 .. 0, NT-1 .. 1], 24 rows each) so that a start offset of i0 blocks rotates them onto the TMEM
     // slots; padded to the rows the widest start (NT-1 blocks in) reads with N = bank columns
