@@ -193,10 +193,17 @@ int lc_hist_codes(const int32_t* d_q, int64_t n, int esc, int bias0, int bias1, 
  * sym = v + bias if 0 <= v+bias < esc else esc; escaped values go to d_esc in order. */
 int lc_symbolize_i32(const int32_t* d_q, int64_t n, int diff, int bias, int esc, uint8_t* d_sym,
                      int32_t* d_esc, unsigned long long* d_nesc, void* d_ws, void* stream);
+/* d_esc == NULL: the stream holds no escape symbol (the container header says so): plain element-wise inverse. */
 int lc_unsymbolize_i32(const uint8_t* d_sym, int64_t n, int diff, int bias, int esc,
                        const int32_t* d_esc, int32_t* d_q, void* d_ws, void* stream);
+/* lc_symbolize_i32 for a stream whose histogram shows that no value leaves [0, esc) after the bias: no escape
+ * list, no scan, one pass at memory speed. */
+int lc_symbolize_plain_i32(const int32_t* d_q, int64_t n, int diff, int bias, uint8_t* d_sym, void* stream);
 /* Pack five 3-state mask values per byte (m0 + 3 m1 + 9 m2 + 27 m3 + 81 m4), tail zero padded. */
 int lc_pack_trits(const int8_t* d_mask, int64_t n, uint8_t* d_sym, void* stream);
+/* The same packing plus the 256-bin histogram of the packed bytes in one pass (d_hist: 256 x uint32, zeroed by the
+ * call): what the entropy stage needs to build the mask's Huffman table and to decide whether run tokens pay. */
+int lc_pack_trits_hist(const int8_t* d_mask, int64_t n, uint8_t* d_sym, uint32_t* d_hist, void* stream);
 int lc_unpack_trits(const uint8_t* d_sym, int64_t n, int8_t* d_mask, void* stream);
 
 /* Run tokens for sparse streams (large abs_error): a Huffman code cannot spend less than one bit per symbol,

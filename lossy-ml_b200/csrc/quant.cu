@@ -60,81 +60,158 @@ __device__ __forceinline__ float decoded_value(float r, float mean, float stdv, 
   return __fadd_rn(rr, val);                              // decompress.py:104
 }
 
-// CHECK: also decode every element exactly as reconstruct_kernel will and count |x - xhat| > abs_err in
-// fp64 (out3[1]) with the largest error (out3[2], bits of a non-negative double) -- the strict mode's bound
-// check without a second pass over the field.
-template <bool CHECK>
-__global__ void __launch_bounds__(kThreads)
-quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ recon, long long n,
-                float mean, float stdv, float thr, float thr2, int8_t* __restrict__ mask,
-                int32_t* __restrict__ qout, unsigned long long* __restrict__ count,
-                unsigned long long* ws, bool vec_x, bool vec_r, bool vec_m, double thr2_dec,
-                double abs_err) {
-  const int tile = take_ticket(ws);
+// CHECK: also decode every element exactly as reconstruct_kernel will and count |x - xhat| > abs_err (out3[1])
+// with the largest error (out3[2], bits of a non-negative double) -- the strict mode's bound check without a second
+// pass over the field.  The comparison is exact without fp64 on the common path: x and xhat agree to within a
+// factor of two (Sterbenz), so d = fl32(x - xhat) is the exact difference, and |d| <= abs_err holds iff
+// |d| <= chk_f, the largest float not above abs_err; only elements whose difference is not small against |x|
+// (tiny values) take the fp64 comparison.  Per-tile verdicts go to 64-way partial words in the workspace BEFORE the
+// tile publishes its scan aggregate, so the last tile -- whose look-back transitively waited for every publication --
+// can fold them into out3 (two atomics per tile on one address each were a serial chain of 12 000 L2 round trips).
+constexpr int kPart = 64;
+
+template <bool CHECK, bool FULL>
+__device__ __forceinline__ void quantize_tile(const float* __restrict__ x, int C, const float* __restrict__ recon,
+                                              long long n, float mean, float stdv, float thr, float thr2,
+                                              int8_t* __restrict__ mask, int32_t* __restrict__ qout,
+                                              unsigned long long* __restrict__ count, unsigned long long* ws,
+                                              double thr2_dec, double abs_err, float chk_f, int tile, int n_tiles,
+                                              int32_t* s_q, double* s_worst, int* s_bad) {
   const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
   float xv[kItems], rv[kItems];
-  load8_strided(x, C, i0, n, vec_x, xv);
-  load8_strided(recon, 1, i0, n, vec_r, rv);
+  if (FULL) {
+    const float4* px = reinterpret_cast<const float4*>(x + i0 * 2);
+#pragma unroll
+    for (int k = 0; k < kItems / 2; ++k) {
+      const float4 a = __ldg(px + k);
+      xv[2 * k] = a.x;
+      xv[2 * k + 1] = a.z;
+    }
+    const float4* pr = reinterpret_cast<const float4*>(recon + i0);
+#pragma unroll
+    for (int k = 0; k < kItems / 4; ++k) {
+      const float4 a = __ldg(pr + k);
+      rv[4 * k] = a.x; rv[4 * k + 1] = a.y; rv[4 * k + 2] = a.z; rv[4 * k + 3] = a.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      xv[k] = (i0 + k < n) ? __ldg(x + (i0 + k) * C) : 0.f;
+      rv[k] = (i0 + k < n) ? __ldg(recon + i0 + k) : 0.f;
+    }
+  }
   int q[kItems];
-  int m[kItems];
-  int cnt = 0;
+  unsigned long long pk = 0;
+  int cnt = 0, bad = 0;
+  float worst = 0.f;
+  double worst_d = 0.0;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    m[k] = (i0 + k < n) ? classify(xv[k], rv[k], mean, stdv, thr, thr2, q[k]) : 0;
-    cnt += (m[k] != 0);
+    const bool in = FULL || (i0 + k < n);
+    const float rr = __fadd_rn(__fmul_rn(rv[k], stdv), mean);   // compress.py:114
+    const float e = __fsub_rn(xv[k], rr);                       // compress.py:117
+    const float a = fabsf(e);
+    const bool out = in && (a > thr);                           // compress.py:121 (|e| <= thr -> 0; NaN -> 0)
+    int m = 0;
+    q[k] = 0;
+    if (out) {
+      q[k] = __float2int_rn(__fdiv_rn(a, thr2));                // compress.py:135
+      m = e > 0.f ? 1 : 2;                                      // compress.py:122-123
+    }
+    cnt += out;
+    pk |= (unsigned long long)m << (8 * k);
+    if (CHECK && in) {
+      // decompress.py:86-104: val = fl32(fl64(q) * thr2), negated where mask == 2; xhat = fl32(rr + val)
+      float val = 0.f;
+      if (out) {
+        val = (float)((double)q[k] * thr2_dec);
+        if (m == 2) val = -val;
+      }
+      const float y = __fadd_rn(rr, val);
+      const float d = fabsf(__fsub_rn(xv[k], y));
+      if (d <= 0.49f * fabsf(xv[k])) {          // x/2 <= xhat <= 2x: the float difference is exact
+        bad += !(d <= chk_f);
+        worst = fmaxf(worst, d);
+      } else {                                  // tiny values (or NaN): compare in fp64
+        const double dd = fabs((double)xv[k] - (double)y);
+        bad += !(dd <= abs_err);
+        worst_d = fmax(worst_d, dd);
+      }
+    }
   }
-  if (i0 + kItems <= n && vec_m) {
-    unsigned long long pk = 0;
-#pragma unroll
-    for (int k = 0; k < kItems; ++k) pk |= (unsigned long long)(m[k] & 0xff) << (8 * k);
+  if (FULL) {
     *reinterpret_cast<unsigned long long*>(mask + i0) = pk;
   } else {
 #pragma unroll
     for (int k = 0; k < kItems; ++k)
-      if (i0 + k < n) mask[i0 + k] = (int8_t)m[k];
-  }
-  if (CHECK) {
-    int bad = 0;
-    double worst = 0.0;
-#pragma unroll
-    for (int k = 0; k < kItems; ++k) {
-      if (i0 + k < n) {
-        const float y = decoded_value(rv[k], mean, stdv, m[k], q[k], thr2_dec);
-        const double d = fabs((double)xv[k] - (double)y);
-        if (!(d <= abs_err)) ++bad;            // NaN counts as a violation
-        worst = fmax(worst, d);
-      }
-    }
-    __shared__ double s_worst[kThreads / 32];
-    __shared__ int s_bad[kThreads / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      bad += __shfl_xor_sync(0xffffffffu, bad, o);
-      worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-    }
-    if ((threadIdx.x & 31) == 0) { s_worst[threadIdx.x >> 5] = worst; s_bad[threadIdx.x >> 5] = bad; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int w = 1; w < kThreads / 32; ++w) { worst = fmax(worst, s_worst[w]); bad += s_bad[w]; }
-      if (bad) atomicAdd(count + 1, (unsigned long long)bad);
-      if (worst > 0.0) atomicMax(count + 2, (unsigned long long)__double_as_longlong(worst));
-    }
+      if (i0 + k < n) mask[i0 + k] = (int8_t)((pk >> (8 * k)) & 0xff);
   }
   // compaction through shared memory: the tile's outliers are gathered in C order and written out as one
   // coalesced run (per-thread 4-byte stores would touch every 32-byte sector several times, each a partial write)
-  __shared__ int32_t s_q[kTile];
+  if (CHECK) {
+    double w = fmax((double)worst, worst_d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bad += __shfl_xor_sync(0xffffffffu, bad, o);
+      w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_worst[threadIdx.x >> 5] = w; s_bad[threadIdx.x >> 5] = bad; }
+  }
   int total;
-  const int texcl = block_exclusive<int>(cnt, total);
+  const int texcl = block_exclusive<int>(cnt, total);      // contains __syncthreads: s_worst / s_bad are visible after it
   {
     int o = texcl;
 #pragma unroll
     for (int k = 0; k < kItems; ++k)
-      if (m[k] != 0) s_q[o++] = q[k];
+      if ((pk >> (8 * k)) & 0xff) s_q[o++] = q[k];
+  }
+  unsigned long long* part = ws + 1 + n_tiles + 1;         // [kPart] violation counts, [kPart] worst-error bits
+  if (CHECK && threadIdx.x == 0) {
+    double w = s_worst[0];
+    int bsum = s_bad[0];
+#pragma unroll
+    for (int i = 1; i < kThreads / 32; ++i) { w = fmax(w, s_worst[i]); bsum += s_bad[i]; }
+    if (bsum) atomicAdd(part + (tile & (kPart - 1)), (unsigned long long)bsum);
+    const unsigned long long wb = (unsigned long long)__double_as_longlong(w);
+    unsigned long long* pw = part + kPart + (tile & (kPart - 1));
+    if (wb > ld_status(pw)) atomicMax(pw, wb);
+    __threadfence();                                       // before this tile's aggregate is published
   }
   const unsigned long long base = tile_prefix(ws, tile, (unsigned long long)total);   // contains a __syncthreads
   for (int i = threadIdx.x; i < total; i += kThreads) qout[base + i] = s_q[i];
-  if ((long long)(tile + 1) * kTile >= n && threadIdx.x == 0) *count = base + (unsigned long long)total;
+  if (tile == n_tiles - 1 && threadIdx.x == 0) {
+    count[0] = base + (unsigned long long)total;
+    if (CHECK) {
+      __threadfence();
+      unsigned long long b2 = 0, w2 = 0;
+      for (int i = 0; i < kPart; ++i) {
+        b2 += ld_status(part + i);
+        const unsigned long long v = ld_status(part + kPart + i);
+        w2 = v > w2 ? v : w2;
+      }
+      count[1] = b2;
+      count[2] = w2;
+    }
+  }
+}
+
+template <bool CHECK>
+__global__ void __launch_bounds__(kThreads, 4)
+quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ recon, long long n,
+                float mean, float stdv, float thr, float thr2, int8_t* __restrict__ mask,
+                int32_t* __restrict__ qout, unsigned long long* __restrict__ count,
+                unsigned long long* ws, bool vec, double thr2_dec, double abs_err, float chk_f, int n_tiles) {
+  __shared__ int32_t s_q[kTile];
+  __shared__ double s_worst[kThreads / 32];
+  __shared__ int s_bad[kThreads / 32];
+  const int tile = take_ticket(ws);
+  // block-uniform: whole tile in range, two interleaved channels, every pointer aligned for vector access
+  if (vec && (long long)(tile + 1) * kTile <= n)
+    quantize_tile<CHECK, true>(x, C, recon, n, mean, stdv, thr, thr2, mask, qout, count, ws, thr2_dec, abs_err, chk_f,
+                               tile, n_tiles, s_q, s_worst, s_bad);
+  else
+    quantize_tile<CHECK, false>(x, C, recon, n, mean, stdv, thr, thr2, mask, qout, count, ws, thr2_dec, abs_err,
+                                chk_f, tile, n_tiles, s_q, s_worst, s_bad);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -255,7 +332,15 @@ inline long long tiles_for(long long n) { return (n + kTile - 1) / kTile; }
 
 }  // namespace
 
-extern "C" size_t lc_scan_workspace_bytes(int64_t n) { return ws_bytes(tiles_for(n < 1 ? 1 : n)); }
+// status words of the look-back scan + the 2 x 64 partial verdict words of quantize_kernel<true>
+extern "C" size_t lc_scan_workspace_bytes(int64_t n) { return ws_bytes(tiles_for(n < 1 ? 1 : n)) + 2 * kPart * 8; }
+
+// largest float that does not exceed the (positive) double v
+static float float_not_above(double v) {
+  float f = (float)v;
+  if ((double)f > v) f = nextafterf(f, 0.f);
+  return f;
+}
 
 extern "C" int lc_quantize(const float* d_x, int C, const float* d_recon, int64_t n_vox, float mean,
                            float stdv, float thr, float thr2, int8_t* d_mask, int32_t* d_q,
@@ -265,9 +350,10 @@ extern "C" int lc_quantize(const float* d_x, int C, const float* d_recon, int64_
   cudaStream_t s = as_stream(stream);
   const long long nt = tiles_for(n_vox);
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
+  const bool vec = C == 2 && aligned16(d_x) && aligned16(d_recon) && aligned8(d_mask);
   quantize_kernel<false><<<(unsigned)nt, kThreads, 0, s>>>(
       d_x, C, d_recon, n_vox, mean, stdv, thr, thr2, d_mask, d_q, d_count,
-      reinterpret_cast<unsigned long long*>(d_ws), aligned16(d_x), aligned16(d_recon), aligned8(d_mask), 0.0, 0.0);
+      reinterpret_cast<unsigned long long*>(d_ws), vec, 0.0, 0.0, 0.f, (int)nt);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }
@@ -279,13 +365,13 @@ extern "C" int lc_quantize_checked(const float* d_x, int C, const float* d_recon
   LC_REQUIRE(d_x && d_recon && d_mask && d_q && d_out3 && d_ws, "null argument");
   LC_REQUIRE(n_vox > 0 && C >= 1, "empty input");
   cudaStream_t s = as_stream(stream);
+  LC_REQUIRE(abs_err > 0.0, "abs_err must be positive");
   const long long nt = tiles_for(n_vox);
-  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
-  LC_CUDA(cudaMemsetAsync(d_out3, 0, 3 * sizeof(unsigned long long), s));
+  LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt) + 2 * kPart * 8, s));
+  const bool vec = C == 2 && aligned16(d_x) && aligned16(d_recon) && aligned8(d_mask);
   quantize_kernel<true><<<(unsigned)nt, kThreads, 0, s>>>(
       d_x, C, d_recon, n_vox, mean, stdv, thr, thr2, d_mask, d_q, d_out3,
-      reinterpret_cast<unsigned long long*>(d_ws), aligned16(d_x), aligned16(d_recon), aligned8(d_mask),
-      thr2_dec, abs_err);
+      reinterpret_cast<unsigned long long*>(d_ws), vec, thr2_dec, abs_err, float_not_above(abs_err), (int)nt);
   LC_LAUNCH_CHECK();
   return LC_OK;
 }

@@ -31,6 +31,7 @@ LATENT_SEG = 256                # ... of the small latent plane, decoded on deco
 ESC = 255                       # escape symbol of the code stream
 MASK_RUN = (0, 243)             # run tokens of the mask stream: runs of byte 0, tokens 243..247
 CODE_RUN = (1, 250)             # run tokens of the code stream: runs of code 1 (undifferenced), tokens 250..254
+RLE_GATE = 0.2                  # zero-run tokens of the mask are only tried when more than this share of its bytes is zero
 # Revision of the autoencoder kernels' arithmetic (summation order, rounding points).  The error bound only
 # holds when the decoder reproduces the compressor's reconstruction bit for bit, so blobs record the
 # revision they were written with and a build with different arithmetic refuses them.
@@ -567,8 +568,7 @@ class Engine:
         q = t.empty(n, dtype=t.int32, device=self.dev)
         if n == 0:
             return q
-        esc = t.from_numpy(np.frombuffer(escb, dtype="<i4").copy()).to(self.dev) if ne else \
-            t.zeros(1, dtype=t.int32, device=self.dev)
+        esc = t.from_numpy(np.frombuffer(escb, dtype="<i4").copy()).to(self.dev) if ne else None
         ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n))
         N.check(self.lib.lc_unsymbolize_i32(_ptr(sym), n, meta["diff"], meta["bias"], meta["esc"], _ptr(esc),
                                             _ptr(q), _ptr(ws), self._stream()), "lc_unsymbolize_i32")
@@ -651,32 +651,37 @@ class Engine:
         if n_q == 0 or n_m == 0:
             ce, cm = self.pack_codes(q), self.pack_mask(mask)
             return (DevPieces([ce]), DevPieces([cm])) if device_out else (ce, cm)
-        # ---- pass 1 (async): symbols of the mask, histograms of everything
-        sym_m = t.empty((n_m + 4) // 5, dtype=t.uint8, device=self.dev)
-        N.check(self.lib.lc_pack_trits(_ptr(mask), n_m, _ptr(sym_m), self._stream()), "lc_pack_trits")
-        # histograms: [0:256] mask bytes, [256:768] the two code candidates, [768:1024] zero-run tokens of the mask,
-        # [1024:1026] their count (uint64)
-        h3 = t.empty(1026, dtype=t.int32, device=self.dev)
+        # ---- pass 1 (async): symbols of the mask + their histogram in one kernel, both code histograms in another
+        n_sym = (n_m + 4) // 5
+        sym_m = t.empty(n_sym, dtype=t.uint8, device=self.dev)
+        # histograms: [0:256] mask bytes, [256:768] the two code candidates
+        h3 = t.empty(768, dtype=t.int32, device=self.dev)
+        N.check(self.lib.lc_pack_trits_hist(_ptr(mask), n_m, _ptr(sym_m), _ptr(h3), self._stream()), "lc_pack_trits_hist")
         cand = ((0, 0), (1, 127))
         N.check(self.lib.lc_hist_codes(_ptr(q), n_q, ESC, cand[0][1], cand[1][1],
                                        C.c_void_p(h3.data_ptr() + 1024), self._stream()), "lc_hist_codes")
-        tok_m = t.empty(sym_m.numel(), dtype=t.uint8, device=self.dev)
-        ws_r = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(sym_m.numel()))
-        N.check(self.lib.lc_rle_tokens(_ptr(sym_m), sym_m.numel(), *MASK_RUN, _ptr(tok_m),
-                                       C.c_void_p(h3.data_ptr() + 4096), C.c_void_p(h3.data_ptr() + 3072), _ptr(h3),
-                                       _ptr(ws_r), self._stream()), "lc_rle_tokens")     # also fills h3[0:256]
-        self.launches += 3
-        hh = h3.cpu().numpy()                                                     # sync 1
-        n_tok = int(hh[1024:1026].view(np.int64)[0])
-        hh = hh[:1024].astype(np.int64) & 0xFFFFFFFF
-        hist_m, hists_q, hist_t = hh[:256], (hh[256:512], hh[512:768]), hh[768:1024]
-        # ---- host: tables; the mask goes out as zero-run tokens when that is shorter (sparse masks)
+        self.launches += 2
+        hh = h3.cpu().numpy().astype(np.int64) & 0xFFFFFFFF                        # sync 1
+        hist_m, hists_q = hh[:256], (hh[256:512], hh[512:768])
+        # ---- host: tables.  Sparse masks (large abs_error: most 5-trit bytes are zero) are tried as zero-run
+        # tokens too and go out that way when it is shorter; a mask with few zero bytes cannot gain from run tokens,
+        # so the tokeniser (the slowest kernel of the stage) and its host sync only run when zero bytes are frequent
         tab_m = HF.build_table_native(hist_m)
-        tab_t = HF.build_table_native(hist_t)
         mask_extra = {"kind": "mask5", "n_mask": int(n_m)}
-        if tab_t.encoded_bits(hist_t) + 16 * (n_tok // SEG) < tab_m.encoded_bits(hist_m) + 16 * (sym_m.numel() // SEG):
-            sym_m, tab_m, hist_m = tok_m[:n_tok], tab_t, hist_t
-            mask_extra.update(rle=1, n_sym=int((n_m + 4) // 5), run_sym=MASK_RUN[0], run_first=MASK_RUN[1])
+        if hist_m[MASK_RUN[0]] > RLE_GATE * n_sym and not hist_m[MASK_RUN[1]:MASK_RUN[1] + 5].any():
+            tok_m = t.empty(n_sym, dtype=t.uint8, device=self.dev)
+            ht = t.empty(258, dtype=t.int32, device=self.dev)
+            ws_r = self._buf("scan_rle", self.lib.lc_rle_workspace_bytes(n_sym))
+            N.check(self.lib.lc_rle_tokens(_ptr(sym_m), n_sym, *MASK_RUN, _ptr(tok_m), C.c_void_p(ht.data_ptr() + 1024),
+                                           _ptr(ht), None, _ptr(ws_r), self._stream()), "lc_rle_tokens")
+            self.launches += 1
+            hv = ht.cpu().numpy()                                                  # sync (sparse regime only)
+            n_tok = int(hv[256:258].view(np.int64)[0])
+            hist_t = hv[:256].astype(np.int64) & 0xFFFFFFFF
+            tab_t = HF.build_table_native(hist_t)
+            if tab_t.encoded_bits(hist_t) + 16 * (n_tok // SEG) < tab_m.encoded_bits(hist_m) + 16 * (n_sym // SEG):
+                sym_m, tab_m, hist_m = tok_m[:n_tok], tab_t, hist_t
+                mask_extra.update(rle=1, n_sym=int(n_sym), run_sym=MASK_RUN[0], run_first=MASK_RUN[1])
         tabs_q = [HF.build_table_native(h) for h in hists_q]
         costs = [tb.encoded_bits(h) + 32 * int(h[ESC]) for tb, h in zip(tabs_q, hists_q)]
         pick = 0 if costs[0] <= costs[1] else 1
@@ -684,11 +689,16 @@ class Engine:
         ne = int(hists_q[pick][ESC])
         # ---- pass 2 (async): symbolise the codes, pack both streams, copy out
         sym_q = t.empty(n_q, dtype=t.uint8, device=self.dev)
-        esc = t.empty(max(ne, 1), dtype=t.int32, device=self.dev)
-        nesc = t.zeros(1, dtype=t.int64, device=self.dev)
-        ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n_q))
-        N.check(self.lib.lc_symbolize_i32(_ptr(q), n_q, diff, bias, ESC, _ptr(sym_q), _ptr(esc), _ptr(nesc),
-                                          _ptr(ws), self._stream()), "lc_symbolize_i32")
+        esc = None
+        if ne == 0:           # the histogram shows no escapes: element-wise map at memory speed
+            N.check(self.lib.lc_symbolize_plain_i32(_ptr(q), n_q, diff, bias, _ptr(sym_q), self._stream()),
+                    "lc_symbolize_plain_i32")
+        else:
+            esc = t.empty(ne, dtype=t.int32, device=self.dev)
+            nesc = t.zeros(1, dtype=t.int64, device=self.dev)
+            ws = self._buf("scan", self.lib.lc_scan_workspace_bytes(n_q))
+            N.check(self.lib.lc_symbolize_i32(_ptr(q), n_q, diff, bias, ESC, _ptr(sym_q), _ptr(esc), _ptr(nesc),
+                                              _ptr(ws), self._stream()), "lc_symbolize_i32")
         self.launches += 1
         job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", mask_extra, device_out=device_out)
         tab_q, hist_q = tabs_q[pick], hists_q[pick]

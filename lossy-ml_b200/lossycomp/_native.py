@@ -67,7 +67,9 @@ SIGNATURES = {
     "lc_hist_codes": (_i, [_p, _i64, _i, _i, _i, _p, _p]),
     "lc_symbolize_i32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p]),
     "lc_unsymbolize_i32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p]),
+    "lc_symbolize_plain_i32": (_i, [_p, _i64, _i, _i, _p, _p]),
     "lc_pack_trits": (_i, [_p, _i64, _p, _p]),
+    "lc_pack_trits_hist": (_i, [_p, _i64, _p, _p, _p]),
     "lc_unpack_trits": (_i, [_p, _i64, _p, _p]),
     "lc_rle_workspace_bytes": (_sz, [_i64]),
     "lc_rle_tokens": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p, _p]),
