@@ -1013,8 +1013,12 @@ int tc_mode_of(const lc_codec* h, int i) {
     if (i == nl - 1 && L.cout == 1 && L.cin > 16 && L.cin <= 24 && i != h->n_enc)
       return allowed(MODE_K4_OUT1) ? MODE_K4_OUT1 : 0;
   }
-  if (L.kind == 0 && L.k == 4 && L.stride == 2 && L.cin > 16 && L.cin <= 24 && L.cout > 16 && L.cout <= 24 &&
-      L.in_t % 2 == 0 && L.in_h % 2 == 0 && L.in_w % 2 == 0 && L.in_h >= 12 && i != 0 && i != h->n_enc - 1)
+  // stride-2 conv: inner layers (24-channel group planes) and the FIRST layer of the models without a ResBlock
+  // (results/models/{basic,coords,landsea}_model: 1 / 5 / 2 input channels in one 8-channel group, written in the
+  // parity-split layout by the chunk gather)
+  if (L.kind == 0 && L.k == 4 && L.stride == 2 && L.cout > 16 && L.cout <= 24 &&
+      ((i != 0 && L.cin > 16 && L.cin <= 24) || (i == 0 && L.cin <= 8 && full)) &&
+      L.in_t % 2 == 0 && L.in_h % 2 == 0 && L.in_w % 2 == 0 && L.in_h >= 12 && i != h->n_enc - 1)
     return allowed(MODE_DOWN) ? MODE_DOWN : 0;
   if (L.kind == 1 && L.k == 4 && L.stride == 2 && L.cin > 16 && L.cin <= 24 && L.cout > 16 && L.cout <= 24 &&
       L.in_h >= 6 && i != h->n_enc && i != nl - 1)
@@ -1055,6 +1059,40 @@ __global__ void gather_blocks_kernel(const float* __restrict__ x, ChunkGeom g, i
     float* dst = out + (size_t)chunk * chunk_stride + (size_t)vox * C;
     dst[0] = __fdiv_rn(__fsub_rn(src[0], mean), stdv);
     for (int c = 1; c < C; ++c) dst[c] = src[c];
+  }
+}
+
+// K2 (stride-2 tensor-core first layer): standardise and gather into the 16-bit group-plane layout the layer reads
+// (parity-split for MODE_DOWN); one thread per voxel and channel group, channels beyond C are zero
+__global__ void gather_gp_kernel(const float* __restrict__ x, ChunkGeom g, int C, float mean, float stdv,
+                                 int chunk_begin, int n_chunks, ActView out) {
+  const long long total = (long long)n_chunks * CT * CH * CW * out.G;
+  uint4* o = reinterpret_cast<uint4*>(out.base);
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int gi = (int)(v % out.G);
+    long long r = v / out.G;
+    const int lw = (int)(r % CW);
+    r /= CW;
+    const int lh = (int)(r % CH);
+    r /= CH;
+    const int lt = (int)(r % CT);
+    const int chunk = (int)(r / CT);
+    int t0, h0, w0;
+    g.origin(chunk_begin + chunk, t0, h0, w0);
+    const float* src = x + (((size_t)(t0 + lt) * g.H + (h0 + lh)) * g.W + (w0 + lw)) * C;
+    float f[8];
+#pragma unroll
+    for (int k8 = 0; k8 < 8; ++k8) {
+      const int c = gi * 8 + k8;
+      float val = 0.f;
+      if (c < C) {
+        val = src[c];
+        if (c == 0) val = __fdiv_rn(__fsub_rn(val, mean), stdv);
+      }
+      f[k8] = val;
+    }
+    o[gp_vec_index(out, chunk, lt, lh, lw, gi)] = pack8(f, out.half);
   }
 }
 
@@ -1558,6 +1596,8 @@ int tc_prepare(lc_codec* h) {
   if (mode[0] == MODE_K4) {
     P->in_enc = make_wfold(CT, CH, CW, h->in_channels, h->layers[0].k, h->layers[0].pad_lo);
     P->wfold_k = h->layers[0].k;
+  } else if (mode[0] == MODE_DOWN) {
+    P->in_enc = make_gp(CT, CH, CW, h->in_channels, 1, LAYOUT_PARITY);
   } else {
     P->in_enc = make_f32(CT, CH, CW, h->in_channels);
   }
@@ -1672,6 +1712,8 @@ int tc_encode(lc_codec* h, const float* d_x, const ChunkGeom& g, int C, float me
   if (P->in_enc.fmt == FMT_F32) {
     gather_blocks_kernel<<<h->num_sms * 8, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count,
                                                         reinterpret_cast<float*>(in.base), in.chunk_stride);
+  } else if (P->in_enc.layout != LAYOUT_WFOLD) {
+    gather_gp_kernel<<<h->num_sms * 16, 256, 0, s>>>(d_x, g, C, mean, stdv, chunk_begin, chunk_count, in);
   } else {
     if (C == 2 && P->wfold_k == 4 && in.G == 1 && (reinterpret_cast<uintptr_t>(d_x) & 7) == 0)
       gather_wfold_c2k4_kernel<<<h->num_sms * 16, 256, 0, s>>>(d_x, g, mean, stdv, chunk_begin, chunk_count, in,

@@ -156,7 +156,10 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     if comp_data is None:
         comp_data = eng.pack_latent(latent, latent_codec, staged)                    # compress.py:142-144
     tm and tm.mark("latent_pack")
-    lshape = (latent.shape[0],) + tuple(eng.model.arch.latent_shape()[1:])
+    # compress.py:142 squeezes the latent's time axis, which is 1 after four reducing convolutions; the 3-conv
+    # variant keeps its (2, 6, 6, F) bottleneck whole
+    ls = tuple(eng.model.arch.latent_shape())
+    lshape = (latent.shape[0],) + (ls[1:] if ls[0] == 1 else ls)
     if codec == "bz2":
         dq = eng.diff(q).cpu().numpy()                                               # compress.py:147-151
         dm = eng.diff(mask).cpu().numpy()                                            # compress.py:159-163
@@ -186,10 +189,14 @@ def compress(array, err_threshold, verbose=False, *, mode="strict", codec="huff"
     assert err_threshold != 0, "The absolute error can't be 0."
     if array.dtype != np.float32:                                                    # compress.py:37-38
         array = np.array(array, dtype=np.float32)
-    assert array.ndim == 4 and array.shape[3] == 2, "Input should have 2 channels."
+    eng = Engine.get(model, precision, device)
+    # compress.py:55 for the default 2-channel model; the 1- and 5-channel models (compress_test.py:90-115) take
+    # their own channel count
+    nch = eng.model.arch.in_channels
+    assert array.ndim == 4 and array.shape[3] == nch, \
+        "Input should have 2 channels." if nch == 2 else "Input should have %d channels." % nch
     assert array.shape[0] >= 16 and array.shape[1] >= 48 and array.shape[2] >= 48, \
         "Chunks size cannot be larger than the data size."                           # dataLoader.py:447
-    eng = Engine.get(model, precision, device)
     x = _hostio.h2d(eng, array)
     slots, info = compress_device(eng, x, err_threshold, mode=mode, codec=codec, verify=verify)
     out = dumps_slots(slots)                                                         # compress.py:168
@@ -220,7 +227,8 @@ def compress_stream(arrays, err_threshold, *, mode="strict", codec="huff", preci
         assert err_threshold != 0, "The absolute error can't be 0."
         if array.dtype != np.float32:
             array = np.array(array, dtype=np.float32)
-        assert array.ndim == 4 and array.shape[3] == 2, "Input should have 2 channels."
+        assert array.ndim == 4 and array.shape[3] == eng.model.arch.in_channels, \
+            "Input should have %d channels." % eng.model.arch.in_channels
         assert array.shape[0] >= 16 and array.shape[1] >= 48 and array.shape[2] >= 48, \
             "Chunks size cannot be larger than the data size."
         src = torch.from_numpy(np.ascontiguousarray(array))

@@ -674,7 +674,8 @@ def compress_sharded_host(array_local, err_threshold, *, t0, T, precision=None, 
     eng = Engine.get(model, precision, device)
     if array_local.dtype != np.float32:
         array_local = np.array(array_local, dtype=np.float32)
-    assert array_local.ndim == 4 and array_local.shape[3] == 2, "Input should have 2 channels."
+    assert array_local.ndim == 4 and array_local.shape[3] == eng.model.arch.in_channels, \
+        "Input should have %d channels." % eng.model.arch.in_channels
     if array_local.shape[0]:
         x = _hostio.h2d(eng, array_local)
     else:
@@ -706,7 +707,8 @@ def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=Non
     def upload(slot, array):
         if array.dtype != np.float32:
             array = np.array(array, dtype=np.float32)
-        assert array.ndim == 4 and array.shape[3] == 2, "Input should have 2 channels."
+        assert array.ndim == 4 and array.shape[3] == eng.model.arch.in_channels, \
+            "Input should have %d channels." % eng.model.arch.in_channels
         src = torch.from_numpy(np.ascontiguousarray(array))
         if not src.is_pinned() or not array.shape[0]:
             bufs[slot] = _hostio.h2d(eng, array) if array.shape[0] else \

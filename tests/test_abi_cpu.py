@@ -172,3 +172,26 @@ def test_dumps_slots_loads_like_pickle():
         assert type(a) is type(b) and a == b
     assert back == pickle.loads(pickle.dumps(slots))
     pickletools.dis(blob, out=open(os.devnull, "w"))
+
+
+def test_coordinate_encodings_match_reference_values():
+    """lossycomp/encodings.py:4-23 (encode_lon / encode_lat): values produced by the reference's own functions, and
+    the channel order of dataLoader.py:284-301 for the 5-channel model's input."""
+    from lossycomp.encodings import add_coords, encode_lat, encode_lon
+    ref_lon = {-180: (0.0, 1.0), -100.5: (0.9832549075639545, 0.18223552549214767), 0: (1.2246467991473532e-16, -1.0),
+               33.25: (-0.5482932295199135, -0.8362861558477597), 180: (-2.4492935982947064e-16, 1.0)}
+    ref_lat = {-90: (0.0, 1.0), -30.25: (0.8638355052043957, 0.5037739770455263), 0: (1.0, 6.123233995736766e-17),
+               45: (0.7071067811865476, -0.7071067811865475), 90: (1.2246467991473532e-16, -1.0)}
+    for v, want in ref_lon.items():
+        assert encode_lon(v) == want
+    for v, want in ref_lat.items():
+        assert encode_lat(v) == want
+    with pytest.raises(AssertionError):
+        encode_lon(181)
+    with pytest.raises(AssertionError):
+        encode_lat(-91)
+    d = np.arange(2 * 3 * 4, dtype=np.float32).reshape(2, 3, 4)
+    x = add_coords(d, [45, 0, -30.25], [-180, -100.5, 0, 33.25])
+    assert x.shape == (2, 3, 4, 5) and x.dtype == np.float32 and np.array_equal(x[..., 0], d)
+    assert np.allclose(x[1, 2, :, 1], 0.8638355052043957) and np.allclose(x[0, 2, :, 2], 0.5037739770455263)   # sin/cos(lat)
+    assert np.allclose(x[0, :, 1, 3], 0.9832549075639545) and np.allclose(x[1, :, 1, 4], 0.18223552549214767)   # sin/cos(lon)

@@ -143,3 +143,57 @@ def test_other_architectures_run_and_match_oracle(prec, tol):
         assert np.abs(lat - lat_ref.reshape(lat.shape)).max() <= tol * scale, m.arch.name
         rec = eng.decode(dev(lat_ref.reshape(lat.shape)), *x.shape[:3]).cpu().numpy()
         assert np.abs(rec - rec_ref).max() <= tol * max(1.0, float(np.abs(rec_ref).max())), m.arch.name
+
+
+@pytest.mark.parametrize("name,cin", [("basic_model", 1), ("landsea_model", 2), ("coords_model", 5), ("3_convs", 1)])
+def test_shipped_model_variants_on_tensor_cores(name, cin):
+    """results/models/* (compress_test.py:90-115): the 1-channel, 2-channel (land-sea mask) and 5-channel (lat/lon
+    sin/cos coordinates, encodings.py:4-23 + dataLoader.py:284-301) models without a ResBlock, with their shipped
+    weights: every full-resolution layer runs on a tensor-core kernel, the autoencoder matches the oracle within the
+    fp16 tolerance, and the public API round-trips with zero bound violations (the blob names its model, so
+    decompress() finds the weights by itself)."""
+    import os
+    from lossycomp._engine import Engine
+    from lossycomp.compress import compress
+    from lossycomp.decompress import decompress
+    from lossycomp.encodings import add_coords
+    from lossycomp.models import Model
+    from oracle import lossycomp_oracle as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "lossy-ml_b200", "weights", f"{name}.lcw")
+    m = Model.load(path)
+    assert m.arch.in_channels == cin
+    g = golden_case("two_by_three")
+    x2 = g["x"]
+    T, H, W, _ = x2.shape
+    if cin == 1:
+        x = np.ascontiguousarray(x2[..., :1])
+    elif cin == 2:
+        x = x2
+    else:
+        x = add_coords(x2[..., 0], np.linspace(60.0, 36.25, H), np.linspace(-20.0, 15.75, W))
+        assert x.shape == (T, H, W, 5) and np.array_equal(x[..., 0], x2[..., 0])
+    eng = Engine(m, "fp16", 0)
+    shape = (16, 48, 48)
+    for i, L in enumerate(m.layers):
+        out = L.out_shape(shape)
+        full_res = max(shape) == 48 or max(out) == 48
+        if full_res:
+            assert eng.layer_backends()[i] != 0, (name, L.name, "runs on CUDA cores")
+        shape = out
+    mean, std = np.mean(x[..., 0]), np.std(x[..., 0])
+    xs = x.copy()
+    xs[..., 0] = (x[..., 0] - mean) / std
+    chunks = O.chunk_data(xs)
+    lat_ref = O.encoder_forward(m, chunks)
+    rec_ref = O.merge_data(O.decoder_forward(m, lat_ref), x.shape)[..., 0]
+    lat = eng.encode(dev(x), mean, std).cpu().numpy()
+    scale = max(1.0, float(np.abs(lat_ref).max()))
+    assert np.abs(lat - lat_ref.reshape(lat.shape)).max() <= TOL_VS_ORACLE["fp16"] * scale
+    rec = eng.decode(dev(lat_ref.reshape(lat.shape)), T, H, W).cpu().numpy()
+    assert np.abs(rec - rec_ref).max() <= TOL_VS_ORACLE["fp16"] * max(1.0, float(np.abs(rec_ref).max()))
+    blob = compress(x, 0.1, model=path)
+    xhat = decompress(blob)
+    assert xhat.shape == (T, H, W, 1)
+    assert np.abs(x[..., 0].astype(np.float64) - xhat[..., 0]).max() <= 0.1
+    assert len(blob) < x[..., 0].nbytes / 4

@@ -22,6 +22,10 @@ REF = "/root/reference/results"
 SOURCES = [
     ("model_2", "final_models/model_2/weigths/weight.hdf5", "final_models/model_2/model-history.pkl", 2),
     ("landsea_model", "models/landsea_model/weigths/weight.hdf5", None, 2),
+    # 1-channel and 5-channel (lat/lon sin/cos coordinates) variants of compress_test.py:90-115
+    ("basic_model", "models/basic_model/weights/weight.hdf5", None, 1),
+    ("coords_model", "models/coords_model/weigths/weight.hdf5", None, 5),
+    ("3_convs", "models/3_convs/weights/weight.hdf5", None, 1),
 ]
 
 
@@ -35,7 +39,9 @@ def convert(name, h5, hist, cin):
                     num_convs=p["num_convs"], in_channels=cin, name=name)
     else:  # results/models/*: 4 reducing convs, no res block (compress_test.py:101-115)
         k = ds["Encoder/conv3d/kernel:0"].shape
-        arch = Arch(filters=k[4], kernel=k[0], res_blocks=0, num_convs=4, in_channels=cin, name=name)
+        assert k[3] == cin, (name, k)
+        n_convs = sum(1 for key in ds if key.startswith("Encoder/") and key.endswith("kernel:0"))
+        arch = Arch(filters=k[4], kernel=k[0], res_blocks=0, num_convs=n_convs, in_channels=cin, name=name)
     layers = arch.layers()
     for L in layers:
         L.kernel = ds[f"{L.part}/{L.name}/kernel:0"]
