@@ -159,3 +159,55 @@ def test_two_devices_in_one_process(torch):
     b1 = compress(g["x"], 0.1, device=1)
     assert b0 == b1
     assert np.array_equal(decompress(b0, device=1), decompress(b1, device=0))
+
+
+def test_no_writes_outside_the_buffers(torch):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_closed.txt), so out-of-bounds WRITES are
+    hunted with guard zones instead: every output of the C-ABI path (latent, reconstruction, mask, codes, the
+    autoencoder workspace) sits between two 1 MB zones of a known pattern, on ragged shapes that exercise the tile
+    tails of every kernel; the zones must be intact afterwards and the results must equal the unguarded run."""
+    from lossycomp import _native as N
+    from lossycomp._engine import Engine
+    from oracle import lossycomp_oracle as O
+    G = 1 << 20
+
+    def guarded(nbytes, dtype):
+        raw = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[G:G + nbytes].view(dtype)
+
+    def intact(raw, nbytes):
+        return bool((raw[:G] == 0xA5).all()) and bool((raw[G + nbytes:] == 0xA5).all())
+
+    for prec in ("fp16", "fp32"):
+        eng = Engine.get(None, prec, 0)
+        lib = eng.lib
+        for shape in ((17, 49, 50), (33, 100, 97)):
+            x = torch.from_numpy(O.synthetic_field(*shape, seed=9, h0=50, w0=900)).cuda()
+            T, H, W, Cc = x.shape
+            n = eng.n_chunks(T, H, W)
+            mean, std, _ = eng.stats(x)
+            want_lat = eng.encode(x, mean, std)
+            want_rec = eng.decode(want_lat, T, H, W)
+            want_mask, want_q = eng.quantize(x, want_rec, mean, std, 0.1)
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            ws_bytes = lib.lc_ae_workspace_bytes(eng.h, n)
+            ws_raw, ws = guarded(ws_bytes, torch.uint8)
+            N.check(lib.lc_ae_workspace_init(eng.h, _ptr(ws), ws_bytes, stream), "init")
+            lat_raw, lat = guarded(want_lat.numel() * 4, torch.float32)
+            N.check(lib.lc_encode(eng.h, _ptr(x), T, H, W, Cc, float(mean), float(std), 0, n, _ptr(lat), _ptr(ws), ws_bytes,
+                                  stream), "lc_encode")
+            rec_raw, rec = guarded(T * H * W * 4, torch.float32)
+            N.check(lib.lc_decode(eng.h, _ptr(lat), T, H, W, 0, n, _ptr(rec), _ptr(ws), ws_bytes, stream), "lc_decode")
+            m_raw, mask = guarded(T * H * W, torch.int8)
+            q_raw, q = guarded(T * H * W * 4, torch.int32)
+            cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            sw = torch.empty(lib.lc_scan_workspace_bytes(T * H * W), dtype=torch.uint8, device="cuda")
+            N.check(lib.lc_quantize(_ptr(x), Cc, _ptr(rec), T * H * W, float(mean), float(std), float(np.float32(0.1)),
+                                    float(np.float32(0.2)), _ptr(mask), _ptr(q), _ptr(cnt), _ptr(sw), stream), "lc_quantize")
+            torch.cuda.synchronize()
+            assert intact(ws_raw, ws_bytes) and intact(lat_raw, want_lat.numel() * 4) and intact(rec_raw, T * H * W * 4)
+            assert intact(m_raw, T * H * W) and intact(q_raw, T * H * W * 4)
+            assert torch.equal(lat.view(want_lat.shape), want_lat) and torch.equal(rec.view(want_rec.shape), want_rec)
+            k = int(cnt.item())
+            assert k == want_q.numel() and torch.equal(q[:k], want_q) and torch.equal(mask, want_mask)
+            N.check(lib.lc_ae_workspace_release(eng.h, _ptr(ws)), "release")
