@@ -35,6 +35,22 @@ def _threads():
     return _pool
 
 
+_big = None
+
+
+def gather_pool():
+    """Copy threads of the ONE rank per node that assembles (or distributes) the blob of a time-sharded field: it moves
+    every rank's payload through host memory, so it gets up to half the node's cores instead of its 1/N share."""
+    global _big
+    if _big is None:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 2
+        _big = ThreadPoolExecutor(max_workers=max(2, min(16, cores // 2)), thread_name_prefix="lossycomp-gather")
+    return _big
+
+
 def _bounds(n, parts):
     step = -(-n // parts)
     step = -(-step // 1024) * 1024

@@ -481,7 +481,7 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
             done.synchronize()
         hv = memoryview(pin.numpy())
         rank_slots = [parse_frame(hv[o:o + n]) for o, n, _ in table if n]
-        pool = _hostio._threads()
+        pool = _hostio.gather_pool()
         jobs = []
         if pickled:
             # the pickle stream of the whole blob, cut straight out of the pinned buffer: every payload byte is
@@ -616,7 +616,7 @@ def decompress_sharded(eng, slots_or_none, *, group=None, src=0):
                 dsts.append(pv[o:o + len(p)])
                 srcs.append(np.frombuffer(p, dtype=np.uint8))
                 o += (len(p) + 15) & ~15
-        _copy_views(dsts, srcs, _hostio._threads())
+        _copy_views(dsts, srcs, _hostio.gather_pool())
         dbuf = torch.empty(max(total, 16), dtype=torch.uint8, device=dev)
         dbuf[:total].copy_(pin[:total], non_blocking=True)
         sbuf = dbuf if nccl else pin            # gloo: send from host memory

@@ -606,3 +606,35 @@ def test_fp32_engine_against_cudnn(eng, torch, model2):
     assert np.abs(rec - rec_cudnn).max() <= AE_FP32_TOL * max(1.0, float(np.abs(rec_cudnn).max()))
     # and cuDNN agrees with the CPU oracle the goldens were made with
     assert np.abs(lat_cudnn - g["latent"]).max() <= AE_FP32_TOL * scale
+
+
+def test_multi_variable_stack_abs_err_sweep():
+    """BASELINE.json configs[3]: a multi-variable stack -- the reference concatenates variables on the level axis
+    (dataLoader.py:416-424), i.e. V independent 2-channel problems -- with an abs_err sweep 1e-3 ... 1 (relative to
+    each variable's scale): temperature (K), specific humidity (kg/kg, values near zero, where the bound check's
+    fp64 branch is taken) and geopotential (m^2/s^2, large magnitudes, where the float32 guard band is widest).
+    Every element of every variable meets its bound; the compression factor grows with the bound."""
+    from lossycomp.field import compress_field, decompress_field
+    from oracle import lossycomp_oracle as O
+    base = O.synthetic_field(16, 96, 144, seed=21, h0=200, w0=400)
+    t = base[..., 0].astype(np.float64)
+    z = (t - t.mean()) / t.std()
+    variables = {"temperature": (t, 1.0), "specific_humidity": (np.clip(8e-3 + 4e-3 * z, 0, None), 4e-3),
+                 "geopotential": (5.4e4 + 2.5e3 * z, 2.5e3 / 16.0)}
+    lsm = base[0, :, :, 1]
+    for name, (v, scale) in variables.items():
+        var = np.repeat(v[:, None].astype(np.float32), 5, axis=1)              # 5 "levels", one per bound
+        errs = [scale * e for e in (1e-3, 1e-2, 0.1, 0.3, 1.0)]
+        if name == "geopotential":
+            errs[0] = max(errs[0], 0.05)                                       # float32 resolution at 5.4e4 is 0.004
+        c = compress_field(var, lsm, errs)
+        back = decompress_field(c)
+        import pickle
+        blobs = pickle.loads(c)["blobs"]
+        sizes = []
+        for l, e in enumerate(errs):
+            d = np.abs(var[:, l].astype(np.float64) - back[:, l].astype(np.float64)).max()
+            assert d <= e, (name, e, d)
+            sizes.append(len(blobs[l]))
+        assert sizes == sorted(sizes, reverse=True), (name, sizes)
+        assert sizes[-1] < var[:, 0].nbytes / 8
