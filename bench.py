@@ -384,10 +384,11 @@ def run_ours(args):
         else:
             it = LD.compress_sharded_stream([xh] * k, ABS_ERR, t0=t0r, T=T, precision=args.precision,
                                             codec=args.codec, dst=dst)
-        same = True
-        for blob in it:
-            same = same and (want is None or blob is None or blob == want)
-        return same
+        same, last = True, None
+        for blob in it:          # lengths on the fly; the last blob is compared byte for byte after the clock stops
+            same = same and (want is None or blob is None or len(blob) == len(want))
+            last = blob
+        return same, last
 
     b = e2e_step()
     barrier()
@@ -399,9 +400,10 @@ def run_ours(args):
     e2e_stream(2)
     barrier()
     t0 = time.perf_counter()
-    stream_equal = bool(e2e_stream(args.steps, want=b))
+    same_len, last_blob = e2e_stream(args.steps, want=b)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    stream_equal = bool(same_len and (b is None or last_blob == b))
     e2e = {"value": in_bytes / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": in_bytes * 2,
            "d2h_bytes_per_step": blob_len, "ms_per_step": e2e_s * 1e3,
            "api": ("lossycomp.compress.compress_stream" if world == 1 else "lossycomp.dist.compress_sharded_stream")

@@ -580,6 +580,91 @@ huff_decode_kernel(const uint32_t* __restrict__ words, long long n_words, long l
   for (int k = 0; k < rem; ++k) sym[i1 - rem + k] = (uint8_t)(pack >> (8 * k));
 }
 
+// Staged form: the bit stream of the block's kDecSegs consecutive segments is copied into shared memory first
+// (coalesced), and every thread decodes its segment from there, storing 16 symbols at a time.  The plain kernel above
+// reads the stream word by word from global memory with one word of look-ahead: a refill every ~13 symbols that
+// costs an L2 / DRAM round trip the two or three resident warps per SM cannot hide (measured: 233 ns per symbol on
+// the 5 M-symbol mask stream, 239 us for a kernel that moves 8 MB).  Blocks whose window does not fit (barely
+// compressible data) take the plain path.
+constexpr int kDecSegs = 64;
+constexpr int kDecWinWords = 24 * 1024;        // 96 KB of bit stream per block
+
+__global__ void __launch_bounds__(kDecSegs)
+huff_decode_staged_kernel(const uint32_t* __restrict__ words, long long n_words, long long n, int seg,
+                          const unsigned long long* __restrict__ seg_bits, const uint16_t* __restrict__ lut,
+                          int lut_bits, const int32_t* __restrict__ tree, uint8_t* __restrict__ sym) {
+  extern __shared__ uint32_t s_dec[];
+  uint32_t* s_words = s_dec;
+  uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_dec + kDecWinWords);
+  for (int i = threadIdx.x; i < (1 << lut_bits); i += blockDim.x) s_lut[i] = lut[i];
+  const long long nseg = (n + seg - 1) / seg;
+  const long long sg0 = (long long)blockIdx.x * kDecSegs;
+  const long long sg = sg0 + threadIdx.x;
+  // the block's window of the stream: from the first word of its first segment to the last word any of its segments
+  // can touch (the start of the next block's first segment, or the end of the buffer) plus the look-ahead words
+  long long w0 = (long long)(seg_bits[sg0] >> 5);
+  long long w1 = (sg0 + kDecSegs < nseg) ? (long long)(seg_bits[sg0 + kDecSegs] >> 5) + 3 : n_words;
+  if (w0 > n_words - 3) w0 = 0;
+  if (w1 > n_words) w1 = n_words;
+  const long long nw = w1 - w0;
+  const bool staged = nw > 0 && nw <= kDecWinWords;
+  if (staged)
+    for (long long i = threadIdx.x; i < nw; i += blockDim.x) s_words[i] = __ldg(words + w0 + i);
+  __syncthreads();
+  if (sg >= nseg) return;
+  unsigned long long pos = seg_bits[sg];
+  if ((long long)(pos >> 5) > n_words - 3 || (long long)(pos >> 5) < w0) pos = (unsigned long long)w0 << 5;
+  const uint32_t* base = staged ? s_words : words + w0;
+  const long long last = nw - 1;
+  long long wi = (long long)(pos >> 5) - w0;
+  if (wi > last - 2) wi = last - 2 < 0 ? 0 : last - 2;
+  unsigned long long buf = ((unsigned long long)__byte_perm(base[wi], 0, 0x0123) << 32) | __byte_perm(base[wi + 1], 0, 0x0123);
+  wi += 2;
+  uint32_t ahead = base[wi];
+  int used = (int)(pos & 31);
+  const long long i0 = sg * seg;
+  const long long i1 = (i0 + seg < n) ? i0 + seg : n;
+  const bool one_symbol = (tree[0] < 0 && tree[1] < 0 && tree[0] == tree[1]);
+  unsigned long long plo = 0, phi = 0;                  // 16 decoded symbols, stored as one 16-byte vector
+  for (long long i = i0; i < i1; ++i) {
+    const unsigned long long win = buf << used;          // >= 33 valid bits at the top
+    const uint16_t e = s_lut[win >> (64 - lut_bits)];
+    int l = e >> 8;
+    int sy = e & 0xff;
+    if (l == 0) {   // code longer than lut_bits (or the empty code of a one-symbol alphabet)
+      if (one_symbol) {
+        sy = ~tree[0];
+      } else {
+        int node = 0;
+        while (l < 32) {
+          const int bit = (int)((win >> (63 - l)) & 1);
+          ++l;
+          const int nx = tree[2 * node + bit];
+          if (nx < 0) { sy = ~nx; break; }
+          node = nx;
+        }
+      }
+    }
+    used += l;
+    if (used >= 32) {
+      buf = (buf << 32) | __byte_perm(ahead, 0, 0x0123);
+      used -= 32;
+      wi = (wi < last) ? wi + 1 : wi;                    // saturates: a damaged stream decodes to garbage, never faults
+      ahead = base[wi];
+    }
+    const int k = (int)(i - i0) & 15;
+    const unsigned long long v = (unsigned long long)sy << (8 * (k & 7));
+    if (k < 8) plo |= v; else phi |= v;
+    if (k == 15) {
+      *reinterpret_cast<uint4*>(sym + i - 15) =
+          make_uint4((uint32_t)plo, (uint32_t)(plo >> 32), (uint32_t)phi, (uint32_t)(phi >> 32));
+      plo = phi = 0;
+    }
+  }
+  const int rem = (int)(i1 - i0) & 15;
+  for (int k = 0; k < rem; ++k) sym[i1 - rem + k] = (uint8_t)((k < 8 ? plo : phi) >> (8 * (k & 7)));
+}
+
 inline unsigned grid_for(long long n, int per_block) {
   long long b = (n + per_block - 1) / per_block;
   if (b > 148 * 32) b = 148 * 32;
@@ -769,6 +854,20 @@ extern "C" int lc_huff_decode(const uint8_t* d_bits, int64_t n_bytes, int64_t n,
   // zero padded to 8 more bytes; pass the conservative size bound
   LC_REQUIRE((reinterpret_cast<uintptr_t>(d_bits) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_sym) & 3) == 0 &&
                  seg % 4 == 0, "bit stream and symbol buffers must be 4-byte aligned");
+  if (seg % 16 == 0 && (reinterpret_cast<uintptr_t>(d_sym) & 15) == 0 && !getenv("LOSSYCOMP_PLAIN_DECODE")) {
+    const size_t smem = (size_t)kDecWinWords * 4 + (size_t)(1 << lut_bits) * 2;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    LC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      LC_CUDA(cudaFuncSetAttribute(huff_decode_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    huff_decode_staged_kernel<<<(unsigned)((nseg + kDecSegs - 1) / kDecSegs), kDecSegs, smem, as_stream(stream)>>>(
+        reinterpret_cast<const uint32_t*>(d_bits), n_bytes / 4, n, seg, d_seg_bits, d_lut, lut_bits, d_tree, d_sym);
+    LC_LAUNCH_CHECK();
+    return LC_OK;
+  }
   huff_decode_kernel<<<(unsigned)((nseg + 127) / 128), 128, (size_t)(1 << lut_bits) * 2,
                        as_stream(stream)>>>(reinterpret_cast<const uint32_t*>(d_bits), n_bytes / 4, n, seg, d_seg_bits,
                                             d_lut, lut_bits, d_tree, d_sym);

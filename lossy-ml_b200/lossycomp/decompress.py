@@ -43,12 +43,29 @@ def decompress_device(eng: Engine, slots, *, inject=None, batch=None, rows=None)
     else:
         recon = eng.decode(latent, T, H, W, batch=batch)                             # decompress.py:66-72
     n = T_all * H * W
+    huff_mask = comp_mask[:4] in (HUFF_MAGIC, MULTI_MAGIC)
+    side_done = None
+    if huff_mask and comp_error[:4] in (HUFF_MAGIC, MULTI_MAGIC):
+        # The two Huffman streams are independent and each decode kernel occupies a fraction of the GPU (one thread
+        # per 1024-symbol segment, a serial chain per thread): the mask goes to the side stream once the decoder's
+        # convolutions are through (beside them it would cost the convolution CTAs their residency), the codes stay
+        # on the main stream, and reconstruct() waits for both.
+        main = torch.cuda.current_stream(eng.dev)
+        side = eng.side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            mask = eng.unpack_mask(comp_mask)
+            side_done = torch.cuda.Event()
+            side_done.record(side)
+        mask.record_stream(main)
     if comp_error[:4] in (HUFF_MAGIC, MULTI_MAGIC):
         q = eng.unpack_codes(comp_error)
     else:                                                                            # decompress.py:75-78
         dq = np.frombuffer(bz2.decompress(comp_error), dtype=np.int32).reshape(error_shape)
         q = eng.cumsum(torch.from_numpy(dq.copy()).to(eng.dev))
-    if comp_mask[:4] in (HUFF_MAGIC, MULTI_MAGIC):
+    if side_done is not None:
+        torch.cuda.current_stream(eng.dev).wait_event(side_done)
+    elif huff_mask:
         mask = eng.unpack_mask(comp_mask)
     else:                                                                            # decompress.py:81-84
         dm = np.frombuffer(bz2.decompress(comp_mask), dtype=np.int8).reshape((n,))
