@@ -1230,10 +1230,13 @@ int launch_acc_variant(const SweepParams& p, int grid, int smem, cudaStream_t s)
 }
 
 int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStream_t s) {
-  if (lp.acc_smem_bytes > 0 && lp.backend == MODE_K3) {
+  if (lp.acc_smem_bytes > 0 && (lp.backend == MODE_K3 || lp.backend == MODE_K4)) {
     int grid = h->num_sms < p.n_items ? h->num_sms : p.n_items;
     int rc;
-    if (p.half) rc = p.relu ? launch_acc_variant<3, 1, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<3, 1, 0>(p, grid, lp.acc_smem_bytes, s);
+    if (lp.backend == MODE_K4) {
+      if (p.half) rc = p.relu ? launch_acc_variant<4, 1, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<4, 1, 0>(p, grid, lp.acc_smem_bytes, s);
+      else rc = p.relu ? launch_acc_variant<4, 0, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<4, 0, 0>(p, grid, lp.acc_smem_bytes, s);
+    } else if (p.half) rc = p.relu ? launch_acc_variant<3, 1, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<3, 1, 0>(p, grid, lp.acc_smem_bytes, s);
     else rc = p.relu ? launch_acc_variant<3, 0, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<3, 0, 0>(p, grid, lp.acc_smem_bytes, s);
     if (rc != LC_OK) return rc;
     LC_LAUNCH_CHECK();
@@ -1502,7 +1505,8 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   // (input + skip tile + output, 5.1 GB per launch on the benchmark field) rather than by the shared-memory operand
   // fetch, and measured 4 % slower in the four-banks-per-SM form (1.17 vs 1.12 ms).
   const bool acc_ok = !L.res_add || (p.skip_mma && getenv("LOSSYCOMP_ACC_SKIP") && atoi(getenv("LOSSYCOMP_ACC_SKIP")));
-  if (mode == MODE_K3 && acc_ok && cout <= 24 && !getenv("LOSSYCOMP_NO_ACC")) {
+  const bool acc_mode = mode == MODE_K3 || (mode == MODE_K4 && L.pad_lo == 1 && !getenv("LOSSYCOMP_NO_ACC_K4"));
+  if (acc_mode && acc_ok && cout <= 24 && !getenv("LOSSYCOMP_NO_ACC")) {
     // weight image of sweep_acc_kernel: per 8-channel K group, the NT time blocks twice in decreasing order
     // ([dt = NT-1 .. 0, NT-1 .. 1], 24 rows each) so that a start offset of i0 blocks rotates them onto the TMEM
     // slots; padded to the rows the widest start (NT-1 blocks in) reads with N = bank columns
@@ -1521,9 +1525,14 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
             continue;
           }
           for (int k8 = 0; k8 < 8; ++k8) {
-            const int ci = kg.ci0 + k8;
+            int ci = kg.ci0 + k8, kw = kg.tap_w;
+            if (mode == MODE_K4) {   // w-folded input: pseudo-channel -> (dw, ci)
+              kw = ci / cin;
+              ci -= kw * cin;
+              if (kw >= k) continue;
+            }
             if (ci >= cin) continue;
-            dst[k8] = to_h16_host(w16[((size_t)((kt * k + kg.tap_h) * k + kg.tap_w) * cin + ci) * cout + co], half);
+            dst[k8] = to_h16_host(w16[((size_t)((kt * k + kg.tap_h) * k + kw) * cin + ci) * cout + co], half);
           }
         }
       }
