@@ -584,10 +584,11 @@ class Engine:
         return b
 
     def _launch_pack(self, sym, table: HF.Table, bits: int, tag: str, extra: dict, tail_len: int = 0, seg: int = SEG,
-                     device_out: bool = False):
+                     device_out: bool = False, defer: bool = False):
         """Enqueue the Huffman packing of `sym` (no sync) and allocate the finished 'LCH1' container as one
         uninitialised bytes object: everything but the segment lengths, the payload and the tail is known now.
-        With device_out the payload stays on the device (no bytes object; _finish_pack returns DevPieces)."""
+        With device_out the payload stays on the device (no bytes object; _finish_pack returns DevPieces).  With
+        defer the caller places the container inside a larger buffer (_place_pack) before collecting it."""
         t = self.torch
         n = sym.numel()
         nseg = (n + seg - 1) // seg
@@ -613,10 +614,18 @@ class Engine:
         if device_out:
             return dict(nseg=nseg, bits=bits, nbytes=nbytes, h_seg=h_seg, head=head, out=out, keep=(segb, d_tab),
                         device_out=True)
-        blob, view = _new_bytes(pay_off + nbytes + tail_len)
-        view[:len(head)] = np.frombuffer(head, dtype=np.uint8)
-        return dict(nseg=nseg, bits=bits, nbytes=nbytes, h_seg=h_seg, head_len=len(head), pay_off=pay_off, blob=blob,
-                    view=view, out=out, keep=(segb, d_tab))
+        job = dict(nseg=nseg, bits=bits, nbytes=nbytes, h_seg=h_seg, head_len=len(head), pay_off=pay_off, blob=None,
+                   view=None, out=out, keep=(segb, d_tab), head=head, size=pay_off + nbytes + tail_len)
+        if not defer:
+            blob, view = _new_bytes(job["size"])
+            self._place_pack(job, view, blob)
+        return job
+
+    @staticmethod
+    def _place_pack(job, view, blob=None):
+        """Give a deferred container its place: `view` is the uint8 window (job["size"] bytes) it is written to."""
+        job["view"], job["blob"] = view, blob
+        view[:job["head_len"]] = np.frombuffer(job.pop("head"), dtype=np.uint8)
 
     def _collect_pack(self, job):
         """Copy the packed payload from the device straight into its place in the container (blocking)."""
@@ -642,10 +651,13 @@ class Engine:
         job.clear()
         return blob
 
-    def pack_streams(self, mask, q, device_out: bool = False):
+    def pack_streams(self, mask, q, device_out: bool = False, frame=None):
         """Entropy-code the mask and the code stream together -> (comp_error, comp_mask).
         Same containers as pack_codes()/pack_mask(); the two pipelines share their host syncs.
-        With device_out the results are DevPieces whose Huffman payloads stay in device memory."""
+        With device_out the results are DevPieces whose Huffman payloads stay in device memory.
+        frame = (bytes before, bytes after): the two containers are written as consecutive pickle byte strings
+        (BINBYTES8) between them, straight into ONE bytes object -- the finished blob of compress() -- so the payloads
+        cross PCIe into their final place and nothing is copied afterwards; the return value is then that blob."""
         t = self.torch
         n_m, n_q = mask.numel(), q.numel()
         if n_q == 0 or n_m == 0:
@@ -700,7 +712,9 @@ class Engine:
             N.check(self.lib.lc_symbolize_i32(_ptr(q), n_q, diff, bias, ESC, _ptr(sym_q), _ptr(esc), _ptr(nesc),
                                               _ptr(ws), self._stream()), "lc_symbolize_i32")
         self.launches += 1
-        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", mask_extra, device_out=device_out)
+        framed = frame is not None and not device_out
+        job_m = self._launch_pack(sym_m, tab_m, tab_m.encoded_bits(hist_m), "m", mask_extra, device_out=device_out,
+                                  defer=framed)
         tab_q, hist_q = tabs_q[pick], hists_q[pick]
         code_extra = {"kind": "codes", "diff": diff, "bias": bias, "esc": ESC, "n_esc": ne}
         # Large abs_error: nearly every code is 1 and the one-bit floor of the Huffman code dominates the slot.
@@ -721,7 +735,24 @@ class Engine:
                 sym_q, tab_q, hist_q = tok_q[:n_tok], tab_t, hist_t
                 code_extra.update(rle=1, n_sym=int(n_q), run_sym=CODE_RUN[0], run_first=CODE_RUN[1])
         job_q = self._launch_pack(sym_q, tab_q, tab_q.encoded_bits(hist_q), "q", code_extra, tail_len=4 * ne,
-                                  device_out=device_out)
+                                  device_out=device_out, defer=framed)
+        final = None
+        if framed:
+            before, after = frame
+            hq = b"\x8e" + struct.pack("<Q", job_q["size"])            # pickle BINBYTES8: slot 6, then slot 7
+            hm = b"\x8e" + struct.pack("<Q", job_m["size"])
+            final, fv = _new_bytes(len(before) + len(hq) + job_q["size"] + len(hm) + job_m["size"] + len(after))
+            o = 0
+            for piece in (before, hq):
+                fv[o:o + len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+                o += len(piece)
+            self._place_pack(job_q, fv[o:o + job_q["size"]])
+            o += job_q["size"]
+            fv[o:o + len(hm)] = np.frombuffer(hm, dtype=np.uint8)
+            o += len(hm)
+            self._place_pack(job_m, fv[o:o + job_m["size"]])
+            o += job_m["size"]
+            fv[o:] = np.frombuffer(after, dtype=np.uint8)
         h_esc = None
         if ne:
             h_esc = self._pinned("esc", 4 * ne)
@@ -731,8 +762,11 @@ class Engine:
         self._collect_pack(job_q)
         self.torch.cuda.current_stream(self.dev).synchronize()                    # sync 2
         escb = bytes(memoryview(h_esc.numpy())[:4 * ne]) if ne else b""
+        sizes = (job_q["size"], job_m["size"]) if framed else None
         comp_mask = self._finish_pack(job_m)
         comp_error = self._finish_pack(job_q, tail=escb)
+        if framed:
+            return final, sizes
         return comp_error, comp_mask
 
     # -- latent slot (compress.py:142-144; fpzip is replaced by a tagged container) -----

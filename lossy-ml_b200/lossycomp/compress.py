@@ -57,6 +57,17 @@ def pickle_parts(slots) -> list:
     return parts
 
 
+def pickle_frame(slots) -> tuple:
+    """(bytes before slot 6, bytes after slot 7) of the blob's pickle stream, given the slot list with slots 6 and 7
+    still to come: Engine.pack_streams(frame=...) writes the two entropy containers between them, straight into the
+    finished blob."""
+    parts = pickle_parts(list(slots[:6]) + [b"", b""] + list(slots[8:]))
+    # the two empty placeholders are each [opcode, length, payload]; cut them out
+    i = next(k for k in range(len(parts) - 5) if parts[k] == b"\x8e" and parts[k + 2] == b"" and parts[k + 3] == b"\x8e"
+             and parts[k + 5] == b"")
+    return b"".join(bytes(p) for p in parts[:i]), b"".join(bytes(p) for p in parts[i + 6:])
+
+
 def dumps_slots(slots) -> bytes:
     """pickle.dumps(slots) for the 9-slot list (compress.py:168), written with a single copy of the payloads;
     pickle.loads() of the result is the same list, which is all decompress.py:54 relies on."""
@@ -88,12 +99,14 @@ class _StageTimer:
 
 def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff", verify=None,
                     inject=None, latent_codec=None, batch=None, return_parts=False, timing=False,
-                    device_out=False, guard_scale=1.0, retry=True):
+                    device_out=False, guard_scale=1.0, retry=True, as_blob=False):
     """x: torch float32 CUDA tensor (T,H,W,2).  Returns (slots list, info dict).
     device_out: slots 0/6/7 come back as _engine.DevPieces whose payloads are still in device memory (the
     multi-GPU path sends them over NCCL from there).  guard_scale multiplies strict mode's guard band; retry=False
     reports a bound violation in info["violations"] instead of widening the band and quantising again
-    (dist.compress_sharded makes that decision for all ranks together)."""
+    (dist.compress_sharded makes that decision for all ranks together).  as_blob: return the finished blob (bytes,
+    what compress() returns) in place of the slot list -- the entropy payloads are then copied from the device straight
+    into it."""
     assert err_threshold != 0, "The absolute error can't be 0."                      # compress.py:34
     assert x.dim() == 4 and x.shape[3] == eng.model.arch.in_channels, \
         "Input should have %d channels." % eng.model.arch.in_channels                # compress.py:55
@@ -166,7 +179,13 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         comp_error = bz2.compress(dq.tobytes(), 9)                                   # compress.py:156
         comp_mask = bz2.compress(dm.tobytes(), 9)                                    # compress.py:166
     elif codec == "huff":
-        comp_error, comp_mask = eng.pack_streams(mask, q, device_out=device_out)
+        blob = None
+        if as_blob and not device_out and n_out and mask.numel():
+            head = [comp_data, lshape, (T, H, W, int(x.shape[3])), (n_out,), mean, std, None, None, thr2]
+            blob, (ne_b, nm_b) = eng.pack_streams(mask, q, frame=pickle_frame(head))
+            comp_error, comp_mask = range(ne_b), range(nm_b)           # only their lengths are reported below
+        else:
+            comp_error, comp_mask = eng.pack_streams(mask, q, device_out=device_out)
         tm and tm.mark("pack_streams")
     else:
         raise ValueError("codec must be 'huff' or 'bz2'")
@@ -177,6 +196,8 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         info["timing_ms"] = tm.ms
     if return_parts:
         info.update(latent=latent, recon_std=recon, mask=mask, q=q)
+    if as_blob:
+        return (blob if codec == "huff" and blob is not None else dumps_slots(slots)), info
     return slots, info
 
 
@@ -198,8 +219,7 @@ def compress(array, err_threshold, verbose=False, *, mode="strict", codec="huff"
     assert array.shape[0] >= 16 and array.shape[1] >= 48 and array.shape[2] >= 48, \
         "Chunks size cannot be larger than the data size."                           # dataLoader.py:447
     x = _hostio.h2d(eng, array)
-    slots, info = compress_device(eng, x, err_threshold, mode=mode, codec=codec, verify=verify)
-    out = dumps_slots(slots)                                                         # compress.py:168
+    out, info = compress_device(eng, x, err_threshold, mode=mode, codec=codec, verify=verify, as_blob=True)   # compress.py:168
     if verbose:
         tot = info["latent_bytes"] + info["error_bytes"] + info["mask_bytes"]
         print("Latent space (%):", info["latent_bytes"] / tot)
@@ -261,10 +281,10 @@ def compress_stream(arrays, err_threshold, *, mode="strict", codec="huff", preci
             more = True
         except StopIteration:
             more = False
-        slots, _ = compress_device(eng, bufs[slot], err_threshold, mode=mode, codec=codec)
+        blob, _ = compress_device(eng, bufs[slot], err_threshold, mode=mode, codec=codec, as_blob=True)
         freed[slot] = torch.cuda.Event()
         freed[slot].record(main)
-        yield dumps_slots(slots)
+        yield blob
         if not more:
             return
         k += 1
