@@ -69,6 +69,14 @@ __device__ __forceinline__ float decoded_value(float r, float mean, float stdv, 
 // tile publishes its scan aggregate, so the last tile -- whose look-back transitively waited for every publication --
 // can fold them into out3 (two atomics per tile on one address each were a serial chain of 12 000 L2 round trips).
 constexpr int kPart = 64;
+// elements per thread of the quantiser.  16 (4096-element tiles: half the look-backs and block barriers per
+// element, 128 registers) was measured against 8 on the benchmark field: 0.255 / 0.291 ms (plain / checked) against
+// 0.242 / 0.276 ms -- the kernel is not paced by its barriers alone
+#ifndef LC_QITEMS
+#define LC_QITEMS 8
+#endif
+constexpr int kQItems = LC_QITEMS;
+constexpr int kQTile = kThreads * kQItems;
 
 template <bool CHECK, bool FULL>
 __device__ __forceinline__ void quantize_tile(const float* __restrict__ x, int C, const float* __restrict__ recon,
@@ -77,36 +85,36 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ x, int C
                                               unsigned long long* __restrict__ count, unsigned long long* ws,
                                               double thr2_dec, double abs_err, float chk_f, int tile, int n_tiles,
                                               int32_t* s_q, double* s_worst, int* s_bad) {
-  const long long i0 = (long long)tile * kTile + (long long)threadIdx.x * kItems;
-  float xv[kItems], rv[kItems];
+  const long long i0 = (long long)tile * kQTile + (long long)threadIdx.x * kQItems;
+  float xv[kQItems], rv[kQItems];
   if (FULL) {
     const float4* px = reinterpret_cast<const float4*>(x + i0 * 2);
 #pragma unroll
-    for (int k = 0; k < kItems / 2; ++k) {
+    for (int k = 0; k < kQItems / 2; ++k) {
       const float4 a = __ldg(px + k);
       xv[2 * k] = a.x;
       xv[2 * k + 1] = a.z;
     }
     const float4* pr = reinterpret_cast<const float4*>(recon + i0);
 #pragma unroll
-    for (int k = 0; k < kItems / 4; ++k) {
+    for (int k = 0; k < kQItems / 4; ++k) {
       const float4 a = __ldg(pr + k);
       rv[4 * k] = a.x; rv[4 * k + 1] = a.y; rv[4 * k + 2] = a.z; rv[4 * k + 3] = a.w;
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) {
+    for (int k = 0; k < kQItems; ++k) {
       xv[k] = (i0 + k < n) ? __ldg(x + (i0 + k) * C) : 0.f;
       rv[k] = (i0 + k < n) ? __ldg(recon + i0 + k) : 0.f;
     }
   }
-  int q[kItems];
-  unsigned long long pk = 0;
+  int q[kQItems];
+  unsigned long long pk[kQItems / 8] = {};
   int cnt = 0, bad = 0;
   float worst = 0.f;
   double worst_d = 0.0;
 #pragma unroll
-  for (int k = 0; k < kItems; ++k) {
+  for (int k = 0; k < kQItems; ++k) {
     const bool in = FULL || (i0 + k < n);
     const float rr = __fadd_rn(__fmul_rn(rv[k], stdv), mean);   // compress.py:114
     const float e = __fsub_rn(xv[k], rr);                       // compress.py:117
@@ -119,7 +127,7 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ x, int C
       m = e > 0.f ? 1 : 2;                                      // compress.py:122-123
     }
     cnt += out;
-    pk |= (unsigned long long)m << (8 * k);
+    pk[k >> 3] |= (unsigned long long)m << (8 * (k & 7));
     if (CHECK && in) {
       // decompress.py:86-104: val = fl32(fl64(q) * thr2), negated where mask == 2; xhat = fl32(rr + val)
       float val = 0.f;
@@ -140,11 +148,12 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ x, int C
     }
   }
   if (FULL) {
-    *reinterpret_cast<unsigned long long*>(mask + i0) = pk;
+#pragma unroll
+    for (int j = 0; j < kQItems / 8; ++j) reinterpret_cast<unsigned long long*>(mask + i0)[j] = pk[j];
   } else {
 #pragma unroll
-    for (int k = 0; k < kItems; ++k)
-      if (i0 + k < n) mask[i0 + k] = (int8_t)((pk >> (8 * k)) & 0xff);
+    for (int k = 0; k < kQItems; ++k)
+      if (i0 + k < n) mask[i0 + k] = (int8_t)((pk[k >> 3] >> (8 * (k & 7))) & 0xff);
   }
   // compaction through shared memory: the tile's outliers are gathered in C order and written out as one
   // coalesced run (per-thread 4-byte stores would touch every 32-byte sector several times, each a partial write)
@@ -162,8 +171,8 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ x, int C
   {
     int o = texcl;
 #pragma unroll
-    for (int k = 0; k < kItems; ++k)
-      if ((pk >> (8 * k)) & 0xff) s_q[o++] = q[k];
+    for (int k = 0; k < kQItems; ++k)
+      if ((pk[k >> 3] >> (8 * (k & 7))) & 0xff) s_q[o++] = q[k];
   }
   unsigned long long* part = ws + 1 + n_tiles + 1;         // [kPart] violation counts, [kPart] worst-error bits
   if (CHECK && threadIdx.x == 0) {
@@ -196,17 +205,17 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ x, int C
 }
 
 template <bool CHECK>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, (kQItems > 8) ? 2 : 4)
 quantize_kernel(const float* __restrict__ x, int C, const float* __restrict__ recon, long long n,
                 float mean, float stdv, float thr, float thr2, int8_t* __restrict__ mask,
                 int32_t* __restrict__ qout, unsigned long long* __restrict__ count,
                 unsigned long long* ws, bool vec, double thr2_dec, double abs_err, float chk_f, int n_tiles) {
-  __shared__ int32_t s_q[kTile];
+  __shared__ int32_t s_q[kQTile];
   __shared__ double s_worst[kThreads / 32];
   __shared__ int s_bad[kThreads / 32];
   const int tile = take_ticket(ws);
   // block-uniform: whole tile in range, two interleaved channels, every pointer aligned for vector access
-  if (vec && (long long)(tile + 1) * kTile <= n)
+  if (vec && (long long)(tile + 1) * kQTile <= n)
     quantize_tile<CHECK, true>(x, C, recon, n, mean, stdv, thr, thr2, mask, qout, count, ws, thr2_dec, abs_err, chk_f,
                                tile, n_tiles, s_q, s_worst, s_bad);
   else
@@ -348,7 +357,7 @@ extern "C" int lc_quantize(const float* d_x, int C, const float* d_recon, int64_
   LC_REQUIRE(d_x && d_recon && d_mask && d_q && d_count && d_ws, "null argument");
   LC_REQUIRE(n_vox > 0 && C >= 1, "empty input");
   cudaStream_t s = as_stream(stream);
-  const long long nt = tiles_for(n_vox);
+  const long long nt = (n_vox + kQTile - 1) / kQTile;
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt), s));
   const bool vec = C == 2 && aligned16(d_x) && aligned16(d_recon) && aligned8(d_mask);
   quantize_kernel<false><<<(unsigned)nt, kThreads, 0, s>>>(
@@ -366,7 +375,7 @@ extern "C" int lc_quantize_checked(const float* d_x, int C, const float* d_recon
   LC_REQUIRE(n_vox > 0 && C >= 1, "empty input");
   cudaStream_t s = as_stream(stream);
   LC_REQUIRE(abs_err > 0.0, "abs_err must be positive");
-  const long long nt = tiles_for(n_vox);
+  const long long nt = (n_vox + kQTile - 1) / kQTile;
   LC_CUDA(cudaMemsetAsync(d_ws, 0, ws_bytes(nt) + 2 * kPart * 8, s));
   const bool vec = C == 2 && aligned16(d_x) && aligned16(d_recon) && aligned8(d_mask);
   quantize_kernel<true><<<(unsigned)nt, kThreads, 0, s>>>(
