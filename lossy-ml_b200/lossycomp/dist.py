@@ -252,7 +252,9 @@ def gather_tensors(frame, meta: int = 0, dst: int = 0, group=None, veto=None):
     sizes = [(a_, b_) for a_, b_, _ in sizes]
     if rank != dst:
         if frame.numel():
-            dist.send(frame, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+            peer = dist.get_global_rank(group, dst) if group is not None else dst
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, frame, peer, group)]):
+                req.wait()
         return None
     offs, o = [], 0
     for ln, _ in sizes:
