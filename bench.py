@@ -57,6 +57,8 @@ def parse():
                     help="N > 1: the field has N times this many hours (32 = two whole time chunks per rank)")
     ap.add_argument("--dst", type=int, default=None, help="N > 1: rank that receives the blob (default: the last)")
     ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the single-GPU comparison")
+    ap.add_argument("--lanes", type=int, default=None,
+                    help="fields in flight per GPU (lossycomp.lanes; default LOSSYCOMP_LANES or 2; 1 = one after the other)")
     return ap.parse_args()
 
 
@@ -219,7 +221,7 @@ def run_ours(args):
     from lossycomp import dist as LD
     from lossycomp._engine import Engine
     from lossycomp.compress import compress, compress_device, compress_stream
-    from lossycomp.decompress import decompress, decompress_device
+    from lossycomp.decompress import decompress, decompress_device, decompress_stream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -258,55 +260,78 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         return float(tms.item())
 
-    def step():
+    # Fields in flight: consecutive steps run in alternating lanes (engine + stream + host thread each), so the
+    # kernels of one field fill the host round trips of the other.  Lane 0 is `eng`.
+    from lossycomp.lanes import LaneSet, n_lanes
+    lanes = LaneSet.get(None, args.precision, local, n_lanes(args.lanes))
+    if world > 1:
+        lanes.groups()
+
+    def job(lane):
         if world == 1:
-            return compress_device(eng, x, ABS_ERR, mode="strict", codec=args.codec)
+            return compress_device(lane.eng, x, ABS_ERR, mode="strict", codec=args.codec)
         # rank dst gets a PendingBlob: the gathered blob's device->host copy (copy stream) and its assembly (host
-        # thread) overlap the next step's kernels; the timed region ends when every step's blob is complete
-        return LD.compress_sharded(eng, x, ABS_ERR, t0=t0r, T=T, mode="strict", codec=args.codec, dst=dst, wait=False)
+        # thread) overlap the following kernels; the timed region ends when every step's blob is complete
+        out = LD.compress_sharded(lane.eng, x, ABS_ERR, t0=t0r, T=T, mode="strict", codec=args.codec,
+                                  group=lane.group, dst=dst, wait=False)
+        torch.cuda.current_stream(lane.eng.dev).synchronize()      # this rank's share of the field is done
+        return out
 
-    def finish(out):
-        return out.result() if hasattr(out, "result") else out
+    def step():
+        return lanes.submit(job)
 
-    for _ in range(args.warmup):
-        slots, info = step()
-        slots = finish(slots)
-    eng.profile(True)
-    eng.profile_read()
+    def finish(fut):
+        out, info = fut.result()
+        return (out.result() if hasattr(out, "result") else out), info
+
+    def run_steps(k):
+        """k steps, at most one per lane in flight; -> (slots, info) of the last one.  Results are not hoarded:
+        step j's blob is collected (and dropped) as soon as step j + lanes has been submitted."""
+        inflight, last = [], (None, None)
+        for _ in range(k):
+            inflight.append(step())
+            while len(inflight) > len(lanes):
+                last = finish(inflight.pop(0))
+        while inflight:
+            last = finish(inflight.pop(0))
+        return last
+
+    for _ in range(len(lanes)):          # every lane once on its own (allocations, communicators), then together
+        slots, info = finish(step())
+    slots, info = run_steps(max(args.warmup, 1))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     barrier()
-    slots, info = step()                 # one more untimed step: the GPUs idled while the clock sampler started
-    slots = finish(slots)
-    eng.profile_read()
+    slots, info = run_steps(len(lanes))  # untimed again: the GPUs idled while the clock sampler started
     barrier()
-    launches0 = eng.launches
+    launches0 = lanes.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     e0.record()
-    prev = None
-    marks = [time.perf_counter()]
-    for _ in range(args.steps):
-        out, info = step()
-        if prev is not None:
-            slots = finish(prev)                      # step k-1's blob: completed behind step k's kernels
-        prev = out                                    # (results are not hoarded: their pages are reused)
-        marks.append(time.perf_counter())
-    slots = finish(prev)                              # all K blobs are in host memory before the clock stops
-    marks.append(time.perf_counter())
+    slots, info = run_steps(args.steps)  # all K blobs are in host memory before the clock stops
     e1.record()
-    if os.environ.get("LOSSYCOMP_BENCH_TRACE"):
-        print(f"[bench trace] rank {rank}: host ms per step " + " ".join(f"{1e3 * (b - a):.1f}" for a, b in zip(marks, marks[1:])),
-              file=sys.stderr, flush=True)
     barrier()
     w1 = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launches - launches0
+    launches = lanes.launches() - launches0
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    # Per-layer kernel times (CUDA events around every layer's launch, on the launching stream): taken over the same
+    # K steps run again one after the other on lane 0 -- with two fields in flight an event pair would also span
+    # the other lane's kernels.  The same pass gives the one-field-at-a-time step time.
+    barrier()
+    eng.profile(True)
+    eng.profile_read()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        finish(lanes.lanes[0].submit(job))
+    s1.record()
+    barrier()
+    seq_ms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
     layer_ms, layer_cnt = eng.profile_read()
     eng.profile(False)
-    clocks = sampler.stop(w0, w1) if rank == 0 else None
     value = in_bytes * args.steps / (ms * 1e-3) / 1e9
 
     # ---- N > 1: the sharded blob against a single-GPU call on the same field (outside the timed region)
@@ -355,7 +380,31 @@ def run_ours(args):
         xhat = dstep()
     d1.record()
     barrier()
-    dms = max_over_ranks(d0.elapsed_time(d1))
+    dms_seq = max_over_ranks(d0.elapsed_time(d1))
+    dms = dms_seq
+    if world == 1 and len(lanes) > 1:
+        # the same K decompressions with one blob per lane in flight (host work of one behind the kernels of the other)
+        def djob(lane):
+            out = decompress_device(lane.eng, slots)
+            torch.cuda.current_stream(lane.eng.dev).synchronize()
+            return out
+
+        def drun(k):
+            inflight, last = [], None
+            for _ in range(k):
+                inflight.append(lanes.submit(djob))
+                while len(inflight) > len(lanes):
+                    last = inflight.pop(0).result()
+            while inflight:
+                last = inflight.pop(0).result()
+            return last
+        drun(2 * len(lanes))
+        torch.cuda.synchronize()
+        d0.record()
+        xhat = drun(args.steps)
+        d1.record()
+        torch.cuda.synchronize()
+        dms = d0.elapsed_time(d1)
     dvalue = in_bytes * args.steps / (dms * 1e-3) / 1e9
     viol, max_err = eng.verify(x, xhat, ABS_ERR) if t1r > t0r else (0, 0.0)
     if world > 1:
@@ -380,10 +429,10 @@ def run_ours(args):
         arrive (compared with `want` and dropped -- a consumer that hoards them pays first-touch page faults for
         every new blob instead of reusing warm pages)."""
         if world == 1:
-            it = compress_stream([xh] * k, ABS_ERR, precision=args.precision, codec=args.codec)
+            it = compress_stream([xh] * k, ABS_ERR, precision=args.precision, codec=args.codec, lanes=len(lanes))
         else:
             it = LD.compress_sharded_stream([xh] * k, ABS_ERR, t0=t0r, T=T, precision=args.precision,
-                                            codec=args.codec, dst=dst)
+                                            codec=args.codec, dst=dst, lanes=len(lanes))
         same, last = True, None
         for blob in it:          # lengths on the fly; the last blob is compared byte for byte after the clock stops
             same = same and (want is None or blob is None or len(blob) == len(want))
@@ -409,7 +458,7 @@ def run_ours(args):
            "api": ("lossycomp.compress.compress_stream" if world == 1 else "lossycomp.dist.compress_sharded_stream")
                   + ": K fields from pinned host memory -> K blobs (bytes); every step copies its 2-channel input "
                     "host->device and its blob device->host inside the timed region, overlapped with the kernels "
-                    "of the neighbouring steps",
+                    "of the neighbouring steps (%d fields in flight per GPU)" % len(lanes),
            "single_call_GBps": in_bytes / e2e_single / 1e9, "single_call_ms": e2e_single * 1e3,
            "single_call_api": "lossycomp.compress.compress" if world == 1 else "lossycomp.dist.compress_sharded_host",
            "stream_blobs_equal_single_call": stream_equal}
@@ -426,6 +475,17 @@ def run_ours(args):
         for _ in range(args.steps):
             xr = decompress(b)
         e2e_d = (time.perf_counter() - t0) / args.steps
+        # bulk-job form: K blobs -> K arrays (a ring of result arrays, as a consumer that writes them out would keep)
+        ring = [np.empty(xr.shape, dtype=np.float32) for _ in range(len(lanes) + 2)]
+        outs = [ring[i % len(ring)] for i in range(args.steps)]
+        for _ in decompress_stream([b] * (2 * len(lanes)), lanes=len(lanes), outs=[ring[i % len(ring)] for i in range(2 * len(lanes))]):
+            pass
+        t0 = time.perf_counter()
+        for xs_ in decompress_stream([b] * args.steps, lanes=len(lanes), outs=outs):
+            pass
+        e2e["decompress_stream_GBps"] = in_bytes / ((time.perf_counter() - t0) / args.steps) / 1e9
+        e2e["decompress_stream_equal_single_call"] = bool(np.array_equal(xs_, xr))
+        del ring, outs
         e2e_viol = int((np.abs(xh[..., 0].astype(np.float64) - xr[..., 0]) > ABS_ERR).sum())
     else:
         a_, b_, xr = LD.decompress_sharded_host(b, precision=args.precision, src=dst)
@@ -489,6 +549,8 @@ def run_ours(args):
         "traffic": traffic,
         "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over this kernel's layers, from "
                          f"{traffic_src}") if traffic else "no ncu --set full capture of this chunk count is committed",
+        "timing_note": "per-layer CUDA events over the same K steps run one field at a time right after the timed "
+                       "region (with several fields in flight an event pair would span the other lane's kernels)",
         "peak_source": peak_note, "launch_ms": dom["ms"] / max(dom["launches"], 1), "launches": dom["launches"],
         "algorithmic_flops_per_launch": dom["flops"] / max(dom["launches"], 1),
         "share_of_step": dom["ms"] / ms,
@@ -512,9 +574,14 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic",
         "config": workload_config(world, T, H, W, n_chunks_all, args.codec, args.precision, my_bytes, dst),
+        "lanes": {"fields_in_flight_per_gpu": len(lanes), "one_field_at_a_time_ms_per_step": seq_ms,
+                  "note": "lossycomp.lanes: consecutive steps run in alternating lanes (engine + stream + host thread "
+                          "each), the kernels of one field fill the host round trips of the other; every field is "
+                          "compressed by the single-lane code and the blobs are identical"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": e2e,
-        "decompress": {"value": dvalue, "unit": UNIT, "ms_per_step": dms / args.steps},
+        "decompress": {"value": dvalue, "unit": UNIT, "ms_per_step": dms / args.steps,
+                       "one_blob_at_a_time_ms_per_step": dms_seq / args.steps},
         "compression_factor": cf, "violations": viol, "max_abs_err": max_err,
         "roofline": roofline,
     }

@@ -84,6 +84,11 @@ struct SweepParams {
   const uint4* wimg2;
   int wimg2_bytes, b2_rows, stages2;
   uint64_t b2_desc[kMaxKs];
+  // CTA-pair form (cta_group::2): per-rank weight images holding the rows each CTA's half of N reads
+  const uint4* wimg2c0;
+  const uint4* wimg2c1;
+  int wimg2c_bytes, b2c_rows, stages2c;
+  uint64_t b2c_desc[kMaxKs];
 };
 
 // 12 consecutive accumulator columns of this thread's TMEM lane
@@ -695,11 +700,25 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 //     the weights sit in shared memory once per SM, and 8-12 stages of input planes are in flight.
 // Warps: 0 producer (bulk copies), 1-2 MMA issuers (alternate steps), 3 TMEM allocation, 4.. epilogue (bank =
 // (warp-4)/4, TMEM lane quarter = warp % 4).  Deterministic: fixed accumulation order per output voxel.
-constexpr int kAccBanks = 4;
+#ifndef LC_ACC_BANKS
+#define LC_ACC_BANKS 4
+#endif
+constexpr int kAccBanks = LC_ACC_BANKS;
 constexpr int kAccThreads = 32 * (4 + 4 * kAccBanks);
 constexpr int kAccMaxStages = 12;
 
-template <int NT, int H16, int RELU>
+// NCTA = 2: the two CTAs of an SM pair (cluster of 2) run in lockstep on their own four tiles each, and ONE
+// tcgen05.mma.cta_group::2 of the leader CTA multiplies both A tiles (M = 256: rows 0-127 from the leader's shared
+// memory into the leader's TMEM lanes, rows 128-255 the peer's) with a B operand of which each CTA holds HALF the
+// columns.  The kernel is bound by the shared-memory operand fetch (4 KB of A + 2.5 KB of B per M128 x N80 x K16
+// step); halving B takes 19 % off it.  Everything else stays per CTA: producer, stages, epilogue, stores.  Barriers:
+//   full[s]    leader: own bulk copies (expect_tx) + one arrival relayed from the peer (its issuer warp 1 waits for
+//              its own full[s] and arrives remotely);  peer: own copies only
+//   tfull[b]   committed by the leader into BOTH CTAs (multicast commit)
+//   tempty[b]  leader's: 4 local + 4 remote epilogue warps
+//   empty[s]   local (released by the local epilogue once tfull of the step that read the stage has fired)
+// The peer's weight image is the leader's shifted by N/2 rows, so the same descriptor offsets address each half.
+template <int NT, int H16, int RELU, int NCTA>
 __global__ void __launch_bounds__(kAccThreads, 1)
 sweep_acc_kernel(const __grid_constant__ SweepParams p) {
   constexpr int kBankCols = (NT * 24 + 15) & ~15;       // = the MMA's N (80 for NT = 3: 8 scratch columns)
@@ -708,34 +727,46 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[24];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int rank = (NCTA == 2) ? (int)umma::cluster_ctarank() : 0;
+  const bool leader = rank == 0;
   const int slab_bytes = p.slab_slots * 16;
   const int skip_bytes = p.skip_mma ? p.skip.G * p.skip_slots * 16 : 0;
   const int stage_bytes = p.in_NPG * slab_bytes + skip_bytes;
-  const int stages = p.stages2;
+  const int stages = (NCTA == 2) ? p.stages2c : p.stages2;
+  const int wbytes = (NCTA == 2) ? p.wimg2c_bytes : p.wimg2_bytes;
   uint8_t* sB = smem;
-  uint8_t* sA = smem + ((p.wimg2_bytes + 127) & ~127);
+  uint8_t* sA = smem + ((wbytes + 127) & ~127);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < stages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < kAccBanks; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < stages; ++i) { umma::mbar_init(&full[i], (NCTA == 2 && leader) ? 2 : 1); umma::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kAccBanks; ++i) { umma::mbar_init(&tfull[i], 1); umma::mbar_init(&tempty[i], 4 * NCTA); }
     umma::mbar_init(&wbar, 1);
     umma::fence_barrier_init();
   }
   if (threadIdx.x < 24) s_bias[threadIdx.x] = (threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
-  if (warp == 3) umma::tmem_alloc(&tmem_base_s, 512u);
+  if (warp == 3) {
+    if (NCTA == 2) umma::tmem_alloc2(&tmem_base_s, 512u);
+    else umma::tmem_alloc(&tmem_base_s, 512u);
+  }
   umma::tcgen05_fence_before();
-  __syncthreads();
+  if (NCTA == 2) umma::cluster_sync_all();     // the peer's barriers exist before anything arrives on them
+  else __syncthreads();
   umma::tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
   const int T = p.in_T;
-  // this CTA's items: blockIdx.x + k * gridDim.x, k < cnt; round r works on items 4r .. 4r+3 (one per bank)
-  const int cnt = ((int)blockIdx.x < p.n_items) ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // Work items: unit u = blockIdx.x / NCTA of gridDim.x / NCTA units takes item groups u, u + units, ...; group j is
+  // items NCTA*j + rank (the last group of an odd item count has no item for the peer: it re-runs the last item with
+  // its stores off).  Round r works on groups 4r .. 4r+3 (one per bank).
+  const int unit = (int)blockIdx.x / NCTA, units = (int)gridDim.x / NCTA;
+  const int n_groups = (p.n_items + NCTA - 1) / NCTA;
+  const int cnt = (unit < n_groups) ? (n_groups - unit + units - 1) / units : 0;
   const int rounds = (cnt + kAccBanks - 1) / kAccBanks;
+  auto item_of = [&](int k) { return NCTA * (unit + k * units) + rank; };
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      umma::mbar_arrive_expect_tx(&wbar, (uint32_t)p.wimg2_bytes);
-      umma::bulk_g2s(sB, p.wimg2, (uint32_t)p.wimg2_bytes, &wbar);
+      umma::mbar_arrive_expect_tx(&wbar, (uint32_t)wbytes);
+      umma::bulk_g2s(sB, (NCTA == 2) ? (leader ? p.wimg2c0 : p.wimg2c1) : p.wimg2, (uint32_t)wbytes, &wbar);
       int stage = 0, phase = 0;
       for (int r = 0; r < rounds; ++r) {
         const int nb = min(kAccBanks, cnt - kAccBanks * r);
@@ -743,7 +774,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
         const uint4* sk0[kAccBanks];
 #pragma unroll
         for (int b = 0; b < kAccBanks; ++b) {
-          const int item = (int)blockIdx.x + (kAccBanks * r + b) * (int)gridDim.x;
+          const int item = min(item_of(kAccBanks * r + b), p.n_items - 1);
           const int n = item / p.tiles_per_chunk;
           const int tile = item - n * p.tiles_per_chunk;
           slab0[b] = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start;
@@ -770,11 +801,25 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (NCTA == 2 && !leader && warp == 1) {
+    // ===================== peer CTA: relay "my stage is loaded" to the leader's full barrier =====================
+    if (lane == 0) {
+      umma::mbar_wait(&wbar, 0);                 // the first relayed arrival also vouches for this CTA's weights
+      int stage = 0, phase = 0;
+      for (int r = 0; r < rounds; ++r) {
+        const int nb = min(kAccBanks, cnt - kAccBanks * r);
+        for (int i = 0; i < T * nb; ++i) {
+          umma::mbar_wait(&full[stage], phase);
+          umma::mbar_arrive_cluster(umma::mapa_rank(&full[stage], 0));
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if ((warp == 1 || warp == 2) && leader) {
     // ===================== MMA issuers (alternate steps) =====================
     const int me = warp - 1;
     umma::mbar_wait(&wbar, 0);
-    const uint32_t idesc = umma::make_idesc(128, kBankCols, H16 ? 0 : 1);
+    const uint32_t idesc = umma::make_idesc(128 * NCTA, kBankCols, H16 ? 0 : 1);
     const uint64_t sA_add = (uint64_t)(umma::smem_u32(sA) >> 4), sB_add = (uint64_t)(umma::smem_u32(sB) >> 4);
     int stage = 0, phase = 0, step = 0;
     (void)step;
@@ -791,19 +836,30 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
           // of the one before (alternating issuers by step would let one run a whole phase ahead of the other on
           // the same bank whenever the number of active banks is odd)
           if ((b & 1) == me) {
-            umma::mbar_wait(&tempty[b], kb & 1);
-            umma::mbar_wait(&full[stage], phase);
+            if (NCTA == 2) {
+              umma::mbar_wait_cluster(&tempty[b], kb & 1);
+              umma::mbar_wait_cluster(&full[stage], phase);
+            } else {
+              umma::mbar_wait(&tempty[b], kb & 1);
+              umma::mbar_wait(&full[stage], phase);
+            }
             umma::tcgen05_fence_after();
             const uint64_t a_add = sA_add + (uint64_t)((uint32_t)(stage * stage_bytes) >> 4);
             const uint32_t d_addr = tmem + b * kBankCols;
             const int nks = (p.debug & 1) ? 0 : p.nks;
 #pragma unroll 2
             for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t a = p.a_desc[0][ks] + a_add, bd = p.b2_desc[ks] + b_add;
-              if (umma::elect_one()) umma::mma_f16(d_addr, a, bd, idesc, true);
+              const uint64_t a = p.a_desc[0][ks] + a_add, bd = ((NCTA == 2) ? p.b2c_desc[ks] : p.b2_desc[ks]) + b_add;
+              if (umma::elect_one()) {
+                if (NCTA == 2) umma::mma_f16_2cta(d_addr, a, bd, idesc, true);
+                else umma::mma_f16(d_addr, a, bd, idesc, true);
+              }
             }
             __syncwarp();
-            if (umma::elect_one()) umma::commit(&tfull[b]);
+            if (umma::elect_one()) {
+              if (NCTA == 2) umma::commit_2cta(&tfull[b]);
+              else umma::commit(&tfull[b]);
+            }
             __syncwarp();
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -816,6 +872,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t bank_addr = tmem + ((uint32_t)(q * 32) << 16) + b * kBankCols;
+    const uint32_t tempty_leader = (NCTA == 2) ? umma::mapa_rank(&tempty[b], 0) : 0u;
     uint32_t bias_u[24];
 #pragma unroll
     for (int c = 0; c < 24; ++c) bias_u[c] = __float_as_uint(s_bias[c]);
@@ -828,7 +885,10 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
       umma::tmem_st_wait();
       umma::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&tempty[b]);
+      if (lane == 0) {
+        if (NCTA == 2) umma::mbar_arrive_cluster(tempty_leader);
+        else umma::mbar_arrive(&tempty[b]);
+      }
     };
     // 24 accumulator columns of one slot -> 12 packed 16-bit pairs ((ReLU,) saturate, round to nearest even)
     auto load_pack = [&](int slot, unsigned (&pk)[12]) {
@@ -847,8 +907,10 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
     hand_back();
     for (int r = 0; kAccBanks * r + b < cnt; ++r) {
       const int nb = min(kAccBanks, cnt - kAccBanks * r);
-      const int item = (int)blockIdx.x + (kAccBanks * r + b) * (int)gridDim.x;
+      const int item_raw = item_of(kAccBanks * r + b);
+      const int item = min(item_raw, p.n_items - 1);
       const RowInfo ri = row_info(p, item, row);
+      const bool valid = ri.valid && item_raw < p.n_items;
       const VoxPtr vp = vox_ptr(p, ri.n, ri.h, ri.w);
       auto store_plane = [&](int plane, const unsigned (&pk)[12]) {
         uint4* o = vp.o + (long long)plane * vp.o_t;
@@ -858,7 +920,8 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
       };
       for (int t = 0; t < T; ++t) {
         const int kb = r * T + t;
-        umma::mbar_wait(&tfull[b], kb & 1);
+        if (NCTA == 2) umma::mbar_wait_cluster(&tfull[b], kb & 1);
+        else umma::mbar_wait(&tfull[b], kb & 1);
         umma::tcgen05_fence_after();
         // the MMAs that read this step's stage are complete: hand the stage back to the producer
         // (all earlier rounds were full, so the step index is 4*T*r + t*nb + b)
@@ -870,7 +933,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
           if (pc >= 0) load_pack(slot, pk);
           init_slot(slot);
           hand_back();
-          if (pc >= 0 && ri.valid) store_plane(pc, pk);
+          if (pc >= 0 && valid) store_plane(pc, pk);
         } else {
           // last input plane: the remaining NT-1 planes are complete; all slots restart from the bias
           unsigned pk[NT - 1][12];
@@ -882,14 +945,18 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
           hand_back();
 #pragma unroll
           for (int j = 0; j < NT - 1; ++j)
-            if (pc + j >= 0 && ri.valid) store_plane(pc + j, pk[j]);
+            if (pc + j >= 0 && valid) store_plane(pc + j, pk[j]);
         }
       }
     }
   }
   umma::tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 3) umma::tmem_dealloc(tmem, 512u);
+  if (NCTA == 2) umma::cluster_sync_all();      // no CTA frees TMEM or exits while its partner still uses the pair
+  else __syncthreads();
+  if (warp == 3) {
+    if (NCTA == 2) umma::tmem_dealloc2(tmem, 512u);
+    else umma::tmem_dealloc(tmem, 512u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -912,6 +979,8 @@ struct LayerPlan {
   int smem_bytes;
   int acc_smem_bytes;      // > 0: the layer runs sweep_acc_kernel (time taps accumulated in TMEM)
   void* d_wimg2;
+  int acc2_smem_bytes;     // > 0: the CTA-pair form of sweep_acc_kernel can run the layer
+  void* d_wimg2c[2];
 };
 
 struct TcPlan {
@@ -1222,22 +1291,81 @@ int launch_acc_variant(const SweepParams& p, int grid, int smem, cudaStream_t s)
   int dev = 0;
   LC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  sweep_acc_kernel<NT, H16, RELU><<<grid, kAccThreads, smem, s>>>(p);
+  sweep_acc_kernel<NT, H16, RELU, 1><<<grid, kAccThreads, smem, s>>>(p);
   return LC_OK;
+}
+
+// CTA-pair form: clusters of two CTAs (one SM pair each); the grid is twice the number of pairs that can be resident
+template <int NT, int H16, int RELU>
+int launch_acc2_variant(const SweepParams& p, int n_items, int smem, cudaStream_t s) {
+  static int max_pairs[64] = {};
+  int dev = 0;
+  LC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) {
+    lc_set_error("device index %d out of range", dev);
+    return LC_EINVAL;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kAccThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!max_pairs[dev]) {
+    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    cfg.gridDim = dim3(2);
+    int n = 0;
+    LC_CUDA(cudaOccupancyMaxActiveClusters(&n, sweep_acc_kernel<NT, H16, RELU, 2>, &cfg));
+    if (n < 1) {
+      lc_set_error("no CTA pair of sweep_acc_kernel fits the device");
+      return LC_EUNSUPPORTED;
+    }
+    max_pairs[dev] = n;
+    if (getenv("LOSSYCOMP_ACC2_PAIRS")) max_pairs[dev] = atoi(getenv("LOSSYCOMP_ACC2_PAIRS"));
+    if (getenv("LOSSYCOMP_TC_VERBOSE")) fprintf(stderr, "[lossycomp] sweep_acc_kernel<%d> CTA pairs: occupancy %d, using %d\n", NT, n, max_pairs[dev]);
+  }
+  const int groups = (n_items + 1) / 2;
+  const int pairs = max_pairs[dev] < groups ? max_pairs[dev] : groups;
+  cfg.gridDim = dim3(2 * pairs);
+  LC_CUDA(cudaLaunchKernelEx(&cfg, sweep_acc_kernel<NT, H16, RELU, 2>, p));
+  return LC_OK;
+}
+
+// LOSSYCOMP_ACC_CTA2=1 runs these layers in the CTA-pair form.  Off by default: measured on the benchmark field the
+// pair form is within 2 % of the single-CTA form (0.874 vs 0.890 ms on the 3x3x3 layers, 0.590 vs 0.574 ms on the
+// first layer) -- halving the B fetch does not move a kernel whose operand traffic is 4 KB of A per 1.25 KB of B.
+bool acc_cta2_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LOSSYCOMP_ACC_CTA2");
+    on = e ? (atoi(e) != 0) : 0;
+  }
+  return on != 0;
 }
 
 int launch_sweep(const lc_codec* h, const LayerPlan& lp, SweepParams& p, cudaStream_t s) {
   if (lp.acc_smem_bytes > 0 && (lp.backend == MODE_K3 || lp.backend == MODE_K4)) {
     int grid = h->num_sms < p.n_items ? h->num_sms : p.n_items;
     int rc;
+    const bool pair = lp.acc2_smem_bytes > 0 && acc_cta2_enabled();
+    const int sm = pair ? lp.acc2_smem_bytes : lp.acc_smem_bytes;
+#define LC_ACC_LAUNCH(NT, H, R) \
+    (pair ? launch_acc2_variant<NT, H, R>(p, p.n_items, sm, s) : launch_acc_variant<NT, H, R>(p, grid, sm, s))
     if (lp.backend == MODE_K4) {
-      if (p.half) rc = p.relu ? launch_acc_variant<4, 1, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<4, 1, 0>(p, grid, lp.acc_smem_bytes, s);
-      else rc = p.relu ? launch_acc_variant<4, 0, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<4, 0, 0>(p, grid, lp.acc_smem_bytes, s);
-    } else if (p.half) rc = p.relu ? launch_acc_variant<3, 1, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<3, 1, 0>(p, grid, lp.acc_smem_bytes, s);
-    else rc = p.relu ? launch_acc_variant<3, 0, 1>(p, grid, lp.acc_smem_bytes, s) : launch_acc_variant<3, 0, 0>(p, grid, lp.acc_smem_bytes, s);
+      if (p.half) rc = p.relu ? LC_ACC_LAUNCH(4, 1, 1) : LC_ACC_LAUNCH(4, 1, 0);
+      else rc = p.relu ? LC_ACC_LAUNCH(4, 0, 1) : LC_ACC_LAUNCH(4, 0, 0);
+    } else if (p.half) rc = p.relu ? LC_ACC_LAUNCH(3, 1, 1) : LC_ACC_LAUNCH(3, 1, 0);
+    else rc = p.relu ? LC_ACC_LAUNCH(3, 0, 1) : LC_ACC_LAUNCH(3, 0, 0);
+#undef LC_ACC_LAUNCH
     if (rc != LC_OK) return rc;
     LC_LAUNCH_CHECK();
     return LC_OK;
@@ -1501,6 +1629,8 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   const int stage_bytes = p.in_NPG * p.slab_slots * 16 + (p.skip_mma ? G * p.skip_slots * 16 : 0);
   lp.acc_smem_bytes = 0;
   lp.d_wimg2 = nullptr;
+  lp.acc2_smem_bytes = 0;
+  lp.d_wimg2c[0] = lp.d_wimg2c[1] = nullptr;
   // Layers with a residual input stay on sweep_tc_kernel unless LOSSYCOMP_ACC_SKIP=1: they are bound by HBM traffic
   // (input + skip tile + output, 5.1 GB per launch on the benchmark field) rather than by the shared-memory operand
   // fetch, and measured 4 % slower in the four-banks-per-SM form (1.17 vs 1.12 ms).
@@ -1559,6 +1689,40 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     if (st2 >= 4) {
       p.stages2 = st2;
       lp.acc_smem_bytes = fixed2 + st2 * stage_bytes;
+    }
+    // CTA-pair form: rank r of the pair multiplies columns [r*N/2, (r+1)*N/2) of the rotated window, i.e. rows
+    // [i0*24 + r*N/2, +N/2) of the image above; its own image holds rows [r*N/2, r*N/2 + rows_c) at offset 0, so
+    // that one descriptor addresses the right half in both CTAs
+    {
+      const int half_cols = bank_cols / 2;
+      const int rows_c = ((NT - 1) * 24 + half_cols + 7) & ~7;
+      const bool swap = getenv("LOSSYCOMP_ACC2_SWAP") != nullptr;     // debugging: which CTA owns which half
+      std::vector<unsigned short> imgc[2];
+      for (int r = 0; r < 2; ++r) {
+        imgc[r].assign((size_t)p.nks * 2 * rows_c * 8, 0);
+        const int shift = (swap ? 1 - r : r) * half_cols;
+        for (int gi = 0; gi < ngroups; ++gi)
+          for (int j = 0; j < rows_c; ++j) {
+            if (j + shift >= rows) continue;
+            memcpy(&imgc[r][((size_t)gi * rows_c + j) * 8], &img2[((size_t)gi * rows + j + shift) * 8], 16);
+          }
+      }
+      for (int ks = 0; ks < p.nks; ++ks)
+        p.b2c_desc[ks] = host_desc2((uint32_t)((size_t)ks * 2 * rows_c * 16), (uint32_t)rows_c * 16, 128);
+      p.wimg2c_bytes = (int)(imgc[0].size() * 2);
+      p.b2c_rows = rows_c;
+      for (int r = 0; r < 2; ++r) {
+        LC_CUDA(cudaMalloc(&lp.d_wimg2c[r], imgc[r].size() * 2));
+        LC_CUDA(cudaMemcpy(lp.d_wimg2c[r], imgc[r].data(), imgc[r].size() * 2, cudaMemcpyHostToDevice));
+      }
+      p.wimg2c0 = reinterpret_cast<const uint4*>(lp.d_wimg2c[0]);
+      p.wimg2c1 = reinterpret_cast<const uint4*>(lp.d_wimg2c[1]);
+      const int fixedc = ((p.wimg2c_bytes + 127) & ~127) + 256;
+      int stc = (200 * 1024 - fixedc) / stage_bytes;
+      if (stc > kAccMaxStages) stc = kAccMaxStages;
+      if (getenv("LOSSYCOMP_ACC_STAGES")) stc = atoi(getenv("LOSSYCOMP_ACC_STAGES"));
+      p.stages2c = stc;
+      lp.acc2_smem_bytes = (stc >= 4 && lp.acc_smem_bytes > 0 && bank_cols % 16 == 0) ? fixedc + stc * stage_bytes : 0;
     }
   }
   // dynamic shared memory per CTA; the single-channel mode also holds a 17.6 KB static exchange tile
@@ -1654,6 +1818,8 @@ void tc_release(lc_codec* h) {
   for (int i = 0; i < P->n_layers; ++i) {
     if (P->layer[i].d_w16) cudaFree(P->layer[i].d_w16);
     if (P->layer[i].d_wimg2) cudaFree(P->layer[i].d_wimg2);
+    for (int r = 0; r < 2; ++r)
+      if (P->layer[i].d_wimg2c[r]) cudaFree(P->layer[i].d_wimg2c[r]);
   }
   delete P;
   h->tc_plan = nullptr;

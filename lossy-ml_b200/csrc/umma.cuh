@@ -56,6 +56,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- CTA pairs (cta_group::2): barriers of the leader CTA that the peer CTA arrives on -------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `bar` (an object of this CTA's shared memory layout) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(const void* bar, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(bar)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) uses them: the data the
+  // arrival vouches for travels through the async proxy / TMEM fences, and .release.cluster measured ~1 us per arrival
+#ifdef LC_ARRIVE_RELEASE_CLUSTER
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
+}
+// Waiting for a barrier that another CTA (or the pair's multicast commit) arrives on
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+}
 // ---- bulk async copy global -> shared (TMA engine, 1-D) ----------------------------------
 // size and both addresses must be multiples of 16 bytes; completion is signalled on `bar`.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -74,6 +102,16 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) { 
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t tmem, uint32_t cols) {      // whole warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+}
+// cta_group::2: the same warp of BOTH CTAs of the pair allocates / frees (same destination offset in both)
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t cols) {   // whole warp, both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t tmem, uint32_t cols) {      // whole warp, both CTAs
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -109,6 +147,22 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate));
+}
+// CTA pair: M = 256 (rows 0-127 = the leader's A tile and TMEM lanes, 128-255 = the peer's), each CTA supplies half
+// of B's N columns from the same shared-memory offsets; issued by the leader CTA only
+__device__ __forceinline__ void mma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate));
+}
+// arrives on the barrier at `bar`'s offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
 }
 // arrives on `bar` once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void commit(uint64_t* bar) {

@@ -94,11 +94,13 @@ class Engine:
 
     @classmethod
     def get(cls, model_path: Optional[str] = None, precision: Optional[str] = None,
-            device: Optional[int] = None) -> "Engine":
+            device: Optional[int] = None, lane: int = 0) -> "Engine":
+        """lane > 0: a further, independent instance for the same (model, precision, device) -- lossycomp.lanes
+        keeps one field in flight per instance."""
         torch = N.require_cuda()
         precision = precision or os.environ.get("LOSSYCOMP_PRECISION", DEFAULT_PRECISION)
         device = torch.cuda.current_device() if device is None else device
-        key = (model_path or "default", precision, device)
+        key = (model_path or "default", precision, device) + ((lane,) if lane else ())
         if key not in cls._cache:
             cls._cache[key] = Engine(load_model(model_path), precision, device)
         return cls._cache[key]

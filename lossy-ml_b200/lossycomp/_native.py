@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblossycomp_b200.so")
+LIB_PATH = os.environ.get("LOSSYCOMP_LIB") or os.path.join(_HERE, "liblossycomp_b200.so")   # LOSSYCOMP_LIB: experiment builds
 
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}

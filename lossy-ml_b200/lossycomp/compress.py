@@ -230,20 +230,27 @@ def compress(array, err_threshold, verbose=False, *, mode="strict", codec="huff"
     return out
 
 
-def compress_stream(arrays, err_threshold, *, mode="strict", codec="huff", precision=None, model=None, device=None):
-    """Compress a sequence of fields, yielding one blob per field (each identical to compress(field, ...)).
+def compress_stream(arrays, err_threshold, *, mode="strict", codec="huff", precision=None, model=None, device=None,
+                    lanes=None):
+    """Compress a sequence of fields, yielding one blob per field, in order (each identical to compress(field, ...)).
 
-    Extension for bulk jobs (a month of 24 h slices): while field k is being compressed the host->device copy of
-    field k+1 runs on a second stream into the other half of a double buffer, so the PCIe transfer (3.6 ms of a
-    15 ms call on the benchmark field) disappears behind the kernels.  Pinned inputs overlap; pageable ones are
-    staged like in compress()."""
+    Extension for bulk jobs (a month of 24 h slices).  Two things overlap the kernels of a field: the host->device
+    copy of the next one, on a copy stream into a ring of input buffers (3.6 ms of a 12 ms call on the benchmark
+    field), and the host round trips of its neighbour -- consecutive fields run in alternating lanes
+    (lossycomp.lanes: an engine, a stream and a host thread each; default 2, LOSSYCOMP_LANES), so that while one
+    field waits for its statistics, outlier count or Huffman tables the other one's convolutions keep the GPU busy.
+    Pinned inputs overlap; pageable ones are staged like in compress()."""
+    from collections import deque
+    from .lanes import LaneSet
     torch = N.require_cuda()
-    eng = Engine.get(model, precision, device)
-    main = torch.cuda.current_stream(eng.dev)
+    ls = LaneSet.get(model, precision, device, lanes)
+    eng = ls.lanes[0].eng
     copy = torch.cuda.Stream(device=eng.dev)
-    bufs, ready, freed = [None, None], [None, None], [None, None]
+    nbuf = len(ls) + 1                    # one field per lane in flight + the one being uploaded
+    bufs = [None] * nbuf
 
     def upload(slot, array):
+        """-> (device tensor, event to wait for or None, object to keep alive)"""
         assert err_threshold != 0, "The absolute error can't be 0."
         if array.dtype != np.float32:
             array = np.array(array, dtype=np.float32)
@@ -253,38 +260,25 @@ def compress_stream(arrays, err_threshold, *, mode="strict", codec="huff", preci
             "Chunks size cannot be larger than the data size."
         src = torch.from_numpy(np.ascontiguousarray(array))
         if not src.is_pinned():
-            bufs[slot] = _hostio.h2d(eng, array)
-            ready[slot] = None
-            return
+            return _hostio.h2d(eng, array), None, None
+        # the job that read this buffer nbuf fields ago has been collected (at most len(ls) jobs are in flight)
         if bufs[slot] is None or bufs[slot].shape != src.shape:
             bufs[slot] = torch.empty(src.shape, dtype=torch.float32, device=eng.dev)
-        if freed[slot] is not None:
-            copy.wait_event(freed[slot])          # the kernels that read this buffer two fields ago are done
         with torch.cuda.stream(copy):
             bufs[slot].copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy)
-        ready[slot] = (ev, src)                   # keep the pinned source alive until the copy has been waited for
+        return bufs[slot], ev, src                # the pinned source stays alive until the job has run
 
-    it = iter(arrays)
-    try:
-        upload(0, next(it))
-    except StopIteration:
-        return
-    k = 0
-    while True:
-        slot = k & 1
-        if ready[slot] is not None:
-            main.wait_event(ready[slot][0])
-        try:
-            upload(slot ^ 1, next(it))
-            more = True
-        except StopIteration:
-            more = False
-        blob, _ = compress_device(eng, bufs[slot], err_threshold, mode=mode, codec=codec, as_blob=True)
-        freed[slot] = torch.cuda.Event()
-        freed[slot].record(main)
-        yield blob
-        if not more:
-            return
-        k += 1
+    def job(lane, x, ev, _keep):
+        if ev is not None:
+            lane.stream.wait_event(ev)
+        return compress_device(lane.eng, x, err_threshold, mode=mode, codec=codec, as_blob=True)[0]
+
+    inflight = deque()
+    for k, array in enumerate(arrays):
+        inflight.append(ls.submit(job, *upload(k % nbuf, array)))
+        while len(inflight) > len(ls):
+            yield inflight.popleft().result()
+    while inflight:
+        yield inflight.popleft().result()

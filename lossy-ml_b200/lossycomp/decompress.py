@@ -81,10 +81,8 @@ def decompress_device(eng: Engine, slots, *, inject=None, batch=None, rows=None)
     return eng.reconstruct(recon, mask, q, mean, std, thr2)                          # decompress.py:86-104
 
 
-def decompress(compressed_data, verbose=False, *, precision=None, model=None, device=None, out=None):
-    """Decompression method (reference: decompress.py:21).  Returns the reconstructed data.
-    `out` (optional, float32, T*H*W elements) is filled and returned instead of a new array."""
-    N.require_cuda()
+def _open_blob(compressed_data, precision=None, model=None):
+    """-> (slot list, precision, model path) the blob asks for (decompress.py:54 + the 'LCL1' header of slot 0)."""
     slots = pickle.loads(compressed_data)                                            # decompress.py:54
     try:
         meta = _peek_meta(slots[0])
@@ -99,17 +97,59 @@ def decompress(compressed_data, verbose=False, *, precision=None, model=None, de
         cand = shipped_model_path(meta["model"])
         if cand and cand != default_model_path():
             model = cand
-    eng = Engine.get(model, precision, device)
+    return slots, precision, model
+
+
+def _decompress_on(eng: Engine, slots, out=None):
     T, H, W = (int(v) for v in slots[2][:3])
     pending = ()
     if out is None:            # fresh result: its page faults are taken by the thread pool while the GPU decodes
         out, pending = _hostio.prefault((T, H, W, 1))
     dev_out = decompress_device(eng, slots)
-    if verbose:
-        print("Done.")
     res = _hostio.d2h(eng, dev_out, (T, H, W, 1), out=out, wait=pending)             # decompress.py:104-108
     eng.check_reconstruct()              # the copy synchronised the stream: outlier count of the mask == code count
     return res
+
+
+def decompress(compressed_data, verbose=False, *, precision=None, model=None, device=None, out=None):
+    """Decompression method (reference: decompress.py:21).  Returns the reconstructed data.
+    `out` (optional, float32, T*H*W elements) is filled and returned instead of a new array."""
+    N.require_cuda()
+    slots, precision, model = _open_blob(compressed_data, precision, model)
+    res = _decompress_on(Engine.get(model, precision, device), slots, out)
+    if verbose:
+        print("Done.")
+    return res
+
+
+def decompress_stream(blobs, *, precision=None, model=None, device=None, lanes=None, outs=None):
+    """Decompress a sequence of blobs, yielding one array per blob, in order (each identical to decompress(blob)).
+
+    Bulk-job counterpart of compress_stream(): consecutive blobs run in alternating lanes (lossycomp.lanes), so the
+    host work of one blob -- unpickling, Huffman decode tables, the upload of its payloads and above all the
+    device->host copy of its 100 MB result -- runs behind the decoder kernels of the other.  All blobs must come
+    from the same model and precision (the first one decides; a mismatch raises like in decompress()).
+    outs: optional sequence of float32 arrays to fill, one per blob."""
+    from collections import deque
+    from .lanes import LaneSet
+    N.require_cuda()
+    ls = None
+    outs = iter(outs) if outs is not None else None
+
+    def job(lane, slots, out):
+        return _decompress_on(lane.eng, slots, out)
+
+    inflight = deque()
+    for blob in blobs:
+        slots, p, m = _open_blob(blob, precision, model)
+        if ls is None:
+            precision, model = p, m
+            ls = LaneSet.get(model, precision, device, lanes)
+        inflight.append(ls.submit(job, slots, next(outs) if outs is not None else None))
+        while len(inflight) > len(ls):
+            yield inflight.popleft().result()
+    while inflight:
+        yield inflight.popleft().result()
 
 
 def _peek_meta(comp_data: bytes) -> dict:

@@ -688,23 +688,25 @@ def compress_sharded_host(array_local, err_threshold, *, t0, T, precision=None, 
 
 
 def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=None, model=None, device=None,
-                            mode="strict", codec="huff", group=None, dst=0):
+                            mode="strict", codec="huff", group=None, dst=0, lanes=None):
     """Bulk-job form of compress_sharded_host: a sequence of fields (each given by this rank's rows of it, all with
-    the same sharding) -> one blob per field on rank `dst` (None elsewhere), each identical to the blob
-    compress_sharded_host returns.  The host->device copy of field k+1 runs on a second stream behind the kernels
-    of field k (pinned inputs), and the gathered blob of field k reaches the host (copy stream + host thread)
-    behind the kernels of field k+1."""
+    the same sharding) -> one blob per field on rank `dst` (None elsewhere), in order, each identical to the blob
+    compress_sharded_host returns.  The host->device copy of the next field runs on a copy stream, consecutive fields
+    run in alternating lanes (lossycomp.lanes; every lane has its own process group, so the collectives of two
+    fields in flight stay in the same order on every rank), and the gathered blob of a field reaches the host (copy
+    stream + host thread) behind the kernels of the fields after it."""
+    from collections import deque
     import torch.distributed as dist
     from . import _hostio
     from . import _native as N
-    from ._engine import Engine
-    from .compress import dumps_slots
+    from .lanes import LaneSet
     torch = N.require_cuda()
-    eng = Engine.get(model, precision, device)
-    main = torch.cuda.current_stream(eng.dev)
+    ls = LaneSet.get(model, precision, device, lanes).groups(group)
+    eng = ls.lanes[0].eng
     copy = torch.cuda.Stream(device=eng.dev)
     is_dst = dist.get_rank(group) == dst
-    bufs, ready, freed = [None, None], [None, None], [None, None]
+    nbuf = len(ls) + 1
+    bufs = [None] * nbuf
 
     def upload(slot, array):
         if array.dtype != np.float32:
@@ -712,47 +714,39 @@ def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=Non
         assert array.ndim == 4 and array.shape[3] == eng.model.arch.in_channels, \
             "Input should have %d channels." % eng.model.arch.in_channels
         src = torch.from_numpy(np.ascontiguousarray(array))
-        if not src.is_pinned() or not array.shape[0]:
-            bufs[slot] = _hostio.h2d(eng, array) if array.shape[0] else \
-                torch.empty(array.shape, dtype=torch.float32, device=eng.dev)
-            ready[slot] = None
-            return
+        if not array.shape[0]:
+            return torch.empty(array.shape, dtype=torch.float32, device=eng.dev), None, None
+        if not src.is_pinned():
+            return _hostio.h2d(eng, array), None, None
         if bufs[slot] is None or bufs[slot].shape != src.shape:
             bufs[slot] = torch.empty(src.shape, dtype=torch.float32, device=eng.dev)
-        if freed[slot] is not None:
-            copy.wait_event(freed[slot])
         with torch.cuda.stream(copy):
             bufs[slot].copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy)
-        ready[slot] = (ev, src)
+        return bufs[slot], ev, src
 
-    it = iter(arrays_local)
-    try:
-        upload(0, next(it))
-    except StopIteration:
-        return
-    k, prev = 0, None
-    while True:
-        slot = k & 1
-        if ready[slot] is not None:
-            main.wait_event(ready[slot][0])
-        try:
-            upload(slot ^ 1, next(it))
-            more = True
-        except StopIteration:
-            more = False
-        pend, _ = compress_sharded(eng, bufs[slot], err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=group,
+    def job(lane, x, ev, _keep):
+        if ev is not None:
+            lane.stream.wait_event(ev)
+        pend, _ = compress_sharded(lane.eng, x, err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=lane.group,
                                    dst=dst, wait=False, pickled=True)
-        freed[slot] = torch.cuda.Event()
-        freed[slot].record(main)
-        if prev is not None:                      # the previous field's blob was finished behind this field's kernels
-            yield prev.result() if is_dst else None
-        prev = pend if is_dst else True
-        if not more:
-            yield prev.result() if is_dst else None
-            return
-        k += 1
+        # the lane's kernels are done with x once its stream is drained (the next upload into this buffer is only
+        # issued after this job has been collected)
+        torch.cuda.current_stream(lane.eng.dev).synchronize()
+        return pend
+
+    def collect(fut):
+        pend = fut.result()
+        return pend.result() if is_dst else None
+
+    inflight = deque()
+    for k, array in enumerate(arrays_local):
+        inflight.append(ls.submit(job, *upload(k % nbuf, array)))
+        while len(inflight) > len(ls):
+            yield collect(inflight.popleft())
+    while inflight:
+        yield collect(inflight.popleft())
 
 
 def decompress_sharded_host(blob_or_none, *, precision=None, model=None, device=None, group=None, src=0):
