@@ -263,7 +263,9 @@ def run_ours(args):
     # Fields in flight: consecutive steps run in alternating lanes (engine + stream + host thread each), so the
     # kernels of one field fill the host round trips of the other.  Lane 0 is `eng`.
     from lossycomp.lanes import LaneSet, n_lanes
-    lanes = LaneSet.get(None, args.precision, local, n_lanes(args.lanes))
+    # N > 1 runs one field at a time unless --lanes says otherwise (two NCCL communicators driven from two threads
+    # deadlocked on 2 GPUs; see lossycomp.dist.compress_sharded_stream)
+    lanes = LaneSet.get(None, args.precision, local, n_lanes(args.lanes) if (world == 1 or args.lanes) else 1)
     if world > 1:
         lanes.groups()
 

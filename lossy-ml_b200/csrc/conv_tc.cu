@@ -78,7 +78,7 @@ struct SweepParams {
   uint64_t a_desc[kMaxVar][kMaxKs], b_desc[kMaxVar][kMaxKs];   // descriptors for smem offsets relative to sA / sB
   const float* bias;
   int cout, relu, half, out_T;
-  int debug;   // ablation: bit0 no MMA issue, bit3 no bulk copies, bit4 single issuer warp
+  int debug;   // ablation: bit0 no MMA issue, bit2 no global stores (sweep_acc_kernel), bit3 no bulk copies, bit4 single issuer warp
   // sweep_acc_kernel (time taps accumulated in TMEM): weight image with the time blocks stored twice in decreasing
   // order, 8-row-group pitch b2_rows, descriptors relative to its start
   const uint4* wimg2;
@@ -368,7 +368,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
       umma::tcgen05_fence_after();
       // the MMAs that read this step's stage are complete: hand the stage back to the producer
       if (last_of_stage) {
-        if (warp == 2 && lane == 0) umma::mbar_arrive(&empty[estage]);
+        if (warp == 2 && lane == 0) umma::mbar_arrive_relaxed(&empty[estage]);
         if (++estage == p.stages) estage = 0;
       }
       return lane_addr + ebuf * p.acc_stride;
@@ -376,7 +376,7 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
     auto release_d = [&]() {
       umma::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&tempty[ebuf]);
+      if (lane == 0) umma::mbar_arrive_relaxed(&tempty[ebuf]);
       if (++ebuf == p.nbuf) { ebuf = 0; ephase ^= 1; }
     };
     const int G = p.out.G;
@@ -887,7 +887,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
       __syncwarp();
       if (lane == 0) {
         if (NCTA == 2) umma::mbar_arrive_cluster(tempty_leader);
-        else umma::mbar_arrive(&tempty[b]);
+        else umma::mbar_arrive_relaxed(&tempty[b]);
       }
     };
     // 24 accumulator columns of one slot -> 12 packed 16-bit pairs ((ReLU,) saturate, round to nearest even)
@@ -910,7 +910,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
       const int item_raw = item_of(kAccBanks * r + b);
       const int item = min(item_raw, p.n_items - 1);
       const RowInfo ri = row_info(p, item, row);
-      const bool valid = ri.valid && item_raw < p.n_items;
+      const bool valid = ri.valid && item_raw < p.n_items && !(p.debug & 4);   // debug bit 2: no global stores
       const VoxPtr vp = vox_ptr(p, ri.n, ri.h, ri.w);
       auto store_plane = [&](int plane, const unsigned (&pk)[12]) {
         uint4* o = vp.o + (long long)plane * vp.o_t;
@@ -925,7 +925,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
         umma::tcgen05_fence_after();
         // the MMAs that read this step's stage are complete: hand the stage back to the producer
         // (all earlier rounds were full, so the step index is 4*T*r + t*nb + b)
-        if (q == 0 && lane == 0) umma::mbar_arrive(&empty[(kAccBanks * T * r + t * nb + b) % stages]);
+        if (q == 0 && lane == 0) umma::mbar_arrive_relaxed(&empty[(kAccBanks * T * r + t * nb + b) % stages]);
         const int pc = t - (NT - 2);                              // the plane that completed with this step
         if (t + 1 < T) {
           unsigned pk[12];

@@ -30,6 +30,18 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrival without release semantics, for the epilogue's hand-overs (a TMEM accumulator back to the issuer, a shared-
+// memory stage back to the producer).  What those arrivals vouch for is ordered by other means -- the accumulator by
+// tcgen05.wait::st + tcgen05.fence::before_thread_sync, the stage by the commit that signalled the MMAs reading it
+// were done -- while a releasing arrival also waits until the thread's earlier GLOBAL stores (the previous plane's
+// output) are performed, which put an L2 round trip into every accumulator hand-over.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+#ifdef LC_ARRIVE_RELEASE
+  mbar_arrive(bar);
+#else
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+#endif
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
@@ -76,8 +88,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // arrival vouches for travels through the async proxy / TMEM fences, and .release.cluster measured ~1 us per arrival
 #ifdef LC_ARRIVE_RELEASE_CLUSTER
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-#else
+#elif defined(LC_ARRIVE_RELEASE)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 #endif
 }
 // Waiting for a barrier that another CTA (or the pair's multicast commit) arrives on

@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import math
 import pickle
+import os
 import struct
 from typing import List, Optional, Sequence, Tuple
 
@@ -701,6 +702,12 @@ def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=Non
     from . import _native as N
     from .lanes import LaneSet
     torch = N.require_cuda()
+    # One lane unless asked for more.  With NCCL, two lanes put collectives of two communicators in flight from two
+    # threads; a device-wide synchronisation inside one thread (a pinned or device allocation that misses the caches)
+    # then waits for the other lane's NCCL kernel, which waits for the peer rank, whose thread may be in the mirror
+    # situation -- observed as a hang on 2 GPUs.  The single-GPU entry points default to two lanes.
+    if lanes is None:
+        lanes = int(os.environ.get("LOSSYCOMP_SHARD_LANES", "1"))
     ls = LaneSet.get(model, precision, device, lanes).groups(group)
     eng = ls.lanes[0].eng
     copy = torch.cuda.Stream(device=eng.dev)

@@ -48,6 +48,8 @@ def _rank_main(rank, world, port, shape, abs_err, q):
         xl = full[t0:t1].cpu().numpy()
         blob = D.compress_sharded_host(xl, abs_err, t0=t0, T=T, precision="fp16", dst=dst)
         blobs = list(D.compress_sharded_stream([xl, xl, xl], abs_err, t0=t0, T=T, precision="fp16", dst=dst))
+        # two fields in flight (one process group per lane; gloo here -- see compress_sharded_stream on NCCL)
+        blobs += list(D.compress_sharded_stream([xl, xl, xl], abs_err, t0=t0, T=T, precision="fp16", dst=dst, lanes=2))
         a3, b3, rows3 = D.decompress_sharded_host(blob, precision="fp16", src=dst)
         a, b, rows = D.decompress_sharded(eng, slots, src=dst)                       # aligned: parts scattered
         assert (a, b) == (t0, t1)
@@ -67,11 +69,11 @@ def _rank_main(rank, world, port, shape, abs_err, q):
                 n_parts=len(D.unpack_multipart(slots[7])),
                 host_blob_equal=bool(pickle.loads(blob) == [bytes(v) if isinstance(v, (bytes, memoryview)) else v
                                                             for v in slots]),
-                stream_equal=bool(blobs == [blob] * 3),
+                stream_equal=bool(blobs == [blob] * 6),
                 types=[type(s).__name__ for s in slots])
             unaligned = ref                      # a single-part blob on two ranks: the broadcast + slice path
         else:
-            assert slots is None and slots2 is None and blob is None and blobs == [None] * 3
+            assert slots is None and slots2 is None and blob is None and blobs == [None] * 6
             unaligned = None
         res["host_rows_equal"] = bool((a3, b3) == (a, b) and np.array_equal(rows3[..., 0], rows.cpu().numpy()))
         a2, b2, rows2 = D.decompress_sharded(eng, unaligned, src=dst)
