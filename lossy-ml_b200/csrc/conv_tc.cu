@@ -89,6 +89,9 @@ struct SweepParams {
   const uint4* wimg2c1;
   int wimg2c_bytes, b2c_rows, stages2c;
   uint64_t b2c_desc[kMaxKs];
+  // sweep_acc_kernel: 1 = the epilogue stages every output plane in shared memory and writes it with bulk copies
+  // (needs the output planes in the input's row numbering: a tile's 128 rows are 128 consecutive output slots)
+  int tma_store;
 };
 
 // 12 consecutive accumulator columns of this thread's TMEM lane
@@ -273,31 +276,40 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 
   if (warp == 0) {
     // ===================== producer: bulk async copies (TMA engine) =====================
+    // The whole warp works: lane c issues copy c of a stage (input slabs first, then the skip tiles), lane 0 also
+    // waits for the stage and posts the byte count.  One thread issuing every copy of every stage was the slowest
+    // stage of the pipeline (its ~150 dependent scalar instructions per stage outlasted the MMAs of the stage).
     if (lane == 0) {
       umma::mbar_arrive_expect_tx(&wbar, (uint32_t)p.wimg_bytes);
       umma::bulk_g2s(sB, p.wimg, (uint32_t)p.wimg_bytes, &wbar);
-      int stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int n = item / per_chunk;
-        const int tile = (item - n * per_chunk) % p.tiles_per_chunk;
-        const long long slab0 = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start;
-        for (int t = 0; t < p.in_T; ++t) {
+    }
+    const int ncop = p.in_NPG + (p.skip_mma ? p.skip.G : 0);      // <= 32 (checked by the host)
+    const bool is_in = lane < p.in_NPG, act = lane < ncop;
+    const int cs = lane - p.in_NPG;                               // skip copy index
+    const uint32_t my_bytes = is_in ? (uint32_t)slab_bytes : (uint32_t)(p.skip_slots * 16);
+    const int my_dst = is_in ? lane * slab_bytes : p.in_NPG * slab_bytes + cs * p.skip_slots * 16;
+    const long long my_tstride = is_in ? (long long)p.in_NPG * p.in_S : (long long)p.skip.G * p.skip.S;
+    int stage = 0, phase = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int n = item / per_chunk;
+      const int tile = (item - n * per_chunk) % p.tiles_per_chunk;
+      const uint4* src;
+      if (is_in)
+        src = p.in + (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start +
+              (long long)lane * p.in_S;
+      else   // rows of this tile of the skip planes (same row numbering as the input planes)
+        src = reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride + p.skip.GL + p.row0 +
+              tile * 128 - p.skip_pad + (long long)cs * p.skip.S;
+      for (int t = 0; t < p.in_T; ++t) {
+        if (lane == 0) {
           umma::mbar_wait(&empty[stage], phase ^ 1);
-          if (p.debug & 8) { umma::mbar_arrive(&full[stage]); if (++stage == p.stages) { stage = 0; phase ^= 1; } continue; }
-          umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
-          for (int g = 0; g < p.in_NPG; ++g)
-            umma::bulk_g2s(sA + stage * stage_bytes + g * slab_bytes,
-                           p.in + slab0 + (long long)(t * p.in_NPG + g) * p.in_S, (uint32_t)slab_bytes,
-                           &full[stage]);
-          if (p.skip_mma) {   // rows of this tile of skip plane t (same row numbering as the input planes)
-            const uint4* sk = reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride +
-                              p.skip.GL + p.row0 + tile * 128 - p.skip_pad;
-            for (int g = 0; g < p.skip.G; ++g)
-              umma::bulk_g2s(sA + stage * stage_bytes + p.in_NPG * slab_bytes + g * p.skip_slots * 16,
-                             sk + (long long)(t * p.skip.G + g) * p.skip.S, (uint32_t)(p.skip_slots * 16), &full[stage]);
-          }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (p.debug & 8) umma::mbar_arrive(&full[stage]);
+          else umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
         }
+        __syncwarp();
+        if (act && !(p.debug & 8))
+          umma::bulk_g2s(sA + stage * stage_bytes + my_dst, src + (long long)t * my_tstride, my_bytes, &full[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 || warp == 10) {
@@ -733,6 +745,12 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
   const int skip_bytes = p.skip_mma ? p.skip.G * p.skip_slots * 16 : 0;
   const int stage_bytes = p.in_NPG * slab_bytes + skip_bytes;
   const int stages = (NCTA == 2) ? p.stages2c : p.stages2;
+  // Every bank owns its own ring of spb stages (stage = bank + kAccBanks * (kb % spb) for the bank's step kb, parity
+  // (kb / spb) & 1).  A ring shared by the banks is unsafe with parity waits: the two issuer warps each wait only for
+  // the stages of their own banks, so a stage's previous use may belong to the other issuer's bank, and when that load
+  // completes late (memory contention from a kernel of another stream) the barrier is still a whole phase behind, its
+  // parity equals that of the awaited phase's predecessor and the wait passes on stale data.
+  const int spb = stages / kAccBanks;
   const int wbytes = (NCTA == 2) ? p.wimg2c_bytes : p.wimg2_bytes;
   uint8_t* sB = smem;
   uint8_t* sA = smem + ((wbytes + 127) & ~127);
@@ -764,54 +782,60 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
 
   if (warp == 0) {
     // ===================== producer =====================
+    // Whole warp: lane 8*b + c issues copy c of bank b's stage (input slabs, then skip tiles; at most 8 copies per
+    // stage, checked by the host), lane 8*b also waits for the stage and posts the byte count -- the four banks'
+    // stages of one input plane are filled by one pass of the loop instead of four passes of a single thread.
+    static_assert(kAccBanks <= 4, "producer lanes are laid out for at most four banks");
     if (lane == 0) {
       umma::mbar_arrive_expect_tx(&wbar, (uint32_t)wbytes);
       umma::bulk_g2s(sB, (NCTA == 2) ? (leader ? p.wimg2c0 : p.wimg2c1) : p.wimg2, (uint32_t)wbytes, &wbar);
-      int stage = 0, phase = 0;
-      for (int r = 0; r < rounds; ++r) {
-        const int nb = min(kAccBanks, cnt - kAccBanks * r);
-        long long slab0[kAccBanks];
-        const uint4* sk0[kAccBanks];
-#pragma unroll
-        for (int b = 0; b < kAccBanks; ++b) {
-          const int item = min(item_of(kAccBanks * r + b), p.n_items - 1);
-          const int n = item / p.tiles_per_chunk;
-          const int tile = item - n * p.tiles_per_chunk;
-          slab0[b] = (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start;
-          sk0[b] = p.skip_mma ? reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride +
-                                    p.skip.GL + p.row0 + tile * 128 - p.skip_pad
-                              : nullptr;
+    }
+    const int ncop = p.in_NPG + (p.skip_mma ? p.skip.G : 0);
+    const int pb = lane >> 3, pc = lane & 7;
+    const bool is_in = pc < p.in_NPG;
+    const int cs = pc - p.in_NPG;
+    const uint32_t my_bytes = is_in ? (uint32_t)slab_bytes : (uint32_t)(p.skip_slots * 16);
+    const int my_dst = is_in ? pc * slab_bytes : p.in_NPG * slab_bytes + cs * p.skip_slots * 16;
+    const long long my_tstride = is_in ? (long long)p.in_NPG * p.in_S : (long long)p.skip.G * p.skip.S;
+    for (int r = 0; r < rounds; ++r) {
+      const int nb = min(kAccBanks, cnt - kAccBanks * r);
+      const bool act = pb < nb && pc < ncop;
+      const int item = min(item_of(kAccBanks * r + min(pb, nb - 1)), p.n_items - 1);
+      const int n = item / p.tiles_per_chunk;
+      const int tile = item - n * p.tiles_per_chunk;
+      const uint4* src;
+      if (is_in)
+        src = p.in + (long long)n * p.in_cs + p.in_GL + p.row0 + tile * p.row_step - p.row_shift + p.slab_start +
+              (long long)pc * p.in_S;
+      else
+        src = reinterpret_cast<const uint4*>(p.skip.base) + (long long)n * p.skip.chunk_stride + p.skip.GL + p.row0 +
+              tile * 128 - p.skip_pad + (long long)cs * p.skip.S;
+      for (int t = 0; t < T; ++t) {
+        const int kb = r * T + t;
+        const int stage = pb + kAccBanks * (kb % spb), phase = (kb / spb) & 1;
+        if (act && pc == 0) {
+          umma::mbar_wait(&empty[stage], phase ^ 1);
+          if (p.debug & 8) umma::mbar_arrive(&full[stage]);
+          else umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
         }
-        for (int t = 0; t < T; ++t) {
-          for (int b = 0; b < nb; ++b) {
-            umma::mbar_wait(&empty[stage], phase ^ 1);
-            if (p.debug & 8) { umma::mbar_arrive(&full[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
-            umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
-            uint8_t* dst = sA + stage * stage_bytes;
-            for (int g = 0; g < p.in_NPG; ++g)
-              umma::bulk_g2s(dst + g * slab_bytes, p.in + slab0[b] + (long long)(t * p.in_NPG + g) * p.in_S,
-                             (uint32_t)slab_bytes, &full[stage]);
-            if (p.skip_mma)
-              for (int g = 0; g < p.skip.G; ++g)
-                umma::bulk_g2s(dst + p.in_NPG * slab_bytes + g * p.skip_slots * 16,
-                               sk0[b] + (long long)(t * p.skip.G + g) * p.skip.S, (uint32_t)(p.skip_slots * 16),
-                               &full[stage]);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
-          }
-        }
+        __syncwarp();
+        if (act && !(p.debug & 8))
+          umma::bulk_g2s(sA + stage * stage_bytes + my_dst, src + (long long)t * my_tstride, my_bytes, &full[stage]);
       }
     }
   } else if (NCTA == 2 && !leader && warp == 1) {
     // ===================== peer CTA: relay "my stage is loaded" to the leader's full barrier =====================
     if (lane == 0) {
       umma::mbar_wait(&wbar, 0);                 // the first relayed arrival also vouches for this CTA's weights
-      int stage = 0, phase = 0;
       for (int r = 0; r < rounds; ++r) {
         const int nb = min(kAccBanks, cnt - kAccBanks * r);
-        for (int i = 0; i < T * nb; ++i) {
-          umma::mbar_wait(&full[stage], phase);
-          umma::mbar_arrive_cluster(umma::mapa_rank(&full[stage], 0));
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+        for (int t = 0; t < T; ++t) {
+          const int kb = r * T + t;
+          for (int b = 0; b < nb; ++b) {
+            const int stage = b + kAccBanks * (kb % spb);
+            umma::mbar_wait(&full[stage], (kb / spb) & 1);
+            umma::mbar_arrive_cluster(umma::mapa_rank(&full[stage], 0));
+          }
         }
       }
     }
@@ -821,8 +845,6 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
     umma::mbar_wait(&wbar, 0);
     const uint32_t idesc = umma::make_idesc(128 * NCTA, kBankCols, H16 ? 0 : 1);
     const uint64_t sA_add = (uint64_t)(umma::smem_u32(sA) >> 4), sB_add = (uint64_t)(umma::smem_u32(sB) >> 4);
-    int stage = 0, phase = 0, step = 0;
-    (void)step;
     for (int r = 0; r < rounds; ++r) {
       const int nb = min(kAccBanks, cnt - kAccBanks * r);
       for (int t = 0; t < T; ++t) {
@@ -831,7 +853,8 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
         const int i0 = (((NT - 2 - t) % NT) + NT) % NT;
         const uint64_t b_add = sB_add + (uint64_t)(i0 * 24);      // 24 rows of 16 bytes, in 16-byte units
         const int kb = r * T + t;                                 // this bank-step's index (all banks alike)
-        for (int b = 0; b < nb; ++b, ++step) {
+        for (int b = 0; b < nb; ++b) {
+          const int stage = b + kAccBanks * (kb % spb), phase = (kb / spb) & 1;
           // a bank always belongs to the same issuer: its steps must be issued in order, each after the epilogue
           // of the one before (alternating issuers by step would let one run a whole phase ahead of the other on
           // the same bank whenever the number of active banks is odd)
@@ -862,7 +885,6 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
             }
             __syncwarp();
           }
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -901,6 +923,10 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
       for (int i = 0; i < 12; ++i) pk[i] = pack2_t<H16, RELU>(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
     };
     const int G = p.out.G;
+    // Output staging (p.tma_store): [bank][2][3 groups][128 rows] 16-byte vectors behind the input stages.  A warp
+    // only touches its own 32 rows, so the hand-over to its bulk copies needs no block barrier.
+    uint4* const obuf = reinterpret_cast<uint4*>(sA + spb * kAccBanks * stage_bytes) + (b * 2) * (3 * 128);
+    int opar = 0;
     // every slot starts from the bias
 #pragma unroll
     for (int s = 0; s < NT; ++s) init_slot(s);
@@ -912,7 +938,34 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
       const RowInfo ri = row_info(p, item, row);
       const bool valid = ri.valid && item_raw < p.n_items && !(p.debug & 4);   // debug bit 2: no global stores
       const VoxPtr vp = vox_ptr(p, ri.n, ri.h, ri.w);
+      // first output vector of this warp's 32 rows in plane 0, group 0 (tma_store: output slot == row slot)
+      uint4* const warp_o = reinterpret_cast<uint4*>(p.out.base) + (long long)(item / p.tiles_per_chunk) * p.out.chunk_stride +
+                            p.out.GL + p.row0 + (item % p.tiles_per_chunk) * 128 + q * 32;
+      const bool item_ok = item_raw < p.n_items && !(p.debug & 4);
       auto store_plane = [&](int plane, const unsigned (&pk)[12]) {
+        if (p.tma_store) {
+          // rows outside the image are halo / guard slots of the output plane: they hold zeros and get zeros
+          if (lane == 0) umma::bulk_wait_read<1>();      // the copies that read this staging buffer two planes ago
+          __syncwarp();
+          uint4* buf = obuf + opar * (3 * 128) + row;
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          buf[0] = ri.valid ? make_uint4(pk[0], pk[1], pk[2], pk[3]) : z;
+          if (G > 1) buf[128] = ri.valid ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : z;
+          if (G > 2) buf[256] = ri.valid ? make_uint4(pk[8], pk[9], pk[10], pk[11]) : z;
+          umma::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (item_ok) {
+              const uint4* src = obuf + opar * (3 * 128) + q * 32;
+              uint4* dst = warp_o + (long long)plane * G * p.out.S;
+              for (int g = 0; g < G; ++g) umma::bulk_s2g(dst + (long long)g * p.out.S, src + g * 128, 512u);
+            }
+            umma::bulk_commit();
+          }
+          opar ^= 1;
+          return;
+        }
+        if (!valid) return;
         uint4* o = vp.o + (long long)plane * vp.o_t;
         o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         if (G > 1) o[vp.o_g] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -924,8 +977,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
         else umma::mbar_wait(&tfull[b], kb & 1);
         umma::tcgen05_fence_after();
         // the MMAs that read this step's stage are complete: hand the stage back to the producer
-        // (all earlier rounds were full, so the step index is 4*T*r + t*nb + b)
-        if (q == 0 && lane == 0) umma::mbar_arrive_relaxed(&empty[(kAccBanks * T * r + t * nb + b) % stages]);
+        if (q == 0 && lane == 0) umma::mbar_arrive_relaxed(&empty[b + kAccBanks * (kb % spb)]);
         const int pc = t - (NT - 2);                              // the plane that completed with this step
         if (t + 1 < T) {
           unsigned pk[12];
@@ -933,7 +985,7 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
           if (pc >= 0) load_pack(slot, pk);
           init_slot(slot);
           hand_back();
-          if (pc >= 0 && valid) store_plane(pc, pk);
+          if (pc >= 0) store_plane(pc, pk);
         } else {
           // last input plane: the remaining NT-1 planes are complete; all slots restart from the bias
           unsigned pk[NT - 1][12];
@@ -945,11 +997,12 @@ sweep_acc_kernel(const __grid_constant__ SweepParams p) {
           hand_back();
 #pragma unroll
           for (int j = 0; j < NT - 1; ++j)
-            if (pc + j >= 0 && valid) store_plane(pc + j, pk[j]);
+            if (pc + j >= 0) store_plane(pc + j, pk[j]);
         }
       }
     }
   }
+  if (p.tma_store && warp >= 4 && lane == 0) umma::bulk_wait_all();   // staging is read, outputs are written
   umma::tcgen05_fence_before();
   if (NCTA == 2) umma::cluster_sync_all();      // no CTA frees TMEM or exits while its partner still uses the pair
   else __syncthreads();
@@ -1291,7 +1344,7 @@ int launch_acc_variant(const SweepParams& p, int grid, int smem, cudaStream_t s)
   int dev = 0;
   LC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   sweep_acc_kernel<NT, H16, RELU, 1><<<grid, kAccThreads, smem, s>>>(p);
@@ -1321,7 +1374,7 @@ int launch_acc2_variant(const SweepParams& p, int n_items, int smem, cudaStream_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (!max_pairs[dev]) {
-    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    LC_CUDA(cudaFuncSetAttribute(sweep_acc_kernel<NT, H16, RELU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     cfg.gridDim = dim3(2);
     int n = 0;
     LC_CUDA(cudaOccupancyMaxActiveClusters(&n, sweep_acc_kernel<NT, H16, RELU, 2>, &cfg));
@@ -1340,14 +1393,13 @@ int launch_acc2_variant(const SweepParams& p, int n_items, int smem, cudaStream_
   return LC_OK;
 }
 
-// LOSSYCOMP_ACC_CTA2=1 runs these layers in the CTA-pair form.  Off by default: measured on the benchmark field the
-// pair form is within 2 % of the single-CTA form (0.874 vs 0.890 ms on the 3x3x3 layers, 0.590 vs 0.574 ms on the
-// first layer) -- halving the B fetch does not move a kernel whose operand traffic is 4 KB of A per 1.25 KB of B.
+// LOSSYCOMP_ACC_CTA2=0 keeps these layers on the single-CTA form.  Measured on the benchmark field (with the warp-wide
+// producer): 3x3x3 layers 0.897 -> 0.852 ms, with a residual input 1.18 -> 0.98 ms, first layer 0.53 -> 0.54 ms.
 bool acc_cta2_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("LOSSYCOMP_ACC_CTA2");
-    on = e ? (atoi(e) != 0) : 0;
+    on = e ? (atoi(e) != 0) : 1;
   }
   return on != 0;
 }
@@ -1565,6 +1617,10 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   p.nvar = (int)groups.size();
   const int ngroups = (int)groups[0].size();
   p.nks = (ngroups + 1) / 2;
+  if (p.in_NPG + (p.skip_mma ? G : 0) > 32) {
+    lc_set_error("layer %d: %d bulk copies per stage exceed the producer warp", i, p.in_NPG + (p.skip_mma ? G : 0));
+    return LC_EUNSUPPORTED;
+  }
   if (p.nks > kMaxKs || p.nvar > kMaxVar) {
     lc_set_error("layer %d: %d K steps / %d variants exceed the kernel tables", i, p.nks, p.nvar);
     return LC_EUNSUPPORTED;
@@ -1631,12 +1687,12 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   lp.d_wimg2 = nullptr;
   lp.acc2_smem_bytes = 0;
   lp.d_wimg2c[0] = lp.d_wimg2c[1] = nullptr;
-  // Layers with a residual input stay on sweep_tc_kernel unless LOSSYCOMP_ACC_SKIP=1: they are bound by HBM traffic
-  // (input + skip tile + output, 5.1 GB per launch on the benchmark field) rather than by the shared-memory operand
-  // fetch, and measured 4 % slower in the four-banks-per-SM form (1.17 vs 1.12 ms).
-  const bool acc_ok = !L.res_add || (p.skip_mma && getenv("LOSSYCOMP_ACC_SKIP") && atoi(getenv("LOSSYCOMP_ACC_SKIP")));
+  // Layers with a residual input run on sweep_acc_kernel too (LOSSYCOMP_ACC_SKIP=0: back to sweep_tc_kernel's register
+  // fold).  Measured on the benchmark field: register fold 1.12 ms, accumulate form 1.17 ms with a single-thread producer
+  // and one CTA per tile set, 0.98 ms with the warp-wide producer and CTA pairs.
+  const bool acc_ok = !L.res_add || (p.skip_mma && !(getenv("LOSSYCOMP_ACC_SKIP") && !atoi(getenv("LOSSYCOMP_ACC_SKIP"))));
   const bool acc_mode = mode == MODE_K3 || (mode == MODE_K4 && L.pad_lo == 1 && !getenv("LOSSYCOMP_NO_ACC_K4"));
-  if (acc_mode && acc_ok && cout <= 24 && !getenv("LOSSYCOMP_NO_ACC")) {
+  if (acc_mode && acc_ok && cout <= 24 && p.in_NPG + (p.skip_mma ? G : 0) <= 8 && !getenv("LOSSYCOMP_NO_ACC")) {
     // weight image of sweep_acc_kernel: per 8-channel K group, the NT time blocks twice in decreasing order
     // ([dt = NT-1 .. 0, NT-1 .. 1], 24 rows each) so that a start offset of i0 blocks rotates them onto the TMEM
     // slots; padded to the rows the widest start (NT-1 blocks in) reads with N = bank columns
@@ -1682,10 +1738,18 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
     LC_CUDA(cudaMalloc(&lp.d_wimg2, img2.size() * 2));
     LC_CUDA(cudaMemcpy(lp.d_wimg2, img2.data(), img2.size() * 2, cudaMemcpyHostToDevice));
     p.wimg2 = reinterpret_cast<const uint4*>(lp.d_wimg2);
-    const int fixed2 = ((p.wimg2_bytes + 127) & ~127) + 256;
-    int st2 = (200 * 1024 - fixed2) / stage_bytes;
+    // Output staging for the bulk-copy epilogue (LOSSYCOMP_TMA_STORE=1; needs the output planes in the rows' own slot
+    // numbering).  Off by default: measured equal to the per-thread 16-byte stores (0.868 vs 0.849 ms on the 3x3x3
+    // layers in pair form) while its 48 KB of staging cost input stages.
+    p.tma_store = (mode == MODE_K3 && tout.fmt == FMT_GP16 && tout.layout == LAYOUT_PLAIN && tout.PW == tin.PW &&
+                   tout.G <= 3 && getenv("LOSSYCOMP_TMA_STORE") && atoi(getenv("LOSSYCOMP_TMA_STORE"))) ? 1 : 0;
+    const int ostage = p.tma_store ? kAccBanks * 2 * 3 * 128 * 16 : 0;
+    const int kAccSmem = 225 * 1024;
+    const int fixed2 = ((p.wimg2_bytes + 127) & ~127) + 256 + ostage;
+    int st2 = (kAccSmem - fixed2) / stage_bytes;
     if (st2 > kAccMaxStages) st2 = kAccMaxStages;
     if (getenv("LOSSYCOMP_ACC_STAGES")) st2 = atoi(getenv("LOSSYCOMP_ACC_STAGES"));
+    st2 -= st2 % kAccBanks;                  // every bank owns stages / kAccBanks of them
     if (st2 >= 4) {
       p.stages2 = st2;
       lp.acc_smem_bytes = fixed2 + st2 * stage_bytes;
@@ -1717,10 +1781,11 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
       }
       p.wimg2c0 = reinterpret_cast<const uint4*>(lp.d_wimg2c[0]);
       p.wimg2c1 = reinterpret_cast<const uint4*>(lp.d_wimg2c[1]);
-      const int fixedc = ((p.wimg2c_bytes + 127) & ~127) + 256;
-      int stc = (200 * 1024 - fixedc) / stage_bytes;
+      const int fixedc = ((p.wimg2c_bytes + 127) & ~127) + 256 + ostage;
+      int stc = (kAccSmem - fixedc) / stage_bytes;
       if (stc > kAccMaxStages) stc = kAccMaxStages;
       if (getenv("LOSSYCOMP_ACC_STAGES")) stc = atoi(getenv("LOSSYCOMP_ACC_STAGES"));
+      stc -= stc % kAccBanks;
       p.stages2c = stc;
       lp.acc2_smem_bytes = (stc >= 4 && lp.acc_smem_bytes > 0 && bank_cols % 16 == 0) ? fixedc + stc * stage_bytes : 0;
     }
@@ -1730,6 +1795,9 @@ static int build_sweep(lc_codec* h, TcPlan* P, int i, int mode, const TensorPlan
   const int fixed = ((p.wimg_bytes + 127) & ~127) + 256;
   int stages = (budget - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  // an even ring: the two issuer warps take alternate steps, so with an odd ring a stage's previous use belongs to the
+  // other issuer, whose wait this issuer never saw -- the same parity aliasing sweep_acc_kernel's private rings avoid
+  if (stages > 2) stages -= stages % 2;
   if (stages < 2) {
     lc_set_error("layer %d: tensor-core kernel does not fit shared memory (%d + n*%d)", i, fixed, stage_bytes);
     return LC_EUNSUPPORTED;

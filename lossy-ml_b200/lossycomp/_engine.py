@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import bz2
 import ctypes as C
+import contextlib
 import hashlib
 import json
 import math
@@ -35,8 +36,9 @@ RLE_GATE = 0.2                  # zero-run tokens of the mask are only tried whe
 # Revision of the autoencoder kernels' arithmetic (summation order, rounding points).  The error bound only
 # holds when the decoder reproduces the compressor's reconstruction bit for bit, so blobs record the
 # revision they were written with and a build with different arithmetic refuses them.
-NUMERICS_REV = 4      # 2: bias folded into the first block of a plane; 3: residual add inside the MMA accumulation;
-# 4: the 3x3x3 layers accumulate their time taps in TMEM starting from the bias (sweep_acc_kernel)
+NUMERICS_REV = 5      # 2: bias folded into the first block of a plane; 3: residual add inside the MMA accumulation;
+# 4: the 3x3x3 layers accumulate their time taps in TMEM starting from the bias (sweep_acc_kernel); 5: so do the
+# 3x3x3 layers with a residual input
 # chunks per convolution launch: large batches amortise kernel prologues and tails (900 chunks x 19 tiles =
 # 57.8 waves of the 296 resident CTAs); the activation workspace is 19.4 MB per chunk
 DEFAULT_BATCH = int(os.environ.get("LOSSYCOMP_BATCH", "1024"))
@@ -175,6 +177,14 @@ class Engine:
             side = self._small["side_stream"] = self.torch.cuda.Stream(device=self.dev)
         return side
 
+    def _turn(self):
+        """Context of one autoencoder pass.  Engines that share a device through lossycomp.lanes take turns on the
+        GPU for these passes (self.turn, a lanes.GpuTurn): the persistent convolution kernels want every SM (and
+        whole SM pairs), so two passes running against each other only fragment the machine; what the lanes
+        overlap is one field's host round trips and small kernels with the other field's convolutions."""
+        turn = getattr(self, "turn", None)
+        return turn.section(self) if turn is not None else contextlib.nullcontext()
+
     def _ae_ws(self, n_chunks):
         if self._ws is None or self._ws_chunks < n_chunks:
             nbytes = self.lib.lc_ae_workspace_bytes(self.h, n_chunks)
@@ -239,12 +249,13 @@ class Engine:
         batch = min(batch or DEFAULT_BATCH, n)
         latent = self.torch.empty((n, self.latent_floats), dtype=self.torch.float32, device=self.dev)
         ws = self._ae_ws(batch)
-        for b in range(0, n, batch):
-            c = min(batch, n - b)
-            N.check(self.lib.lc_encode(self.h, _ptr(x), T, H, W, Cc, float(mean), float(std), b, c,
-                                       C.c_void_p(latent.data_ptr() + b * self.latent_floats * 4),
-                                       _ptr(ws), ws.numel(), self._stream()), "lc_encode")
-            self.launches += 1 + len(self.model.encoder)
+        with self._turn():
+            for b in range(0, n, batch):
+                c = min(batch, n - b)
+                N.check(self.lib.lc_encode(self.h, _ptr(x), T, H, W, Cc, float(mean), float(std), b, c,
+                                           C.c_void_p(latent.data_ptr() + b * self.latent_floats * 4),
+                                           _ptr(ws), ws.numel(), self._stream()), "lc_encode")
+                self.launches += 1 + len(self.model.encoder)
         return latent
 
     def decode(self, latent, T, H, W, batch=None):
@@ -254,12 +265,13 @@ class Engine:
         batch = min(batch or DEFAULT_BATCH, n)
         recon = self.torch.empty((T, H, W), dtype=self.torch.float32, device=self.dev)
         ws = self._ae_ws(batch)
-        for b in range(0, n, batch):
-            c = min(batch, n - b)
-            N.check(self.lib.lc_decode(self.h, C.c_void_p(latent.data_ptr() + b * self.latent_floats * 4),
-                                       T, H, W, b, c, _ptr(recon), _ptr(ws), ws.numel(), self._stream()),
-                    "lc_decode")
-            self.launches += 1 + len(self.model.decoder)
+        with self._turn():
+            for b in range(0, n, batch):
+                c = min(batch, n - b)
+                N.check(self.lib.lc_decode(self.h, C.c_void_p(latent.data_ptr() + b * self.latent_floats * 4),
+                                           T, H, W, b, c, _ptr(recon), _ptr(ws), ws.numel(), self._stream()),
+                        "lc_decode")
+                self.launches += 1 + len(self.model.decoder)
         return recon
 
     def quantize(self, x, recon, mean, std, thr, check_abs_err=None):

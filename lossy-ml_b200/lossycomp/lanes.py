@@ -12,7 +12,9 @@ fields in flight never share a communicator and each communicator sees its calls
 """
 from __future__ import annotations
 
+import contextlib
 import os
+import threading
 from concurrent.futures import Future, ThreadPoolExecutor
 from typing import Dict, List, Optional
 
@@ -20,6 +22,30 @@ from . import _native as N
 from ._engine import DEFAULT_PRECISION, Engine
 
 DEFAULT_LANES = 2
+
+
+class GpuTurn:
+    """Serialises the autoencoder passes of the lanes of one device.  A pass holds the host lock only while its
+    kernels are being enqueued (they are asynchronous); on the GPU it starts after the event the previous pass left
+    behind, whichever lane that was."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._last = None
+
+    @contextlib.contextmanager
+    def section(self, eng):
+        torch = eng.torch
+        with self._lock:
+            stream = torch.cuda.current_stream(eng.dev)
+            if self._last is not None:
+                stream.wait_event(self._last)
+            try:
+                yield
+            finally:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                self._last = ev
 
 
 class Lane:
@@ -61,6 +87,10 @@ class LaneSet:
 
     def __init__(self, engines: List[Engine]):
         self.lanes = [Lane(e, i) for i, e in enumerate(engines)]
+        if len(engines) > 1 and os.environ.get("LOSSYCOMP_LANE_TURNS", "1") != "0":
+            turn = GpuTurn()
+            for e in engines:
+                e.turn = turn
         self._next = 0
         self._groups_of = None
 

@@ -77,3 +77,42 @@ def test_decompress_stream_equals_decompress(torch, lanes):
     res = list(decompress_stream(blobs, lanes=lanes, outs=outs))
     assert all(r is o or r.base is o for r, o in zip(res, outs)) and all(np.array_equal(o, w) for o, w in zip(outs, want))
     assert list(decompress_stream([], lanes=lanes)) == []
+
+
+def test_two_lanes_under_load_reproduce_the_single_lane_results(torch):
+    """Regression test of the stage-ring parity aliasing in sweep_acc_kernel: with the banks of a CTA sharing one ring
+    of input stages, a load delayed by the OTHER lane's memory traffic let an issuer warp pass a parity wait one phase
+    early and multiply stale data (a few tiles of the last chunks came out a few half-precision ulps off, roughly once
+    in 600 fields, only with two fields in flight).  60 compressions and 60 decompressions of a 24 x 336 x 720 field,
+    two in flight: latent, reconstruction, mask and codes must equal the single-lane ones every time."""
+    from lossycomp import _native as N
+    from lossycomp.compress import compress_device
+    from lossycomp.decompress import decompress_device
+    from lossycomp.lanes import LaneSet
+    ls = LaneSet.get(None, "fp16", 0, 2)
+    eng = ls.lanes[0].eng
+    T, H, W = 24, 336, 720
+    x = torch.empty((T, H, W, 2), dtype=torch.float32, device="cuda")
+    N.check(eng.lib.lc_synth_field(x.data_ptr(), T, H, W, 0, 0, 99, None), "synth")
+    torch.cuda.synchronize()
+    slots, rinfo = compress_device(eng, x, 0.1, return_parts=True)
+    want = {k: rinfo[k].clone() for k in ("latent", "recon_std", "mask", "q")}
+    ref = decompress_device(eng, slots).clone()
+    torch.cuda.synchronize()
+
+    def cjob(lane):
+        s, info = compress_device(lane.eng, x, 0.1, return_parts=True)
+        bad = [k for k in want if info[k].shape != want[k].shape or not bool(torch.equal(info[k], want[k]))]
+        return bad + [i for i in (0, 6, 7) if s[i] != slots[i]]
+
+    def djob(lane):
+        out = decompress_device(lane.eng, slots)
+        ok = bool(torch.equal(out, ref))
+        torch.cuda.current_stream(lane.eng.dev).synchronize()
+        return [] if ok else ["xhat"]
+
+    jobs = []
+    for i in range(60):
+        jobs += [ls.submit(cjob), ls.submit(djob)]
+    for i, j in enumerate(jobs):
+        assert j.result() == [], (i, j.result())
