@@ -710,8 +710,9 @@ sweep_tc_kernel(const __grid_constant__ SweepParams p) {
 //   * one persistent CTA per SM with kAccBanks tiles in flight (bank b = tile 4r+b of the CTA, input planes
 //     interleaved plane by plane): while the epilogue of one bank drains, the tensor pipe works on the other three,
 //     the weights sit in shared memory once per SM, and 8-12 stages of input planes are in flight.
-// Warps: 0 producer (bulk copies), 1-2 MMA issuers (alternate steps), 3 TMEM allocation, 4.. epilogue (bank =
-// (warp-4)/4, TMEM lane quarter = warp % 4).  Deterministic: fixed accumulation order per output voxel.
+// Warps: 0 producer (the whole warp: lane 8*b + c issues bulk copy c of bank b's stage), 1-2 MMA issuers (banks 0/2 and
+// 1/3), 3 TMEM allocation, 4.. epilogue (bank = (warp-4)/4, TMEM lane quarter = warp % 4).  Every bank owns its own
+// ring of input stages.  Deterministic: fixed accumulation order per output voxel.
 #ifndef LC_ACC_BANKS
 #define LC_ACC_BANKS 4
 #endif
