@@ -58,13 +58,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded: a pipeline bug (a barrier nobody arrives on) must not hang the GPU until the watchdog kills the
-// process.  try_wait suspends the thread for a hardware-defined time slice (measured: ~4 us per unsuccessful
-// slice), so 2^21 slices are ~8 s -- three orders of magnitude beyond any legitimate wait of these kernels; then
-// the thread traps, the launch fails with an error the host reports, and the box survives.
+// process.  The bound is elapsed time (~10 s of SM clock, read every 4096 unsuccessful polls), not a poll count: how
+// long an unsuccessful try_wait suspends the thread is hardware-defined (~4 us when measured alone, much less for
+// lanes spinning in a diverged warp), and no legitimate wait of these kernels lasts milliseconds.  Then the thread
+// traps, the launch fails with an error the host reports, and the box survives.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 21)) asm volatile("trap;");
+    if ((++spins & 0xfffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000LL) asm volatile("trap;");
+    }
   }
 }
 
