@@ -546,6 +546,9 @@ def run_ours(args):
     traffic, traffic_src = measured_traffic(dom_name, chunks_per_launch)
     roofline = {
         "bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "kernel_note": "layer groups are named after their convolution mode; the K3 group = the four 3x3x3 layers, which "
+                       "run on sweep_acc_kernel<3> (time taps accumulated in TMEM, tcgen05.mma.cta_group::2 on SM pairs) "
+                       "unless LOSSYCOMP_NO_ACC / LOSSYCOMP_ACC_CTA2=0 say otherwise; K4 = first layer, same kernel",
         "frac": (achieved / peak) if achieved else None,
         "frac_of_burst_peak": (achieved / burst) if achieved else None, "burst_peak": burst,
         "traffic": traffic,
