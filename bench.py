@@ -612,6 +612,26 @@ def run_ours(args):
             "gpu_strict_mode_huff_codec": nb / len(compress(xs, ABS_ERR, precision=args.precision, codec="huff")),
             "input": "oracle.synthetic_field%s, abs_err %g" % (str(CPU_SAMPLE), ABS_ERR)}
         line["cf_same_input"] = e2e["cf_same_input"]
+        # BASELINE configs[3] in small: three variables (temperature; a humidity-like field of small positive values;
+        # a geopotential-like field of large values) x the abs_err sweep, relative to each variable's spread; every
+        # round trip is checked element by element on the host
+        sweep = {}
+        base = xs[..., 0].astype(np.float64)
+        sd = float(base.std())
+        variables = {"temperature": (1.0, 0.0), "humidity_like": (2.5e-3 / sd, -float(base.min()) * 2.5e-3 / sd + 1e-4),
+                     "geopotential_like": (3.0e3 / sd, 5.0e4)}
+        for vname, (scale, offset) in variables.items():
+            xv = np.array(xs)
+            xv[..., 0] = (base * scale + offset).astype(np.float32)
+            for rel in (1e-3, 1e-2, 0.1, 0.3, 1.0):
+                thr = float(rel * scale)                       # the sweep's abs_err in the variable's own units
+                bl = compress(xv, thr, precision=args.precision, codec=args.codec)
+                xr = decompress(bl)
+                err = np.abs(xv[..., 0].astype(np.float64) - xr[..., 0])
+                sweep[f"{vname}@{rel:g}"] = {"abs_err": thr, "compression_factor": nb / len(bl),
+                                             "violations": int((err > thr).sum()), "max_abs_err": float(err.max())}
+        e2e["variable_sweep"] = sweep
+        e2e["variable_sweep_violations"] = int(sum(v["violations"] for v in sweep.values()))
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))
