@@ -260,46 +260,69 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         return float(tms.item())
 
-    # Fields in flight: consecutive steps run in alternating lanes (engine + stream + host thread each), so the
-    # kernels of one field fill the host round trips of the other.  Lane 0 is `eng`.
+    # Fields in flight.  N = 1: consecutive steps run in alternating lanes (engine + stream + host thread each), so the
+    # kernels of one field fill the host round trips of the other.  N > 1: the same overlap as a software pipeline in
+    # THIS thread -- field k+1 is begun (statistics all-reduce, encoder, decoder, quantiser enqueued on the other
+    # engine) before field k is finished (verdict, Huffman tables, NCCL gather) -- so that every collective is issued
+    # by one thread in the same order on every rank.  Lane 0 is `eng`.
     from lossycomp.lanes import LaneSet, n_lanes
-    # N > 1 runs one field at a time unless --lanes says otherwise (two NCCL communicators driven from two threads
-    # deadlocked on 2 GPUs; see lossycomp.dist.compress_sharded_stream)
-    lanes = LaneSet.get(None, args.precision, local, n_lanes(args.lanes) if (world == 1 or args.lanes) else 1)
-    if world > 1:
-        lanes.groups()
+    lanes = LaneSet.get(None, args.precision, local, n_lanes(args.lanes))
 
     def job(lane):
-        if world == 1:
-            return compress_device(lane.eng, x, ABS_ERR, mode="strict", codec=args.codec)
-        # rank dst gets a PendingBlob: the gathered blob's device->host copy (copy stream) and its assembly (host
-        # thread) overlap the following kernels; the timed region ends when every step's blob is complete
-        out = LD.compress_sharded(lane.eng, x, ABS_ERR, t0=t0r, T=T, mode="strict", codec=args.codec,
-                                  group=lane.group, dst=dst, wait=False)
-        torch.cuda.current_stream(lane.eng.dev).synchronize()      # this rank's share of the field is done
-        return out
-
-    def step():
-        return lanes.submit(job)
+        return compress_device(lane.eng, x, ABS_ERR, mode="strict", codec=args.codec)
 
     def finish(fut):
         out, info = fut.result()
         return (out.result() if hasattr(out, "result") else out), info
 
-    def run_steps(k):
+    def sharded_begin(lane):
+        with torch.cuda.stream(lane.stream):
+            return LD.compress_sharded_begin(lane.eng, x, ABS_ERR, t0=t0r, T=T, mode="strict", codec=args.codec)
+
+    def sharded_finish(lane, st):
+        # rank dst gets a PendingBlob: the gathered blob's device->host copy (copy stream) and its assembly (host
+        # thread) overlap the following kernels; the timed region ends when every step's blob is complete
+        with torch.cuda.stream(lane.stream):
+            out, info = LD.compress_sharded_finish(st, dst=dst, wait=False)
+            torch.cuda.current_stream(lane.eng.dev).synchronize()      # this rank's share of the field is done
+        return out, info
+
+    def run_steps(k, one_lane=False):
         """k steps, at most one per lane in flight; -> (slots, info) of the last one.  Results are not hoarded:
-        step j's blob is collected (and dropped) as soon as step j + lanes has been submitted."""
-        inflight, last = [], (None, None)
-        for _ in range(k):
-            inflight.append(step())
-            while len(inflight) > len(lanes):
+        step j's blob is collected (and dropped) while the steps after it run."""
+        L = 1 if one_lane else len(lanes)
+        last = (None, None)
+        if world == 1:
+            inflight = []
+            for i in range(k):
+                inflight.append(lanes.lanes[i % L].submit(job))
+                while len(inflight) > L:
+                    last = finish(inflight.pop(0))
+            while inflight:
                 last = finish(inflight.pop(0))
-        while inflight:
-            last = finish(inflight.pop(0))
+            return last
+        open_fields, pending = [], []
+        for i in range(k):
+            lane = lanes.lanes[i % L]
+            open_fields.append((lane, sharded_begin(lane)))
+            while len(open_fields) > L - 1:
+                pending.append(sharded_finish(*open_fields.pop(0)))
+            while len(pending) > 1:
+                out, info = pending.pop(0)
+                last = (out.result() if hasattr(out, "result") else out, info)
+        while open_fields:
+            pending.append(sharded_finish(*open_fields.pop(0)))
+        while pending:
+            out, info = pending.pop(0)
+            last = (out.result() if hasattr(out, "result") else out, info)
         return last
 
-    for _ in range(len(lanes)):          # every lane once on its own (allocations, communicators), then together
-        slots, info = finish(step())
+    for i in range(len(lanes)):          # every lane once on its own (allocations), then together
+        if world == 1:
+            slots, info = finish(lanes.lanes[i].submit(job))
+        else:
+            out, info = sharded_finish(lanes.lanes[i], sharded_begin(lanes.lanes[i]))
+            slots = out.result() if hasattr(out, "result") else out
     slots, info = run_steps(max(args.warmup, 1))
     sampler = ClockSampler(local)
     if rank == 0:
@@ -327,8 +350,7 @@ def run_ours(args):
     eng.profile_read()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    for _ in range(args.steps):
-        finish(lanes.lanes[0].submit(job))
+    run_steps(args.steps, one_lane=True)
     s1.record()
     barrier()
     seq_ms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
@@ -580,8 +602,10 @@ def run_ours(args):
         "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic",
         "config": workload_config(world, T, H, W, n_chunks_all, args.codec, args.precision, my_bytes, dst),
         "lanes": {"fields_in_flight_per_gpu": len(lanes), "one_field_at_a_time_ms_per_step": seq_ms,
-                  "note": "lossycomp.lanes: consecutive steps run in alternating lanes (engine + stream + host thread "
-                          "each), the kernels of one field fill the host round trips of the other; every field is "
+                  "note": "lossycomp.lanes: consecutive steps alternate between engines (own stream, workspace, staging "
+                          "buffers) so that the kernels of one field fill the host round trips of the other; N = 1: one "
+                          "host thread per lane; N > 1: a software pipeline in one thread (begin field k+1, then "
+                          "finish field k) so that all collectives keep one order on every rank; every field is "
                           "compressed by the single-lane code and the blobs are identical"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": e2e,

@@ -279,6 +279,10 @@ class Engine:
         the float32 forms are made here exactly as NumPy makes them.  Sync (reads the count).
         With check_abs_err the same pass also decodes every element the way reconstruct() will and
         returns (mask, q, violations of |x - xhat| <= check_abs_err, max |x - xhat|)."""
+        return self.quantize_result(self.quantize_launch(x, recon, mean, std, thr, check_abs_err))
+
+    def quantize_launch(self, x, recon, mean, std, thr, check_abs_err=None):
+        """The kernel of quantize() without its host sync: -> pending tuple for quantize_result()."""
         T, H, W, Cc = x.shape
         n = T * H * W
         mask = self.torch.empty(n, dtype=self.torch.int8, device=self.dev)
@@ -292,13 +296,19 @@ class Engine:
             N.check(self.lib.lc_quantize(_ptr(x), Cc, _ptr(recon), n, float(mean), float(std), float(thr32),
                                          float(thr2_32), _ptr(mask), _ptr(q), _ptr(cnt), _ptr(ws), self._stream()),
                     "lc_quantize")
-            n_out = int(cnt.item())
-            return mask, q[:n_out]
+            return (mask, q, cnt, False)
         out3 = self.torch.empty(3, dtype=self.torch.int64, device=self.dev)
         N.check(self.lib.lc_quantize_checked(_ptr(x), Cc, _ptr(recon), n, float(mean), float(std), float(thr32),
                                              float(thr2_32), float(thr * 2.0), float(check_abs_err), _ptr(mask),
                                              _ptr(q), _ptr(out3), _ptr(ws), self._stream()), "lc_quantize_checked")
-        n_out, viol, bits = out3.cpu().tolist()
+        return (mask, q, out3, True)
+
+    def quantize_result(self, pending):
+        """Sync: (mask, q[:n_out]) or, for the checked form, (mask, q[:n_out], violations, max |x - xhat|)."""
+        mask, q, out, checked = pending
+        if not checked:
+            return mask, q[:int(out.item())]
+        n_out, viol, bits = out.cpu().tolist()
         return mask, q[:n_out], int(viol), struct.unpack("<d", struct.pack("<q", bits))[0]
 
     def reconstruct(self, recon, mask, q, mean, std, thr2):

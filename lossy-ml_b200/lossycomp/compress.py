@@ -106,7 +106,21 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     reports a bound violation in info["violations"] instead of widening the band and quantising again
     (dist.compress_sharded makes that decision for all ranks together).  as_blob: return the finished blob (bytes,
     what compress() returns) in place of the slot list -- the entropy payloads are then copied from the device straight
-    into it."""
+    into it.
+
+    = compress_finish(compress_begin(...)): begin enqueues everything up to and including the quantiser without
+    waiting for it, finish needs the host (outlier count, verdict, Huffman tables, payloads).  A caller with several
+    fields may begin the next one (on another engine) before it finishes this one."""
+    st = compress_begin(eng, x, err_threshold, mode=mode, codec=codec, verify=verify, inject=inject,
+                        latent_codec=latent_codec, batch=batch, timing=timing, guard_scale=guard_scale)
+    return compress_finish(st, return_parts=return_parts, device_out=device_out, retry=retry, as_blob=as_blob)
+
+
+def compress_begin(eng: Engine, x, err_threshold, *, mode="strict", codec="huff", verify=None, inject=None,
+                   latent_codec=None, batch=None, timing=False, guard_scale=1.0):
+    """First half of compress_device(): statistics (one host sync unless they are injected), encoder, latent
+    rounding, decoder and the quantiser's launch, all enqueued on the current stream.  Returns the state for
+    compress_finish()."""
     assert err_threshold != 0, "The absolute error can't be 0."                      # compress.py:34
     assert x.dim() == 4 and x.shape[3] == eng.model.arch.in_channels, \
         "Input should have %d channels." % eng.model.arch.in_channels                # compress.py:55
@@ -114,16 +128,19 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     inject = inject or {}
     abs_err = float(err_threshold)
     tm = _StageTimer(eng) if timing else None
-    mean, std, max_abs = eng.stats(x)                                                # compress.py:64-65
+    if "mean" in inject and "max_abs" in inject:     # global statistics of a time-sharded field: nothing to reduce here
+        mean, std, max_abs = np.float32(inject["mean"]), np.float32(inject["std"]), float(inject["max_abs"])
+    else:
+        mean, std, max_abs = eng.stats(x)                                            # compress.py:64-65
+        if "mean" in inject:             # parity tests
+            mean, std = np.float32(inject["mean"]), np.float32(inject["std"])
     tm and tm.mark("stats")
-    if "mean" in inject:                 # parity tests / global statistics of a time-sharded field
-        mean, std = np.float32(inject["mean"]), np.float32(inject["std"])
-        max_abs = float(inject.get("max_abs", max_abs))
     if latent_codec is None:
         # "f16": latent quantised to half precision + Huffman (16-bit engines); compat codec: lossless host coder
         # for the latent too (fpzip's role, compress.py:144); fp32 engine: raw fp32
         latent_codec = "bz2" if codec == "bz2" else ("f16" if eng.precision != "fp32" else "raw")
     latent = eng.encode(x, mean, std, batch=batch)                                   # compress.py:66-86
+    planes = staged = None
     if latent_codec == "f16":
         planes = eng.quantize_latent(latent)     # in place: the decoder below consumes the rounded latent
     else:
@@ -133,21 +150,39 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         recon = inject["recon_std"]
     else:
         recon = eng.decode(latent, T, H, W, batch=batch)                             # compress.py:99-111
-    comp_data = None
-    if latent_codec == "f16":
-        comp_data = eng.pack_latent_f16(*planes, device_out=device_out)              # side stream, behind the decoder
     tm and tm.mark("decode")
     thr = abs_err
-    info = {"mode": mode, "codec": codec}
     if mode == "strict":
         g = _guard(max_abs, abs_err) * float(guard_scale)
         assert abs_err > 2 * g, "abs_error is below the float32 resolution of the data"
         thr = abs_err - g
     elif mode != "parity":
         raise ValueError("mode must be 'strict' or 'parity'")
+    if codec not in ("huff", "bz2"):
+        raise ValueError("codec must be 'huff' or 'bz2'")
     # verify: None/True = bound check fused into the quantisation pass (strict mode's default);
     # "full" = run the decoder's reconstruct kernel and an independent fp64 comparison; False = none
     verify = (mode == "strict") if verify is None else verify
+    pending = None
+    if verify != "full":       # launched here, read in compress_finish()
+        pending = eng.quantize_launch(x, recon, mean, std, thr, check_abs_err=abs_err if verify else None)
+    return dict(eng=eng, x=x, abs_err=abs_err, mode=mode, codec=codec, verify=verify, latent_codec=latent_codec,
+                mean=mean, std=std, thr=thr, latent=latent, planes=planes, staged=staged, recon=recon,
+                pending=pending, tm=tm)
+
+
+def compress_finish(st, *, return_parts=False, device_out=False, retry=True, as_blob=False):
+    """Second half of compress_device(): latent packing (side stream), the quantiser's result (strict mode: verdict,
+    wider guard band and another pass on a violation), entropy coding, the slot list / blob."""
+    eng, x, abs_err, mode, codec, verify = st["eng"], st["x"], st["abs_err"], st["mode"], st["codec"], st["verify"]
+    latent_codec, mean, std, thr, latent, recon, tm = (st["latent_codec"], st["mean"], st["std"], st["thr"],
+                                                       st["latent"], st["recon"], st["tm"])
+    T, H, W, _ = x.shape
+    comp_data = None
+    if latent_codec == "f16":
+        comp_data = eng.pack_latent_f16(*st["planes"], device_out=device_out)        # side stream, behind the decoder
+    info = {"mode": mode, "codec": codec}
+    pending = st["pending"]
     while True:
         thr2 = thr * 2.0                                                             # compress.py:129
         if verify == "full":
@@ -155,9 +190,12 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
             xhat = eng.reconstruct(recon, mask, q, mean, std, thr2)
             viol, max_err = eng.verify(x, xhat, abs_err)
         elif verify:
-            mask, q, viol, max_err = eng.quantize(x, recon, mean, std, thr, check_abs_err=abs_err)
+            if pending is None:
+                pending = eng.quantize_launch(x, recon, mean, std, thr, check_abs_err=abs_err)
+            mask, q, viol, max_err = eng.quantize_result(pending)
+            pending = None
         else:
-            mask, q = eng.quantize(x, recon, mean, std, thr)
+            mask, q = eng.quantize_result(pending)
             break
         info.update(violations=viol, max_err=max_err)
         if viol == 0 or mode != "strict" or not retry:
@@ -167,19 +205,19 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
     tm and tm.mark("quantize+verify")
     n_out = int(q.numel())
     if comp_data is None:
-        comp_data = eng.pack_latent(latent, latent_codec, staged)                    # compress.py:142-144
+        comp_data = eng.pack_latent(latent, latent_codec, st["staged"])              # compress.py:142-144
     tm and tm.mark("latent_pack")
     # compress.py:142 squeezes the latent's time axis, which is 1 after four reducing convolutions; the 3-conv
     # variant keeps its (2, 6, 6, F) bottleneck whole
     ls = tuple(eng.model.arch.latent_shape())
     lshape = (latent.shape[0],) + (ls[1:] if ls[0] == 1 else ls)
+    blob = None
     if codec == "bz2":
         dq = eng.diff(q).cpu().numpy()                                               # compress.py:147-151
         dm = eng.diff(mask).cpu().numpy()                                            # compress.py:159-163
         comp_error = bz2.compress(dq.tobytes(), 9)                                   # compress.py:156
         comp_mask = bz2.compress(dm.tobytes(), 9)                                    # compress.py:166
-    elif codec == "huff":
-        blob = None
+    else:
         if as_blob and not device_out and n_out and mask.numel():
             head = [comp_data, lshape, (T, H, W, int(x.shape[3])), (n_out,), mean, std, None, None, thr2]
             blob, (ne_b, nm_b) = eng.pack_streams(mask, q, frame=pickle_frame(head))
@@ -187,8 +225,6 @@ def compress_device(eng: Engine, x, err_threshold, *, mode="strict", codec="huff
         else:
             comp_error, comp_mask = eng.pack_streams(mask, q, device_out=device_out)
         tm and tm.mark("pack_streams")
-    else:
-        raise ValueError("codec must be 'huff' or 'bz2'")
     slots = [comp_data, lshape, (T, H, W, int(x.shape[3])), (n_out,), mean, std, comp_error, comp_mask, thr2]
     info.update(n_out=n_out, thr=thr, latent_bytes=len(comp_data), error_bytes=len(comp_error),
                 mask_bytes=len(comp_mask))

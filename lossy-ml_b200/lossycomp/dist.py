@@ -393,14 +393,23 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
     wait=False: rank `dst` gets a PendingBlob instead -- the device->host copy of the gathered parts (copy stream)
     and the assembly of the slots (host thread) then overlap the caller's next call; .result() is the slot list.
     pickled=True: the result is the finished blob (bytes, what compress() returns) instead of the slot list, written
-    with one multi-threaded copy straight from the pinned receive buffer."""
+    with one multi-threaded copy straight from the pinned receive buffer.
+
+    = compress_sharded_finish(compress_sharded_begin(...)).  begin holds the statistics exchange and everything the
+    GPU can be given without asking the host again (encoder, decoder, quantiser); finish holds the entropy stage, the
+    strict-mode verdict and the blob gather.  A caller with several fields begins the next one -- on another Engine,
+    see compress_sharded_stream -- before it finishes this one; all collectives stay in one thread and in the same
+    order on every rank."""
+    st = compress_sharded_begin(eng, x_local, err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=group)
+    return compress_sharded_finish(st, dst=dst, wait=wait, pickled=pickled)
+
+
+def compress_sharded_begin(eng, x_local, err_threshold, *, t0=None, T=None, mode="strict", codec="huff", group=None):
     import os
     import time
     import torch
     import torch.distributed as dist
-    from . import _hostio
-    from ._engine import DevPieces, _new_bytes
-    from .compress import compress_device
+    from .compress import compress_begin
     dev = eng.dev
     cdev = comm_device(dev, group)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -411,10 +420,6 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
         if tm is not None:
             torch.cuda.synchronize(dev)
             tm.append((name, time.perf_counter()))
-
-    def timing(info):
-        if tm is not None:
-            info["shard_timing_ms"] = {b[0]: (b[1] - a[1]) * 1e3 for a, b in zip(tm, tm[1:])}
     mark("start")
     if t0 is None or T is None:
         tl = torch.tensor([T_local], dtype=torch.int64, device=cdev)
@@ -427,15 +432,38 @@ def compress_sharded(eng, x_local, err_threshold, *, t0=None, T=None, mode="stri
     blocks = all_reduce_blocks(eng.stats_blocks(x_local) if T_local else None, t0 // CHUNK_T, n_blocks, group, cdev)
     mean, std, max_abs = combine_stats(blocks)
     mark("stats")
+    inner = None
+    if T_local:
+        inner = compress_begin(eng, x_local, err_threshold, mode=mode, codec=codec,
+                               inject={"mean": mean, "std": std, "max_abs": max_abs}, guard_scale=1.0)
+    return dict(eng=eng, x=x_local, err=err_threshold, mode=mode, codec=codec, group=group, T_local=T_local,
+                stats=(mean, std, max_abs), inner=inner, tm=tm, mark=mark)
+
+
+def compress_sharded_finish(st, *, dst=0, wait=True, pickled=False):
+    import torch
+    from . import _hostio
+    from ._engine import DevPieces, _new_bytes
+    from .compress import compress_begin, compress_finish
+    eng, x_local, err_threshold, mode, codec, group = st["eng"], st["x"], st["err"], st["mode"], st["codec"], st["group"]
+    T_local, (mean, std, max_abs), tm, mark = st["T_local"], st["stats"], st["tm"], st["mark"]
+    dev = eng.dev
+
+    def timing(info):
+        if tm is not None:
+            info["shard_timing_ms"] = {b[0]: (b[1] - a[1]) * 1e3 for a, b in zip(tm, tm[1:])}
     # Strict mode's verdict is collective: a rank that finds a bound violation must not widen its guard band alone
     # (the ranks would disagree on the threshold of blob slot 8).  Every rank compresses with the same guard, the
     # violation counts travel with the frame lengths, and if any is non-zero ALL ranks retry with twice the guard.
     guard_scale = 1.0
+    inner = st["inner"]
     while True:
         if T_local:
-            slots, info = compress_device(eng, x_local, err_threshold, mode=mode, codec=codec, device_out=True,
-                                          inject={"mean": mean, "std": std, "max_abs": max_abs},
-                                          guard_scale=guard_scale, retry=False)
+            if inner is None:
+                inner = compress_begin(eng, x_local, err_threshold, mode=mode, codec=codec,
+                                       inject={"mean": mean, "std": std, "max_abs": max_abs}, guard_scale=guard_scale)
+            slots, info = compress_finish(inner, device_out=True, retry=False)
+            inner = None
             for i in BIG:
                 if not isinstance(slots[i], DevPieces):
                     slots[i] = DevPieces([slots[i]])
@@ -692,27 +720,28 @@ def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=Non
                             mode="strict", codec="huff", group=None, dst=0, lanes=None):
     """Bulk-job form of compress_sharded_host: a sequence of fields (each given by this rank's rows of it, all with
     the same sharding) -> one blob per field on rank `dst` (None elsewhere), in order, each identical to the blob
-    compress_sharded_host returns.  The host->device copy of the next field runs on a copy stream, consecutive fields
-    run in alternating lanes (lossycomp.lanes; every lane has its own process group, so the collectives of two
-    fields in flight stay in the same order on every rank), and the gathered blob of a field reaches the host (copy
-    stream + host thread) behind the kernels of the fields after it."""
+    compress_sharded_host returns.
+
+    Software pipeline in ONE host thread: field k+1 is begun (statistics exchange, encoder, decoder, quantiser
+    enqueued on its own engine and stream) before field k is finished (outlier count, verdict, Huffman tables, blob
+    gather), so the host round trips of field k run behind the convolutions of field k+1; the host->device copy of
+    the next field runs on a copy stream and the gathered blob reaches the host (copy stream + host thread) behind
+    the fields after it.  Consecutive fields alternate between `lanes` engines (default 2, LOSSYCOMP_SHARD_LANES;
+    lossycomp.lanes provides the engines, their streams and the turn-taking of the autoencoder passes, not threads):
+    all collectives are issued by this thread, in the same order on every rank, on one communicator."""
     from collections import deque
     import torch.distributed as dist
     from . import _hostio
     from . import _native as N
     from .lanes import LaneSet
     torch = N.require_cuda()
-    # One lane unless asked for more.  With NCCL, two lanes put collectives of two communicators in flight from two
-    # threads; a device-wide synchronisation inside one thread (a pinned or device allocation that misses the caches)
-    # then waits for the other lane's NCCL kernel, which waits for the peer rank, whose thread may be in the mirror
-    # situation -- observed as a hang on 2 GPUs.  The single-GPU entry points default to two lanes.
     if lanes is None:
-        lanes = int(os.environ.get("LOSSYCOMP_SHARD_LANES", "1"))
-    ls = LaneSet.get(model, precision, device, lanes).groups(group)
+        lanes = int(os.environ.get("LOSSYCOMP_SHARD_LANES", "2"))
+    ls = LaneSet.get(model, precision, device, lanes)
     eng = ls.lanes[0].eng
     copy = torch.cuda.Stream(device=eng.dev)
     is_dst = dist.get_rank(group) == dst
-    nbuf = len(ls) + 1
+    nbuf = len(ls) + 2                    # one field uploading ahead, one begun per lane, one being finished
     bufs = [None] * nbuf
 
     def upload(slot, array):
@@ -725,6 +754,7 @@ def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=Non
             return torch.empty(array.shape, dtype=torch.float32, device=eng.dev), None, None
         if not src.is_pinned():
             return _hostio.h2d(eng, array), None, None
+        # the field that read this buffer nbuf fields ago has been finished (at most len(ls) fields are open)
         if bufs[slot] is None or bufs[slot].shape != src.shape:
             bufs[slot] = torch.empty(src.shape, dtype=torch.float32, device=eng.dev)
         with torch.cuda.stream(copy):
@@ -733,27 +763,41 @@ def compress_sharded_stream(arrays_local, err_threshold, *, t0, T, precision=Non
             ev.record(copy)
         return bufs[slot], ev, src
 
-    def job(lane, x, ev, _keep):
-        if ev is not None:
-            lane.stream.wait_event(ev)
-        pend, _ = compress_sharded(lane.eng, x, err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=lane.group,
-                                   dst=dst, wait=False, pickled=True)
-        # the lane's kernels are done with x once its stream is drained (the next upload into this buffer is only
-        # issued after this job has been collected)
-        torch.cuda.current_stream(lane.eng.dev).synchronize()
+    def finish(lane, st, _keep):
+        with torch.cuda.stream(lane.stream):
+            pend, _ = compress_sharded_finish(st, dst=dst, wait=False, pickled=True)
+            # this rank's kernels are done with the field's input once the lane's stream is drained
+            torch.cuda.current_stream(eng.dev).synchronize()
         return pend
 
-    def collect(fut):
-        pend = fut.result()
-        return pend.result() if is_dst else None
-
-    inflight = deque()
-    for k, array in enumerate(arrays_local):
-        inflight.append(ls.submit(job, *upload(k % nbuf, array)))
-        while len(inflight) > len(ls):
-            yield collect(inflight.popleft())
-    while inflight:
-        yield collect(inflight.popleft())
+    # The upload runs one field ahead of the pipeline: begin() needs the host for the statistics exchange, and with
+    # the field's own upload still on the bus that wait would stall this thread for the whole transfer.
+    open_fields, pending = deque(), deque()
+    it = iter(arrays_local)
+    first = next(it, None)
+    ahead = upload(0, first) if first is not None else None
+    k = 0
+    while ahead is not None:
+        x, ev, keep = ahead
+        nxt = next(it, None)
+        ahead = upload((k + 1) % nbuf, nxt) if nxt is not None else None
+        lane = ls.lanes[k % len(ls)]
+        with torch.cuda.stream(lane.stream):
+            if ev is not None:
+                lane.stream.wait_event(ev)
+            st = compress_sharded_begin(lane.eng, x, err_threshold, t0=t0, T=T, mode=mode, codec=codec, group=group)
+        open_fields.append((lane, st, keep))
+        while len(open_fields) > len(ls) - 1:        # two lanes: field k is begun, now field k-1 is finished
+            pending.append(finish(*open_fields.popleft()))
+        while len(pending) > 1:
+            p0 = pending.popleft()
+            yield p0.result() if is_dst else None
+        k += 1
+    while open_fields:
+        pending.append(finish(*open_fields.popleft()))
+    while pending:
+        p0 = pending.popleft()
+        yield p0.result() if is_dst else None
 
 
 def decompress_sharded_host(blob_or_none, *, precision=None, model=None, device=None, group=None, src=0):
