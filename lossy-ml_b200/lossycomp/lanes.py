@@ -7,8 +7,11 @@ workspace, staging buffers), a CUDA stream and one host thread; consecutive fiel
 kernels of one field fill the host gaps of the other.  Nothing is shared between lanes, every field is still
 compressed by exactly the single-lane code, and the blobs are identical (tests/test_gpu_lanes.py).
 
-Time-sharded fields (lossycomp.dist) run in lanes too: every lane owns a process group, so the collectives of two
-fields in flight never share a communicator and each communicator sees its calls in the same order on every rank.
+Time-sharded fields (lossycomp.dist) use the engines, streams and turn-taking of a LaneSet but NOT its threads: one
+thread begins field k+1 on the other engine and then finishes field k (dist.compress_sharded_stream), so every
+collective has one issuer and one order on every rank.  Lane threads with a process group each (LaneSet.groups())
+deadlocked over NCCL: a device-synchronising call made with the GIL held waits for the other thread's NCCL kernel,
+which waits for the peer rank, whose other thread is kept from launching the matching call by the same situation.
 """
 from __future__ import annotations
 
@@ -109,7 +112,8 @@ class LaneSet:
     def groups(self, group=None):
         """Give every lane its own process group over the ranks of `group` (collective: every rank must call it, in
         the same order).  The communicators are created and used once here, one after the other, so that no two
-        threads ever initialise NCCL at the same time."""
+        threads ever initialise NCCL at the same time.  For experiments with threaded lanes over gloo; over NCCL see
+        the module docstring -- the sharded codec does not use this."""
         import torch.distributed as dist
         key = id(group) if group is not None else None
         if self._groups_of is not None and self._groups_of[0] == key:
