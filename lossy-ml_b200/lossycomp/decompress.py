@@ -145,7 +145,13 @@ def decompress_stream(blobs, *, precision=None, model=None, device=None, lanes=N
         if ls is None:
             precision, model = p, m
             ls = LaneSet.get(model, precision, device, lanes)
-        inflight.append(ls.submit(job, slots, next(outs) if outs is not None else None))
+        out = None
+        if outs is not None:
+            try:
+                out = next(outs)
+            except StopIteration:
+                raise ValueError("decompress_stream: fewer `outs` arrays than blobs") from None
+        inflight.append(ls.submit(job, slots, out))
         while len(inflight) > len(ls):
             yield inflight.popleft().result()
     while inflight:
