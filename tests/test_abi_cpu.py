@@ -195,3 +195,24 @@ def test_coordinate_encodings_match_reference_values():
     assert x.shape == (2, 3, 4, 5) and x.dtype == np.float32 and np.array_equal(x[..., 0], d)
     assert np.allclose(x[1, 2, :, 1], 0.8638355052043957) and np.allclose(x[0, 2, :, 2], 0.5037739770455263)   # sin/cos(lat)
     assert np.allclose(x[0, :, 1, 3], 0.9832549075639545) and np.allclose(x[1, :, 1, 4], 0.18223552549214767)   # sin/cos(lon)
+
+
+def test_stream_and_pipeline_entry_points_exist():
+    """The bulk-job API of this package (no counterpart in the reference): stream generators, the begin / finish
+    halves the pipelines are built from, and the lane set -- importable without a GPU, with the keyword surface the
+    docs name."""
+    import inspect
+    from lossycomp import compress as Cm, decompress as Dm, dist as Di, lanes as La
+    assert inspect.isgeneratorfunction(Cm.compress_stream) and inspect.isgeneratorfunction(Dm.decompress_stream)
+    assert inspect.isgeneratorfunction(Di.compress_sharded_stream)
+    assert "lanes" in inspect.signature(Cm.compress_stream).parameters
+    assert {"lanes", "outs"} <= set(inspect.signature(Dm.decompress_stream).parameters)
+    assert {"t0", "T", "dst", "lanes", "group"} <= set(inspect.signature(Di.compress_sharded_stream).parameters)
+    for fn in (Cm.compress_begin, Cm.compress_finish, Di.compress_sharded_begin, Di.compress_sharded_finish):
+        assert callable(fn)
+    # compress_device(...) == compress_finish(compress_begin(...)): the halves take the whole's keywords between them
+    whole = set(inspect.signature(Cm.compress_device).parameters) - {"eng", "x", "err_threshold"}
+    halves = (set(inspect.signature(Cm.compress_begin).parameters) | set(inspect.signature(Cm.compress_finish).parameters)) \
+        - {"eng", "x", "err_threshold", "st"}
+    assert whole == halves, (whole ^ halves)
+    assert La.n_lanes(3) == 3 and La.n_lanes(0) == 1
